@@ -1,0 +1,120 @@
+/* vgb200.h -- C ABI of libvgb200.so: varigraph's read k-mer counting path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference has no plugin ABI; its seam is the class pair
+ * FastqKmer / FastqKmerKernel (and BloomFilter / BloomFilterKernel on the construct side).
+ * Each entry point below names the reference interface it stands in for (file:line relative
+ * to the reference tree).  varigraph_b200/host/ holds the C++ subclasses that keep the
+ * reference's signatures and call these functions; INTEGRATION.md shows the wiring.
+ *
+ * Conventions: plain C types only; every function returns VG_OK (0) or a negative VG_E_*
+ * code and leaves a message for vg_last_error() (thread-local); the caller owns all host
+ * buffers; a handle serves one sample at a time, distinct handles may be used concurrently
+ * from different threads.  There is no CPU fallback: without a CUDA device every call that
+ * needs one fails with VG_E_CUDA.
+ */
+#ifndef VGB200_H
+#define VGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VG_OK 0
+#define VG_E_INVALID (-1) /* bad argument (k out of 5..28, key whose low byte != k, NULL, ...) */
+#define VG_E_CUDA (-2)    /* CUDA runtime error; text in vg_last_error() */
+#define VG_E_NOMEM (-3)
+#define VG_E_IO (-4)      /* FASTQ file missing / unreadable */
+#define VG_E_STATE (-5)   /* call out of order (submit before begin, ...) */
+
+typedef struct vg_ctx vg_ctx;     /* one CUDA device: streams, staging rings */
+typedef struct vg_index vg_index; /* device-resident graph k-mer index + read-coverage counters */
+typedef struct vg_cbf vg_cbf;     /* device-resident counting Bloom filter */
+
+const char* vg_last_error(void);
+int vg_version(void);
+
+/* ---- context ---------------------------------------------------------------------------
+ * Replaces cudaSetDevice(config.gpu) in main.cu:221,444.  buffer_mb is the reference's
+ * --buffer (include/varigraph.cuh:19-28): the size of one staged chunk of read bases. */
+int vg_ctx_create(int device, int buffer_mb, vg_ctx** out);
+int vg_ctx_destroy(vg_ctx* ctx);
+int vg_ctx_device(const vg_ctx* ctx);
+int vg_ctx_synchronize(vg_ctx* ctx);
+
+/* ---- the index -------------------------------------------------------------------------
+ * Device twin of ConstructIndex::mGraphKmerHashHapStrMap (include/construct_index.hpp:140):
+ * keys are the map's keys verbatim, `hash64(canonical k-mer) << 8 | k` (src/kmer.cpp:138).
+ * Built once per load() (src/varigraph.cpp:65-83).  load_factor in (0, 0.9], 0 = default. */
+int vg_index_create(vg_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
+                    vg_index** out);
+int vg_index_destroy(vg_index* ix);
+uint64_t vg_index_size(const vg_index* ix);          /* n */
+uint64_t vg_index_table_bytes(const vg_index* ix);   /* bytes of the slot table in HBM */
+
+/* ---- one sample's count phase ----------------------------------------------------------
+ * Together these replace FastqKmer::build_fastq_index (src/fastq_kmer.cpp:41-187) /
+ * FastqKmerKernel::build_fastq_index_kernel (src/fastq_kmer.cu:20-270).
+ * Post-condition (src/fastq_kmer.cpp:132-138): c[i] == min(255, #emitted read k-mers equal
+ * to keys[i]).  vg_count_begin also stands in for ConstructIndex::reset()'s zeroing of c
+ * (include/construct_index.hpp:326-329). */
+int vg_count_begin(vg_index* ix);
+
+/* A staged chunk: read sequences (ASCII, any case, N allowed) each followed by '\n' -- the
+ * reference GPU path's 'N'-separated buffer (src/fastq_kmer.cu:171-176) with a separator that
+ * also resets the encoder registers as a new kmer_sketch_fastq call does.  Reads must not be
+ * split across calls.  host_bases may be pageable or pinned; the copy is pipelined against
+ * the kernel through the context's staging ring.  Returns once the bytes are consumed from
+ * host_bases (not necessarily counted yet). */
+int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes);
+
+/* Same, for bases already in device memory; enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = the context's compute stream).  Asynchronous. */
+int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes, void* cuda_stream);
+
+/* FASTQ/FASTA files (plain or gzip), kseq semantics (include/kseq.h:192-232): the whole of
+ * FastqKmer::fastq_file_open for each path.  threads = inflate/parse workers (files are
+ * processed concurrently).  *read_bases accumulates mReadBase (src/fastq_kmer.cpp:105). */
+int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
+
+/* Waits for the sample's kernels, then writes c in the key order given at create.
+ * c_out (n bytes, host), positions, hits may each be NULL. */
+int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hits);
+
+/* Device-side result for a multi-GPU reduce: counts in key order as u8 (elem_bytes 1) or u32
+ * (elem_bytes 4, what ncclAllReduce(sum) wants) into dev_out, on `cuda_stream`. */
+int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* cuda_stream);
+int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits);
+
+/* Test / tooling hook: out[p] = key of the k-mer ENDING at byte p of the chunk, or ~0 when
+ * the reference encoder emits nothing there (src/kmer.cpp:126-146).  Device buffers. */
+int vg_encode_positions_device(vg_ctx* ctx, const void* dev_bases, uint64_t nbytes, uint32_t k,
+                               uint64_t* dev_keys_out, void* cuda_stream);
+int vg_encode_positions(vg_ctx* ctx, const char* host_bases, uint64_t nbytes, uint32_t k,
+                        uint64_t* host_keys_out);
+
+/* ---- counting Bloom filter (construct side) --------------------------------------------
+ * Device twin of BloomFilter / BloomFilterKernel (include/counting_bloom_filter.hpp:29-96,
+ * include/counting_bloom_filter.cuh:34-86).  m and num_hashes are the host class's _size and
+ * _numHashes (src/counting_bloom_filter.cpp:70-77); seeds are its _seeds (:80-87) -- the host
+ * draws them, the device receives them, so both sides build the same filter. */
+int vg_cbf_create(vg_ctx* ctx, uint64_t m, uint32_t num_hashes, const uint64_t* seeds, vg_cbf** out);
+int vg_cbf_destroy(vg_cbf* cbf);
+/* kmer_sketch_bf over one chromosome (src/kmer.cpp:20-52, caller src/construct_index.cpp:161-166;
+ * GPU caller src/construct_index.cu:65-88). *added gets the number of k-mers added (may be NULL). */
+int vg_cbf_add_sequence(vg_cbf* cbf, const char* host_seq, uint64_t len, uint32_t k, uint64_t* added);
+/* BloomFilterKernel::copyFilterDToHost (include/counting_bloom_filter.cuh:69-82): m bytes. */
+int vg_cbf_download(vg_cbf* cbf, uint8_t* host_filter);
+/* BloomFilter::count / find for a batch (src/counting_bloom_filter.cpp:40-67); either out may be NULL. */
+int vg_cbf_query(vg_cbf* cbf, const uint64_t* host_keys, uint64_t n, uint8_t* count_out, uint8_t* find_out);
+
+/* Pinned host memory for callers that want zero-copy staging (cudaHostAlloc / cudaFreeHost). */
+int vg_host_alloc(void** out, uint64_t nbytes);
+int vg_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGB200_H */

@@ -1,0 +1,355 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+Bit-exact everywhere: this path is integer / byte work, there is no tolerance."""
+import gzip
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import helpers
+from varigraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+NOKMER = helpers.NOKMER
+
+
+def _rand_lines(rng, nreads, alpha="ACGT", lo=1, hi=260):
+    reads = ["".join(rng.choice(alpha) for _ in range(rng.randint(lo, hi))) for _ in range(nreads)]
+    return ("\n".join(reads) + "\n").encode()
+
+
+# ---- K1: the encoder ----------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [5, 11, 21, 27])
+def test_encoder_odd_k_matches_oracle(ctx, oracle, k):
+    rng = random.Random(k)
+    for alpha in ("ACGT", "ACGTNacgtnU", "AT", "ACGTN\r\x00\x01\x02\x03xyz"):
+        buf = _rand_lines(rng, 300, alpha)
+        got = ctx.encode_positions(buf, k)
+        assert np.array_equal(got, oracle.positions(buf, k)), (k, alpha)
+
+
+@pytest.mark.parametrize("k", [4, 6, 8, 16, 28])
+def test_encoder_even_k_matches_oracle(ctx, oracle, k):
+    """Even k: palindromes skip without advancing the run; registers survive N."""
+    rng = random.Random(100 + k)
+    for alpha in ("ACGT", "AT", "ACGTN", "GC", "ACGTNacgtnU"):
+        buf = _rand_lines(rng, 200, alpha)
+        got = ctx.encode_positions(buf, k)
+        want = oracle.positions(buf, k)
+        assert np.array_equal(got, want), (k, alpha, int((got != want).sum()))
+    adversarial = b"ACGNTACGTA\n" + b"AT" * 40 + b"N" + b"TA" * 33 + b"\n" + b"ACGTTGCA" * 9 + b"NN" + b"TGCAACGT" * 9
+    assert np.array_equal(ctx.encode_positions(adversarial, k), oracle.positions(adversarial, k))
+
+
+def test_encoder_golden_edge_cases(ctx):
+    """Every (seq, k) edge case recorded from the reference itself in tests/golden/primitives.json
+    (lower case, U, N runs, CR, bytes 0x00-0x03 which seq_nt4_table maps to 0-3, short reads)."""
+    n = 0
+    for c in helpers.primitives()["sketch"]:
+        seq = c["seq"].encode("latin1")
+        assert b"\n" not in seq
+        got = ctx.encode_positions(seq, c["k"])
+        assert [str(int(x)) for x in got[got != NOKMER]] == c["keys"], (c["k"], c["seq"])
+        n += 1
+    assert n > 400
+
+
+def test_encoder_alignment_and_tails(ctx, oracle):
+    """Device pointers at every 16-byte phase and lengths around tile edges."""
+    import torch
+    rng = random.Random(5)
+    raw = _rand_lines(rng, 120, "ACGTN", 100, 160)
+    host = np.frombuffer(raw, dtype=np.uint8)
+    k = 27
+    for phase in (0, 1, 7, 15, 16, 33):
+        for n in (1, 26, 27, 28, 4095, 4096, 4097, 8191, len(raw) - phase - 64):
+            n = min(n, len(raw) - phase)
+            dev = torch.zeros(len(raw) + 64, dtype=torch.uint8, device="cuda")
+            dev[phase:phase + n] = torch.from_numpy(host[:n].copy()).cuda()
+            out = torch.empty(n, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            ctx.encode_positions_device(dev.data_ptr() + phase, n, k, out.data_ptr())
+            ctx.synchronize()
+            got = out.cpu().numpy().view(np.uint64)
+            assert np.array_equal(got, oracle.positions(host[:n], k)), (phase, n)
+
+
+# ---- K1+K2+K3: counting ------------------------------------------------------------------------
+def test_count_golden_tiny(ctx, vglib):
+    """T1: per-k-mer counts equal FastqKmer::build_fastq_index on the reference-built graph."""
+    t = helpers.tiny()
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    ix.begin()
+    ix.submit(t["lines"])
+    counts, positions, hits = ix.end()
+    assert np.array_equal(counts, t["counts"])
+    assert hits == int(t["counts"].astype(np.int64).sum())
+    # a second sample on the same handle starts from zero (ConstructIndex::reset)
+    ix.begin()
+    ix.submit(t["lines"][: t["lines"].size // 2 // 151 * 151])
+    half, _, _ = ix.end()
+    assert int(half.astype(np.int64).sum()) < hits and half.max() <= counts.max()
+    ix.close()
+
+
+@pytest.mark.parametrize("k,load", [(27, 0.0), (27, 0.85), (21, 0.3), (28, 0.0), (16, 0.5), (5, 0.0)])
+def test_count_random_vs_oracle(ctx, vglib, oracle, k, load):
+    g = synth.make_genome(120_000, seed=k)
+    lines = synth.random_reads_lines(6000, 150, g, seed=k + 1)
+    pos = oracle.positions(g[:50_000], k)
+    keys = np.unique(pos[pos != NOKMER])
+    rng = np.random.default_rng(k)
+    rng.shuffle(keys)
+    ix = vglib.Index(ctx, keys, k, load)
+    ix.begin()
+    ix.submit(lines)
+    counts, positions, hits = ix.end()
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    assert (positions, hits) == (wpos, whits)
+    assert np.array_equal(counts, want)
+    ix.close()
+
+
+def test_count_saturates_at_255(ctx, vglib, oracle):
+    """c = min(255, occurrences): hot k-mers, including many identical reads inside one warp."""
+    k = 27
+    g = synth.make_genome(3000, seed=9)
+    read = g[100:250].tobytes()
+    repeat = (b"AC" * 75)
+    buf = (read + b"\n") * 700 + (repeat + b"\n") * 40 + (g[500:650].tobytes() + b"\n") * 254
+    pos = oracle.positions(buf, k)
+    keys = np.unique(pos[pos != NOKMER])
+    ix = vglib.Index(ctx, keys, k)
+    ix.begin()
+    ix.submit(buf)
+    counts, positions, hits = ix.end()
+    want, wpos, whits = oracle.count_lines(keys, buf, k)
+    assert counts.max() == 255 and (counts == 254).any()
+    assert np.array_equal(counts, want) and (positions, hits) == (wpos, whits)
+    ix.close()
+
+
+def test_count_chunking_invariance(ctx, vglib, oracle):
+    """Splitting the sample into many submits (and device submits) never changes a count."""
+    import torch
+    t = helpers.tiny()
+    lines = t["lines"]
+    L = 151
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    ix.begin()
+    cuts = [0, L, 5 * L, 1000 * L, 1001 * L, lines.size // L // 2 * L, lines.size]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if (a // L) % 2:
+            dev = torch.from_numpy(lines[a:b].copy()).cuda()
+            ix.submit_device(dev.data_ptr(), b - a, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        else:
+            ix.submit(lines[a:b])
+    counts, _, _ = ix.end()
+    assert np.array_equal(counts, t["counts"])
+    ix.close()
+
+
+def test_count_k28_all_ones_hash(ctx, vglib, oracle):
+    """k = 28: the one hash value (2^56-1) a table slot cannot hold is counted beside the table."""
+    k = 28
+    mask = (1 << 56) - 1
+    # invert hash64 by brute force over the oracle is impossible; craft the key set instead so the
+    # special key is present but never hit, and check ordinary keys around it are unaffected.
+    g = synth.make_genome(30_000, seed=4)
+    lines = synth.random_reads_lines(1500, 150, g, seed=8)
+    pos = oracle.positions(g, k)
+    keys = np.unique(pos[pos != NOKMER])
+    special = np.uint64((mask << 8) | k)
+    keys = np.concatenate([keys[:100], [special], keys[100:]])
+    ix = vglib.Index(ctx, keys, k)
+    ix.begin()
+    ix.submit(lines)
+    counts, positions, hits = ix.end()
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    assert np.array_equal(counts, want) and counts[100] == 0 and (positions, hits) == (wpos, whits)
+    ix.close()
+
+
+def test_count_empty_and_ragged(ctx, vglib, oracle):
+    k = 27
+    g = synth.make_genome(5000, seed=2)
+    pos = oracle.positions(g, k)
+    keys = np.unique(pos[pos != NOKMER])
+    ix = vglib.Index(ctx, keys, k)
+    for buf in (b"", b"\n", b"\n\n\n", b"ACGT\n", g[:26].tobytes(), g[:27].tobytes(),
+                g[:27].tobytes() + b"\n" + g[10:36].tobytes() + b"\n\n" + g[40:4000].tobytes()):
+        ix.begin()
+        if buf:
+            ix.submit(buf)
+        counts, positions, hits = ix.end()
+        want, wpos, whits = oracle.count_lines(keys, buf, k)
+        assert np.array_equal(counts, want) and (positions, hits) == (wpos, whits), buf[:40]
+    ix.close()
+    empty = vglib.Index(ctx, np.zeros(0, np.uint64), k)
+    empty.begin()
+    empty.submit(g.tobytes())
+    counts, positions, hits = empty.end()
+    assert counts.size == 0 and hits == 0 and positions == len(g) - k + 1
+    empty.close()
+
+
+def test_index_rejects_bad_keys(ctx, vglib):
+    with pytest.raises(vglib.VgError) as ei:
+        vglib.Index(ctx, np.array([(5 << 8) | 26], dtype=np.uint64), 27)
+    assert ei.value.code == vglib.VG_E_INVALID
+    with pytest.raises(vglib.VgError):
+        vglib.Index(ctx, np.array([27], dtype=np.uint64), 29)
+    ix = vglib.Index(ctx, np.array([(5 << 8) | 27], dtype=np.uint64), 27)
+    with pytest.raises(vglib.VgError) as ei:
+        ix.submit(b"ACGT\n")  # before begin
+    assert ei.value.code == vglib.VG_E_STATE
+    ix.close()
+
+
+# ---- the file-level entry point (FastqKmerKernel::build_fastq_index_kernel) ----------------------
+@pytest.mark.parametrize("gz", [True, False])
+def test_count_files_golden_tiny(ctx, vglib, tmp_path, gz):
+    t = helpers.tiny()
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t, gz=gz)
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    fk = vglib.FastqKmerKernel(ix, [f1, f2], t["k"], threads=2, buffer=1)
+    fk.build_fastq_index_kernel()
+    assert fk.mReadBase == t["read_bases"]
+    assert np.array_equal(fk.c, t["counts"])
+    ix.close()
+
+
+def test_count_files_kseq_edge_cases(ctx, vglib, oracle, tmp_path):
+    t = helpers.tiny()
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    body = t["m1"][:50]
+    for name, text in helpers.EDGE_FASTQS.items():
+        s0 = body[0].tobytes()
+        extra = b"@x\n%s\n+\n%s\n" % (s0, b"I" * len(s0))
+        data = extra + text + (b"" if name == "no_final_newline" else extra)
+        p = tmp_path / (name + ".fq")
+        p.write_bytes(data)
+        ix.begin()
+        rb = ix.count_files([str(p)], threads=1)
+        counts, _, _ = ix.end()
+        lines, nreads, bases, status = oracle.fastq_to_lines(data)
+        want, _, _ = oracle.count_lines(t["keys"], lines, t["k"])
+        assert rb == bases and np.array_equal(counts, want), name
+    ix.begin()
+    with pytest.raises(vglib.VgError) as ei:
+        ix.count_files([str(tmp_path / "does_not_exist.fq.gz")])
+    assert ei.value.code == vglib.VG_E_IO and "No such file or directory" in str(ei.value)
+    ix.end()
+    ix.close()
+
+
+def test_count_files_vs_reference_live(ctx, vglib, reference, tmp_path):
+    """Same graph.bin, same FASTQ files: reference CPU path vs CUDA path, per k-mer."""
+    t = helpers.tiny()
+    graph = tmp_path / "graph.bin"
+    graph.write_bytes(t["graph_bin"])
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    h, keys, k = reference.graph_load(str(graph))
+    try:
+        ref_counts, ref_bases, _ = reference.count_files(h, keys.size, [f1, f2], threads=4)
+    finally:
+        reference.graph_destroy(h)
+    ix = vglib.Index(ctx, keys, k)
+    ix.begin()
+    rb = ix.count_files([f1, f2], threads=2)
+    counts, _, _ = ix.end()
+    assert rb == ref_bases and np.array_equal(counts, ref_counts)
+    ix.close()
+
+
+# ---- K4 / K5: counting Bloom filter --------------------------------------------------------------
+def test_cbf_golden(ctx, vglib, oracle):
+    g = helpers.cbf_golden()
+    m, k = int(g["m"]), int(g["k"])
+    cbf = vglib.CountingBloom(ctx, m, g["seeds"])
+    added = cbf.add_sequence(g["genome"], k)
+    filt = cbf.download()
+    assert np.array_equal(filt, g["filter"])
+    pos = oracle.positions(g["genome"], k)
+    assert added == int((pos != NOKMER).sum())
+    cnt, fnd = cbf.query(g["probe"])
+    assert np.array_equal(cnt, g["probe_count"]) and np.array_equal(fnd, g["probe_find"])
+    cbf.close()
+
+
+@pytest.mark.parametrize("k", [27, 21, 28, 16])
+def test_cbf_vs_oracle_multi_chromosome(ctx, vglib, oracle, k):
+    rng = np.random.default_rng(k)
+    chroms = [synth.make_genome(n, seed=k * 10 + i) for i, n in enumerate((70_000, 4097, 30, 150_001))]
+    chroms[0][1000:1100] = ord("N")
+    chroms[3][5000:9000] = chroms[0][2000:6000]
+    n = sum(len(c) for c in chroms) - k + 1
+    m = int(oracle.lib.vgo_cbf_size(n, 0.01))
+    seeds = rng.integers(1, 2**63, size=7, dtype=np.uint64)
+    cbf = vglib.CountingBloom(ctx, m, seeds)
+    want = np.zeros(m, dtype=np.uint8)
+    total = 0
+    for c in chroms:
+        added = cbf.add_sequence(c, k)
+        want, nn = oracle.cbf_fill(m, seeds, c, k, want)
+        assert added == nn
+        total += nn
+    assert np.array_equal(cbf.download(), want)
+    probe = oracle.positions(chroms[0][:3000], k)
+    probe = probe[probe != NOKMER][:500]
+    probe = np.concatenate([probe, rng.integers(0, 2**54, size=100, dtype=np.uint64) << np.uint64(8) | np.uint64(k)])
+    cnt, fnd = cbf.query(probe)
+    assert [oracle.cbf_count(want, m, seeds, x) for x in probe] == cnt.tolist()
+    assert [oracle.cbf_find(want, m, seeds, x) for x in probe] == fnd.tolist()
+    cbf.close()
+
+
+# ---- full-size properties (no oracle at this size) -----------------------------------------------
+def test_full_size_properties(vglib):
+    """At bench scale the oracle is too slow; use properties that must hold at any size:
+    (1) counting is order/chunk independent, (2) counting the sample twice gives min(255, 2c),
+    (3) sum of counts == hits when nothing saturates, (4) a sampled slice agrees with the oracle."""
+    import torch
+    from tests import oracle_binding as ob
+    k = 27
+    c = vglib.Context(0, buffer_mb=32)
+    g = synth.make_genome(8_000_000, seed=77)
+    dev_g = torch.from_numpy(g).cuda()
+    allk = torch.empty(g.size, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    c.encode_positions_device(dev_g.data_ptr(), g.size, k, allk.data_ptr())
+    c.synchronize()
+    sel = allk[: g.size // 2]
+    keys = torch.unique(sel[sel != -1]).cpu().numpy().view(np.uint64)
+    lines = synth.random_reads_lines(400_000, 150, g, seed=78)  # 60 Mb of reads, ~7.5x
+    ix = vglib.Index(c, keys, k)
+    ix.begin()
+    ix.submit(lines)
+    c1, pos1, hit1 = ix.end()
+    ix.begin()
+    perm = np.random.default_rng(1).permutation(400_000)
+    shuffled = lines.reshape(-1, 151)[perm].reshape(-1)
+    third = (400_000 // 3) * 151
+    ix.submit(shuffled[:third])
+    dev = torch.from_numpy(shuffled[third:].copy()).cuda()
+    ix.submit_device(dev.data_ptr(), dev.numel(), torch.cuda.current_stream().cuda_stream)
+    c2, pos2, hit2 = ix.end()
+    assert np.array_equal(c1, c2) and (pos1, hit1) == (pos2, hit2)
+    assert c1.max() < 255 and int(c1.astype(np.int64).sum()) == hit1
+    ix.begin()
+    ix.submit(lines)
+    ix.submit(shuffled)
+    c3, pos3, hit3 = ix.end()
+    assert np.array_equal(c3, np.minimum(255, 2 * c1.astype(np.int32)).astype(np.uint8)) and pos3 == 2 * pos1
+    # sampled oracle check: 20k reads against the full index
+    orc = ob.Oracle()
+    sub = lines[: 20_000 * 151]
+    ix.begin()
+    ix.submit(sub)
+    cs, ps, hs = ix.end()
+    want, wp, wh = orc.count_lines(keys, sub, k)
+    assert np.array_equal(cs, want) and (ps, hs) == (wp, wh)
+    ix.close()
+    c.close()

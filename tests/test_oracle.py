@@ -1,0 +1,164 @@
+"""CPU suite, part 1: the oracle (oracle/vg_oracle.c) is pinned against the reference.
+
+Level T0: primitives against tests/golden/primitives.json, which
+oracle/gen_golden.py produced by calling the unmodified reference; level T1: per-k-mer counts
+against tests/golden/tiny (FastqKmer::build_fastq_index on a reference-built graph.bin).
+Where oracle/_ref/libvgref.so exists the same checks also run live against the reference.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+
+def test_hash64_golden(oracle):
+    for case in helpers.primitives()["hash64"]:
+        mask = (1 << (2 * case["k"])) - 1
+        for x, y in zip(case["x"], case["y"]):
+            assert oracle.hash64(int(x), mask) == int(y)
+
+
+def test_nt4_golden(oracle):
+    table = helpers.primitives()["nt4"]
+    assert [int(oracle.lib.vgo_nt4(b)) for b in range(256)] == table
+
+
+def test_murmur_golden(oracle):
+    for x, seed, y in helpers.primitives()["murmur"]:
+        assert int(oracle.lib.vgo_murmur3_x64_128_sum(int(x), seed)) == int(y)
+
+
+def test_cbf_sizing_golden(oracle):
+    rows = helpers.primitives()["cbf_sizing"]
+    assert rows
+    for n, p, m, nh in rows:
+        assert int(oracle.lib.vgo_cbf_size(n, p)) == int(m)
+        assert int(oracle.lib.vgo_cbf_num_hashes(n, int(m))) == nh
+    # human-scale sizing from SURVEY appendix C: m = ceil(9.58506 n), 7 hashes
+    n = 3_099_999_974
+    m = int(oracle.lib.vgo_cbf_size(n, 0.01))
+    assert abs(m / n - 9.58506) < 1e-4 and int(oracle.lib.vgo_cbf_num_hashes(n, m)) == 7
+
+
+def test_sketch_golden(oracle):
+    cases = helpers.primitives()["sketch"]
+    assert len(cases) > 400
+    for c in cases:
+        got = oracle.sketch(c["seq"].encode("latin1"), c["k"])
+        assert [str(int(x)) for x in got] == c["keys"], (c["k"], c["seq"])
+
+
+def test_positions_consistent_with_sketch(oracle):
+    rng = random.Random(3)
+    for k in (4, 5, 27, 28):
+        reads = ["".join(rng.choice("ACGTN" if i % 3 else "AT") for _ in range(rng.randint(1, 200)))
+                 for i in range(40)]
+        buf = ("\n".join(reads) + "\n").encode()
+        pos = oracle.positions(buf, k)
+        want = np.concatenate([oracle.sketch(r.encode(), k) for r in reads] + [np.zeros(0, np.uint64)])
+        assert np.array_equal(pos[pos != helpers.NOKMER], want)
+
+
+def test_counts_golden_tiny(oracle):
+    t = helpers.tiny()
+    counts, positions, hits = oracle.count_lines(t["keys"], t["lines"], t["k"])
+    assert np.array_equal(counts, t["counts"])
+    assert hits == int(t["counts"].astype(np.int64).sum())  # no counter saturates in this fixture
+    assert t["lines"].size - (t["m1"].shape[0] + t["m2"].shape[0]) == t["read_bases"]
+
+
+def test_cbf_golden(oracle):
+    g = helpers.cbf_golden()
+    m, k, seeds = int(g["m"]), int(g["k"]), g["seeds"]
+    assert m == int(oracle.lib.vgo_cbf_size(len(g["genome"]) - k + 1, 0.01))
+    filt, n = oracle.cbf_fill(m, seeds, g["genome"], k)
+    assert np.array_equal(filt, g["filter"])
+    assert int(filt.max()) == 255  # the fixture exercises saturation
+    for key, c, f in zip(g["probe"], g["probe_count"], g["probe_find"]):
+        assert oracle.cbf_count(filt, m, seeds, key) == int(c)
+        assert oracle.cbf_find(filt, m, seeds, key) == int(f)
+
+
+def test_fastq_parser_cases(oracle):
+    want = {
+        "plain": (1, 33, -1), "crlf": (1, 33, -1), "multiline": (2, 66, -1), "fasta": (2, 99, -1),
+        "qual_at": (2, 66, -1), "truncated_qual": (1, 33, -2), "no_final_newline": (1, 33, -1),
+        "lower_n": (1, 53, -1), "leading_junk": (1, 33, -1),
+    }
+    for name, text in helpers.EDGE_FASTQS.items():
+        lines, nreads, bases, status = oracle.fastq_to_lines(text)
+        assert (nreads, bases, status) == want[name], name
+        assert lines.count(b"\n") == nreads and b"\r" not in lines, name
+    assert oracle.fastq_to_lines(b"") == (b"", 0, 0, -1)
+
+
+# ---- live against the unmodified reference (only where oracle/_ref was built) -------------------
+def test_sketch_vs_reference_live(oracle, reference):
+    rng = random.Random(11)
+    for k in (4, 6, 8, 15, 16, 27, 28):
+        for t in range(150):
+            alpha = ["ACGT", "ACGTNacgtnU", "AT", "GC"][t % 4]
+            s = "".join(rng.choice(alpha) for _ in range(rng.randint(1, 300))).encode()
+            assert np.array_equal(oracle.sketch(s, k), reference.sketch(s, k)), (k, s)
+
+
+def test_counts_vs_reference_live(oracle, reference, tmp_path):
+    t = helpers.tiny()
+    graph = tmp_path / "graph.bin"
+    graph.write_bytes(t["graph_bin"])
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    h, keys, k = reference.graph_load(str(graph))
+    try:
+        counts, read_bases, _ = reference.count_files(h, keys.size, [f1, f2], threads=3)
+    finally:
+        reference.graph_destroy(h)
+    assert k == t["k"] and read_bases == t["read_bases"]
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], t["keys"]) and np.array_equal(counts[order], t["counts"])
+    mine, _, _ = oracle.count_lines(keys, t["lines"], k)
+    assert np.array_equal(mine, counts)
+
+
+def test_fastq_parser_vs_reference_live(oracle, reference, tmp_path):
+    """kseq semantics: the reference reads each crafted file; the oracle parser must stage the same reads."""
+    t = helpers.tiny()
+    graph = tmp_path / "graph.bin"
+    graph.write_bytes(t["graph_bin"])
+    h, keys, k = reference.graph_load(str(graph))
+    try:
+        # sequences that certainly hit the index: windows of haplotype reads
+        body = t["m1"][:40]
+        for name, text in helpers.EDGE_FASTQS.items():
+            if name == "lower_n":
+                continue
+            recs = []
+            for i, r in enumerate(body):
+                s = r.tobytes()
+                if name == "crlf":
+                    recs.append(b"@q%d c\r\n%s\r\n+\r\n%s\r\n" % (i, s, b"I" * len(s)))
+                elif name == "multiline":
+                    recs.append(b"@q%d\n%s\n%s\n+\n%s\n%s\n" % (i, s[:70], s[70:], b"I" * 70, b"I" * (len(s) - 70)))
+                elif name == "fasta":
+                    recs.append(b">q%d\n%s\n%s\n" % (i, s[:70], s[70:]))
+                elif name == "qual_at":
+                    recs.append(b"@q%d\n%s\n+\n@%s\n" % (i, s, b"I" * (len(s) - 1)))
+                elif name == "truncated_qual" and i == 25:
+                    recs.append(b"@q%d\n%s\n+\n%s\n" % (i, s, b"I" * 10))
+                elif name == "leading_junk" and i == 0:
+                    recs.append(b"garbage\n\n@q%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+                else:
+                    recs.append(b"@q%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+            data = b"".join(recs)
+            if name == "no_final_newline":
+                data = data[:-1]
+            path = tmp_path / (name + ".fq")
+            path.write_bytes(data)
+            ref_counts, ref_bases, _ = reference.count_files(h, keys.size, [str(path)], threads=2)
+            lines, nreads, bases, status = oracle.fastq_to_lines(data)
+            mine, _, _ = oracle.count_lines(keys, lines, k)
+            assert bases == ref_bases, name
+            assert np.array_equal(mine, ref_counts), name
+    finally:
+        reference.graph_destroy(h)

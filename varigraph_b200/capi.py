@@ -1,0 +1,245 @@
+"""ctypes binding of libvgb200.so (include/vgb200.h) for the tests and bench.py.
+
+The product's host side is C++ (varigraph_b200/host/, mirroring the reference's classes);
+this module only lets Python drive the same C ABI.  There is no fallback: if the shared
+library is missing, importing it raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgb200.so")
+
+VG_OK, VG_E_INVALID, VG_E_CUDA, VG_E_NOMEM, VG_E_IO, VG_E_STATE = 0, -1, -2, -3, -4, -5
+
+
+class VgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libvgb200 error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). varigraph_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    P = POINTER
+    sig = {
+        "vg_last_error": (c_char_p, []),
+        "vg_version": (c_int, []),
+        "vg_ctx_create": (c_int, [c_int, c_int, P(c_void_p)]),
+        "vg_ctx_destroy": (c_int, [c_void_p]),
+        "vg_ctx_device": (c_int, [c_void_p]),
+        "vg_ctx_synchronize": (c_int, [c_void_p]),
+        "vg_index_create": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, P(c_void_p)]),
+        "vg_index_destroy": (c_int, [c_void_p]),
+        "vg_index_size": (c_uint64, [c_void_p]),
+        "vg_index_table_bytes": (c_uint64, [c_void_p]),
+        "vg_count_begin": (c_int, [c_void_p]),
+        "vg_count_submit": (c_int, [c_void_p, c_void_p, c_uint64]),
+        "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+        "vg_count_files": (c_int, [c_void_p, P(c_char_p), c_int, c_int, P(c_uint64)]),
+        "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
+        "vg_count_extract_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+        "vg_count_stats": (c_int, [c_void_p, P(c_uint64), P(c_uint64)]),
+        "vg_encode_positions_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p]),
+        "vg_encode_positions": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
+        "vg_cbf_create": (c_int, [c_void_p, c_uint64, c_uint32, c_void_p, P(c_void_p)]),
+        "vg_cbf_destroy": (c_int, [c_void_p]),
+        "vg_cbf_add_sequence": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, P(c_uint64)]),
+        "vg_cbf_download": (c_int, [c_void_p, c_void_p]),
+        "vg_cbf_query": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
+        "vg_host_alloc": (c_int, [P(c_void_p), c_uint64]),
+        "vg_host_free": (c_int, [c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def _chk(rc: int) -> None:
+    if rc != VG_OK:
+        raise VgError(rc, lib.vg_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: np.ndarray) -> c_void_p:
+    return c_void_p(a.ctypes.data)
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        return np.frombuffer(buf, dtype=np.uint8)
+    a = np.ascontiguousarray(buf)
+    return a.view(np.uint8).reshape(-1)
+
+
+class Context:
+    """One CUDA device (vg_ctx)."""
+
+    def __init__(self, device: int = 0, buffer_mb: int = 64):
+        h = c_void_p()
+        _chk(lib.vg_ctx_create(device, buffer_mb, byref(h)))
+        self._h = h
+        self.device = device
+
+    def synchronize(self) -> None:
+        _chk(lib.vg_ctx_synchronize(self._h))
+
+    def encode_positions(self, bases, k: int) -> np.ndarray:
+        b = _as_u8(bases)
+        out = np.empty(b.size, dtype=np.uint64)
+        _chk(lib.vg_encode_positions(self._h, _ptr(b), b.size, k, _ptr(out)))
+        return out
+
+    def encode_positions_device(self, dev_ptr: int, nbytes: int, k: int, out_ptr: int, stream: int = 0) -> None:
+        _chk(lib.vg_encode_positions_device(self._h, c_void_p(dev_ptr), nbytes, k, c_void_p(out_ptr),
+                                            c_void_p(stream)))
+
+    def close(self) -> None:
+        if self._h:
+            lib.vg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    """Device twin of mGraphKmerHashHapStrMap plus the read-coverage counters (vg_index)."""
+
+    def __init__(self, ctx: Context, keys: np.ndarray, k: int, load_factor: float = 0.0):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        h = c_void_p()
+        _chk(lib.vg_index_create(ctx._h, _ptr(keys), keys.size, k, load_factor, byref(h)))
+        self._h = h
+        self.ctx = ctx
+        self.n = int(keys.size)
+        self.k = k
+
+    @property
+    def table_bytes(self) -> int:
+        return int(lib.vg_index_table_bytes(self._h))
+
+    def begin(self) -> None:
+        _chk(lib.vg_count_begin(self._h))
+
+    def submit(self, bases) -> None:
+        b = _as_u8(bases)
+        _chk(lib.vg_count_submit(self._h, _ptr(b), b.size))
+
+    def submit_ptr(self, host_ptr: int, nbytes: int) -> None:
+        _chk(lib.vg_count_submit(self._h, c_void_p(host_ptr), nbytes))
+
+    def submit_device(self, dev_ptr: int, nbytes: int, stream: int = 0) -> None:
+        _chk(lib.vg_count_submit_device(self._h, c_void_p(dev_ptr), nbytes, c_void_p(stream)))
+
+    def count_files(self, paths, threads: int = 4) -> int:
+        arr = (c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        rb = c_uint64(0)
+        _chk(lib.vg_count_files(self._h, arr, len(paths), threads, byref(rb)))
+        return int(rb.value)
+
+    def end(self, want_counts: bool = True):
+        """-> (counts u8[n] or None, positions, hits)"""
+        out = np.empty(self.n, dtype=np.uint8) if want_counts else None
+        pos, hits = c_uint64(0), c_uint64(0)
+        _chk(lib.vg_count_end(self._h, _ptr(out) if want_counts else None, byref(pos), byref(hits)))
+        return out, int(pos.value), int(hits.value)
+
+    def stats(self):
+        pos, hits = c_uint64(0), c_uint64(0)
+        _chk(lib.vg_count_stats(self._h, byref(pos), byref(hits)))
+        return int(pos.value), int(hits.value)
+
+    def extract_device(self, dev_ptr: int, elem_bytes: int, stream: int = 0) -> None:
+        _chk(lib.vg_count_extract_device(self._h, c_void_p(dev_ptr), elem_bytes, c_void_p(stream)))
+
+    def close(self) -> None:
+        if self._h:
+            lib.vg_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CountingBloom:
+    """Device twin of BloomFilter / BloomFilterKernel (vg_cbf)."""
+
+    def __init__(self, ctx: Context, m: int, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        h = c_void_p()
+        _chk(lib.vg_cbf_create(ctx._h, m, seeds.size, _ptr(seeds), byref(h)))
+        self._h = h
+        self.ctx = ctx
+        self.m = int(m)
+
+    def add_sequence(self, seq, k: int) -> int:
+        b = _as_u8(seq)
+        added = c_uint64(0)
+        _chk(lib.vg_cbf_add_sequence(self._h, _ptr(b), b.size, k, byref(added)))
+        return int(added.value)
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.m, dtype=np.uint8)
+        _chk(lib.vg_cbf_download(self._h, _ptr(out)))
+        return out
+
+    def query(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        cnt = np.empty(keys.size, dtype=np.uint8)
+        fnd = np.empty(keys.size, dtype=np.uint8)
+        _chk(lib.vg_cbf_query(self._h, _ptr(keys), keys.size, _ptr(cnt), _ptr(fnd)))
+        return cnt, fnd
+
+    def close(self) -> None:
+        if self._h:
+            lib.vg_cbf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FastqKmerKernel:
+    """Python mirror of the reference's FastqKmerKernel (include/fastq_kmer.cuh:10-49): same
+    constructor arguments and method name, `mReadBase` as the public result; the map is stood in
+    for by its key array and `c` comes back as a u8 vector in the same order."""
+
+    def __init__(self, index: Index, fastqFileNameVec, kmerLen: int, threads: int, buffer: int = 100):
+        if kmerLen != index.k:
+            raise ValueError("kmerLen differs from the index's k")
+        self.index = index
+        self.fastqFileNameVec_ = list(fastqFileNameVec)
+        self.threads_ = threads
+        self.buffer_ = buffer
+        self.mReadBase = 0
+        self.c = None
+
+    def build_fastq_index_kernel(self) -> None:
+        if not self.fastqFileNameVec_:
+            raise VgError(VG_E_INVALID, "Parameter error: -f")
+        self.index.begin()
+        self.mReadBase += self.index.count_files(self.fastqFileNameVec_, self.threads_)
+        self.c, self.positions, self.hits = self.index.end()

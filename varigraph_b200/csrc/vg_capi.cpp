@@ -1,0 +1,505 @@
+// vg_capi.cpp -- the extern "C" surface declared in include/vgb200.h.
+// Host-side plumbing only: device memory, streams, the pinned staging ring.  All arithmetic of
+// the path lives in vg_kernels.cu.  No CPU fallback exists: every compute entry point needs a
+// CUDA device and fails with VG_E_CUDA otherwise.
+#include "../../include/vgb200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vg_host.h"
+#include "vg_internal.h"
+
+namespace {
+thread_local std::string g_err;
+}
+
+namespace vg {
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace vg
+
+using vg::fail;
+
+#define CU(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e__));                                             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Enqueue one staged piece that already sits in ring slot `si`'s pinned buffer (or at `src`).
+int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
+    vg_ctx* c = ix->ctx;
+    vg::StageSlot& sl = c->ring[(size_t)si];
+    CU(cudaMemcpyAsync(sl.d_buf, src, len, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(sl.copied, c->copy_stream));
+    CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
+    CU(vg::launch_count(ix->view, sl.d_buf, len, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, c->compute_stream));
+    CU(cudaEventRecord(sl.done, c->compute_stream));
+    sl.busy = true;
+    ix->launches += 1;
+    return VG_OK;
+}
+
+extern "C" {
+
+const char* vg_last_error(void) { return g_err.c_str(); }
+int vg_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+int vg_ctx_create(int device, int buffer_mb, vg_ctx** out) {
+    if (!out) return fail(VG_E_INVALID, "vg_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VG_E_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(VG_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    if (buffer_mb <= 0) buffer_mb = 64;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(VG_E_CUDA, "device %d is sm_%d%d; libvgb200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    vg_ctx* c = new vg_ctx();
+    c->device = device;
+    c->nsm = vg::sm_count(device);
+    c->chunk_bytes = (size_t)buffer_mb << 20;
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+    *out = c;
+    return VG_OK;
+}
+
+static int ctx_ensure_ring(vg_ctx* c, int nslots) {
+    while ((int)c->ring.size() < nslots) {
+        vg::StageSlot s;
+        CU(cudaMalloc((void**)&s.d_buf, c->chunk_bytes + 256));
+        CU(cudaHostAlloc((void**)&s.h_pin, c->chunk_bytes + 256, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        c->ring.push_back(s);
+    }
+    return VG_OK;
+}
+
+int vg_ctx_destroy(vg_ctx* c) {
+    if (!c) return VG_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (auto& s : c->ring) {
+        cudaFree(s.d_buf);
+        cudaFreeHost(s.h_pin);
+        cudaEventDestroy(s.copied);
+        cudaEventDestroy(s.done);
+    }
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->compute_stream);
+    delete c;
+    return VG_OK;
+}
+
+int vg_ctx_device(const vg_ctx* c) { return c ? c->device : -1; }
+
+int vg_ctx_synchronize(vg_ctx* c) {
+    if (!c) return fail(VG_E_INVALID, "ctx is NULL");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------
+int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor, vg_index** out) {
+    if (!c || !out || (!keys && n)) return fail(VG_E_INVALID, "vg_index_create: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28 (reference asserts k<=28, src/kmer.cpp:124)", k);
+    if (load_factor <= 0) load_factor = 0.4;
+    if (load_factor > 0.9) return fail(VG_E_INVALID, "load_factor %.3f > 0.9", load_factor);
+    DeviceGuard g(c->device);
+    uint64_t nb64 = (uint64_t)((double)n / (4.0 * load_factor)) + 1;
+    if (nb64 < 64) nb64 = 64;
+    if (nb64 >= 0xffffffffull) return fail(VG_E_INVALID, "index of %llu keys needs too many buckets", (unsigned long long)n);
+
+    vg_index* ix = new vg_index();
+    ix->ctx = c;
+    ix->n = n;
+    ix->view.k = k;
+    ix->view.mask = (1ULL << (2 * k)) - 1;
+    ix->view.nbuckets = (uint32_t)nb64;
+    ix->view.has_special = 0;
+    auto bail = [&](int code) {
+        vg_index_destroy(ix);
+        return code;
+    };
+#define CUB(expr)                                                                      \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return bail(fail(e__ == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "%s: %s", #expr, \
+                             cudaGetErrorString(e__)));                                \
+    } while (0)
+    uint64_t nslots = 4ull * ix->view.nbuckets;
+    CUB(cudaMalloc((void**)&ix->view.slots, nslots * sizeof(uint64_t)));
+    CUB(cudaMalloc((void**)&ix->d_key56, std::max<uint64_t>(n, 1) * sizeof(uint64_t)));
+    CUB(cudaMalloc((void**)&ix->d_counts, std::max<uint64_t>(n, 4)));
+    CUB(cudaMalloc((void**)&ix->d_misc, sizeof(vg::DeviceMisc)));
+    CUB(cudaMemset(ix->d_misc, 0, sizeof(vg::DeviceMisc)));
+    ix->view.special = &ix->d_misc->special;
+    cudaStream_t s = c->compute_stream;
+    CUB(vg::launch_table_fill_empty(ix->view.slots, nslots, s));
+
+    // keys -> key56, staged through a bounded host buffer
+    const uint64_t piece = 1ull << 22;
+    std::vector<uint64_t> tmp((size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
+    for (uint64_t off = 0; off < n; off += piece) {
+        uint64_t m = std::min<uint64_t>(piece, n - off);
+        for (uint64_t i = 0; i < m; ++i) {
+            uint64_t key = keys[off + i];
+            if ((key & 0xffu) != k)
+                return bail(fail(VG_E_INVALID, "keys[%llu]=0x%llx: low byte is not k=%u (src/kmer.cpp:138)",
+                                 (unsigned long long)(off + i), (unsigned long long)key, k));
+            uint64_t h = key >> 8;
+            if (h > ix->view.mask)
+                return bail(fail(VG_E_INVALID, "keys[%llu]: hash exceeds 2k bits", (unsigned long long)(off + i)));
+            if (h == ((1ULL << 56) - 1)) ix->view.has_special = 1;
+            tmp[(size_t)i] = h;
+        }
+        CUB(cudaMemcpyAsync(ix->d_key56 + off, tmp.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        CUB(cudaStreamSynchronize(s));
+    }
+    CUB(vg::launch_insert(ix->view, ix->d_key56, n, &ix->d_misc->report, s));
+    vg::DeviceMisc misc;
+    CUB(cudaMemcpyAsync(&misc, ix->d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));
+    CUB(cudaStreamSynchronize(s));
+    if (misc.report.failed) return bail(fail(VG_E_NOMEM, "index build: %llu keys found no slot", misc.report.failed));
+    ix->duplicates = misc.report.duplicates;
+#undef CUB
+    *out = ix;
+    return VG_OK;
+}
+
+int vg_index_destroy(vg_index* ix) {
+    if (!ix) return VG_OK;
+    DeviceGuard g(ix->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ix->view.slots);
+    cudaFree(ix->d_key56);
+    cudaFree(ix->d_counts);
+    cudaFree(ix->d_misc);
+    delete ix;
+    return VG_OK;
+}
+
+uint64_t vg_index_size(const vg_index* ix) { return ix ? ix->n : 0; }
+uint64_t vg_index_table_bytes(const vg_index* ix) { return ix ? 32ull * ix->view.nbuckets : 0; }
+
+// ---------------------------------------------------------------------------
+// count phase
+// ---------------------------------------------------------------------------
+int vg_count_begin(vg_index* ix) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    CU(vg::launch_clear_counts(ix->view, c->compute_stream));
+    CU(cudaMemsetAsync(&ix->d_misc->stats, 0, sizeof(vg::CountStats), c->compute_stream));
+    ix->counting = true;
+    return VG_OK;
+}
+
+int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes, void* cuda_stream) {
+    if (!ix || (!dev_bases && nbytes)) return fail(VG_E_INVALID, "vg_count_submit_device: NULL argument");
+    if (!ix->counting) return fail(VG_E_STATE, "vg_count_submit_device before vg_count_begin");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
+    if (cuda_stream) {  // order after vg_count_begin's clears on the context stream
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, c->compute_stream));
+        CU(cudaStreamWaitEvent(s, ev, 0));
+        CU(cudaEventDestroy(ev));
+        ix->foreign_streams = true;
+    }
+    CU(vg::launch_count(ix->view, (const uint8_t*)dev_bases, nbytes, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, s));
+    ix->launches += 1;
+    return VG_OK;
+}
+
+int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
+    if (!ix || (!host_bases && nbytes)) return fail(VG_E_INVALID, "vg_count_submit: NULL argument");
+    if (!ix->counting) return fail(VG_E_STATE, "vg_count_submit before vg_count_begin");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    int rc = ctx_ensure_ring(c, 3);
+    if (rc) return rc;
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, host_bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    uint64_t off = 0;
+    while (off < nbytes) {
+        uint64_t len = std::min<uint64_t>(c->chunk_bytes, nbytes - off);
+        if (off + len < nbytes) {  // cut at a read boundary
+            const void* nl = memrchr(host_bases + off, '\n', (size_t)len);
+            if (!nl) return fail(VG_E_INVALID, "a read is longer than the %zu-byte staging buffer", c->chunk_bytes);
+            len = (uint64_t)((const char*)nl - (host_bases + off)) + 1;
+        }
+        int si = c->next_slot;
+        c->next_slot = (c->next_slot + 1) % (int)c->ring.size();
+        vg::StageSlot& sl = c->ring[(size_t)si];
+        if (sl.busy) {
+            CU(cudaEventSynchronize(sl.done));
+            sl.busy = false;
+        }
+        const char* src = host_bases + off;
+        if (!pinned) {
+            memcpy(sl.h_pin, src, (size_t)len);
+            src = (const char*)sl.h_pin;
+        }
+        rc = vg::enqueue_piece(ix, si, src, len);
+        if (rc) return rc;
+        off += len;
+    }
+    return VG_OK;
+}
+
+int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    if (ix->foreign_streams) CU(cudaDeviceSynchronize());
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    vg::CountStats st;
+    CU(cudaMemcpy(&st, &ix->d_misc->stats, sizeof st, cudaMemcpyDeviceToHost));
+    if (positions) *positions = st.positions;
+    if (hits) *hits = st.hits;
+    return VG_OK;
+}
+
+int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* cuda_stream) {
+    if (!ix || !dev_out) return fail(VG_E_INVALID, "vg_count_extract_device: NULL argument");
+    if (elem_bytes != 1 && elem_bytes != 4) return fail(VG_E_INVALID, "elem_bytes must be 1 or 4");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
+    if (cuda_stream) {  // counting kernels submitted through the context must finish first
+        CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(c->compute_stream));
+    }
+    CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, dev_out, elem_bytes, s));
+    return VG_OK;
+}
+
+int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hits) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    if (!ix->counting) return fail(VG_E_STATE, "vg_count_end before vg_count_begin");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    int rc = vg_count_stats(ix, positions, hits);
+    if (rc) return rc;
+    for (auto& sl : c->ring) sl.busy = false;
+    if (c_out && ix->n) {
+        CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, ix->d_counts, 1, c->compute_stream));
+        CU(cudaMemcpyAsync(c_out, ix->d_counts, ix->n, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(cudaStreamSynchronize(c->compute_stream));
+    }
+    ix->counting = false;
+    ix->foreign_streams = false;
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-position keys
+// ---------------------------------------------------------------------------
+int vg_encode_positions_device(vg_ctx* c, const void* dev_bases, uint64_t nbytes, uint32_t k, uint64_t* dev_keys_out,
+                               void* cuda_stream) {
+    if (!c || (!dev_bases && nbytes) || (!dev_keys_out && nbytes)) return fail(VG_E_INVALID, "NULL argument");
+    if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28", k);
+    DeviceGuard g(c->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
+    CU(vg::launch_positions(k, (const uint8_t*)dev_bases, nbytes, dev_keys_out, s));
+    return VG_OK;
+}
+
+int vg_encode_positions(vg_ctx* c, const char* host_bases, uint64_t nbytes, uint32_t k, uint64_t* host_keys_out) {
+    if (!c || (!host_bases && nbytes) || (!host_keys_out && nbytes)) return fail(VG_E_INVALID, "NULL argument");
+    if (nbytes == 0) return VG_OK;
+    DeviceGuard g(c->device);
+    uint8_t* d_b = nullptr;
+    uint64_t* d_k = nullptr;
+    CU(cudaMalloc((void**)&d_b, nbytes + 64));
+    cudaError_t e = cudaMalloc((void**)&d_k, nbytes * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        cudaFree(d_b);
+        return fail(VG_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    int rc = VG_OK;
+    cudaStream_t s = c->compute_stream;
+    if ((e = cudaMemcpyAsync(d_b, host_bases, nbytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = vg::launch_positions(k, d_b, nbytes, d_k, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(host_keys_out, d_k, nbytes * sizeof(uint64_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s)) != cudaSuccess)
+        rc = fail(VG_E_CUDA, "vg_encode_positions: %s", cudaGetErrorString(e));
+    cudaFree(d_b);
+    cudaFree(d_k);
+    if (rc == VG_OK && (k < 1 || k > 28)) rc = fail(VG_E_INVALID, "k=%u outside 1..28", k);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// counting Bloom filter
+// ---------------------------------------------------------------------------
+int vg_cbf_create(vg_ctx* c, uint64_t m, uint32_t num_hashes, const uint64_t* seeds, vg_cbf** out) {
+    if (!c || !out || !seeds) return fail(VG_E_INVALID, "vg_cbf_create: NULL argument");
+    *out = nullptr;
+    if (m == 0) return fail(VG_E_INVALID, "filter size 0");
+    if (num_hashes == 0 || num_hashes > 16) return fail(VG_E_INVALID, "num_hashes=%u outside 1..16", num_hashes);
+    DeviceGuard g(c->device);
+    vg_cbf* f = new vg_cbf();
+    f->ctx = c;
+    f->view.m = m;
+    f->view.num_hashes = num_hashes;
+    for (uint32_t i = 0; i < num_hashes; ++i) f->view.seeds[i] = (uint32_t)seeds[i];  // counting_bloom_filter.cpp:91
+    unsigned __int128 M = (~(unsigned __int128)0) / m + 1;
+    f->view.magic_hi = (uint64_t)(M >> 64);
+    f->view.magic_lo = (uint64_t)M;
+    uint64_t alloc = (m + 3) & ~3ULL;
+    cudaError_t e = cudaMalloc((void**)&f->view.cells, alloc);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_added, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->view.cells, 0, alloc, c->compute_stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->d_added, 0, sizeof(unsigned long long), c->compute_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute_stream);
+    if (e != cudaSuccess) {
+        vg_cbf_destroy(f);
+        return fail(e == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "vg_cbf_create: %s", cudaGetErrorString(e));
+    }
+    *out = f;
+    return VG_OK;
+}
+
+int vg_cbf_destroy(vg_cbf* f) {
+    if (!f) return VG_OK;
+    DeviceGuard g(f->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(f->view.cells);
+    cudaFree(f->d_added);
+    cudaFree(f->d_seq);
+    delete f;
+    return VG_OK;
+}
+
+int vg_cbf_add_sequence(vg_cbf* f, const char* host_seq, uint64_t len, uint32_t k, uint64_t* added) {
+    if (!f || (!host_seq && len)) return fail(VG_E_INVALID, "vg_cbf_add_sequence: NULL argument");
+    if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28", k);
+    if (added) *added = 0;
+    if (len == 0) return VG_OK;
+    vg_ctx* c = f->ctx;
+    DeviceGuard g(c->device);
+    if (f->d_seq_cap < len + 256) {
+        CU(cudaStreamSynchronize(c->compute_stream));
+        cudaFree(f->d_seq);
+        f->d_seq = nullptr;
+        f->d_seq_cap = 0;
+        CU(cudaMalloc((void**)&f->d_seq, len + 256));
+        f->d_seq_cap = len + 256;
+    }
+    CU(cudaMemsetAsync(f->d_added, 0, sizeof(unsigned long long), c->compute_stream));
+    // The chromosome is one contiguous device buffer; it is uploaded in tile-aligned pieces so
+    // the fill of piece i overlaps the copy of piece i+1.  A piece's k-mers may start in the
+    // previous piece: the kernel simply looks back into bytes that are already resident.
+    const uint64_t piece = (uint64_t)vg::kTilePieceBytes;
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    int rc = VG_OK;
+    for (uint64_t off = 0; off < len && rc == VG_OK; off += piece) {
+        uint64_t m = std::min<uint64_t>(piece, len - off);
+        cudaError_t e = cudaMemcpyAsync(f->d_seq + off, host_seq + off, m, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, c->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->compute_stream, ev, 0);
+        if (e == cudaSuccess)
+            e = vg::launch_cbf_add(f->view, k, f->d_seq, off + m, off, f->d_added, c->nsm, c->compute_stream);
+        if (e != cudaSuccess) rc = fail(VG_E_CUDA, "vg_cbf_add_sequence: %s", cudaGetErrorString(e));
+    }
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, f->d_added, sizeof n, cudaMemcpyDeviceToHost, c->compute_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    if (added) *added = n;
+    return VG_OK;
+}
+
+int vg_cbf_download(vg_cbf* f, uint8_t* host_filter) {
+    if (!f || !host_filter) return fail(VG_E_INVALID, "vg_cbf_download: NULL argument");
+    vg_ctx* c = f->ctx;
+    DeviceGuard g(c->device);
+    CU(cudaMemcpyAsync(host_filter, f->view.cells, f->view.m, cudaMemcpyDeviceToHost, c->compute_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    return VG_OK;
+}
+
+int vg_cbf_query(vg_cbf* f, const uint64_t* host_keys, uint64_t n, uint8_t* count_out, uint8_t* find_out) {
+    if (!f || (!host_keys && n)) return fail(VG_E_INVALID, "vg_cbf_query: NULL argument");
+    if (n == 0) return VG_OK;
+    vg_ctx* c = f->ctx;
+    DeviceGuard g(c->device);
+    uint64_t* d_k = nullptr;
+    uint8_t* d_o = nullptr;
+    CU(cudaMalloc((void**)&d_k, n * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc((void**)&d_o, 2 * n);
+    cudaStream_t s = c->compute_stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, host_keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = vg::launch_cbf_query(f->view, d_k, n, d_o, d_o + n, s);
+    if (e == cudaSuccess && count_out) e = cudaMemcpyAsync(count_out, d_o, n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && find_out) e = cudaMemcpyAsync(find_out, d_o + n, n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_k);
+    cudaFree(d_o);
+    if (e != cudaSuccess) return fail(VG_E_CUDA, "vg_cbf_query: %s", cudaGetErrorString(e));
+    return VG_OK;
+}
+
+int vg_host_alloc(void** out, uint64_t nbytes) {
+    if (!out) return fail(VG_E_INVALID, "out is NULL");
+    CU(cudaHostAlloc(out, nbytes ? nbytes : 1, cudaHostAllocDefault));
+    return VG_OK;
+}
+int vg_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return VG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// vg_device.cuh -- device-side primitives of the read k-mer counting path (sm_100a).
+//
+// What each piece reproduces (reference file:line, /root/reference):
+//   nt4 LUT            include/seq_nt4_table.hpp:5-22   (byte -> 0..3, else ambiguous)
+//   hash64             include/hash64.hpp:5-14
+//   rolling encoder    src/kmer.cpp:126-146             (fwd/rev registers, run length, fwd==rev skip)
+//   murmur3_x64_128    src/MurmurHash3.cpp:255-332 for len == 8, summed as
+//                      src/counting_bloom_filter.cpp:90-98
+// The layout of the index (one 32-byte sector = 4 slots of [hash:56 | count:8]) is ours.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vg {
+
+constexpr uint64_t kNoKmer = ~0ULL;                // "this position emits nothing"
+constexpr uint64_t kSlotEmpty = ~0ULL;             // never equals a live slot (see kKey56Max)
+constexpr uint64_t kKey56Max = (1ULL << 56) - 1;   // only reachable for k == 28: kept outside the table
+constexpr uint32_t kFullMask = 0xffffffffu;
+constexpr int kSegBytes = 16;                      // bytes per lane per step (one 128-bit load)
+constexpr int kCtaThreads = 256;
+constexpr int kTileBytes = kCtaThreads * kSegBytes;  // 4 KiB of bases per CTA step
+
+// LUT entry: bits 0-1 code, bit 2 valid, bit 3 newline (hard read boundary).
+__device__ __forceinline__ uint8_t nt4_entry(uint32_t b) {
+    uint32_t code = 0, valid = 0;
+    uint32_t up = b & 0xDFu;
+    if (b < 4) { code = b; valid = 1; }
+    else if (up == 'A') { code = 0; valid = 1; }
+    else if (up == 'C') { code = 1; valid = 1; }
+    else if (up == 'G') { code = 2; valid = 1; }
+    else if (up == 'T' || up == 'U') { code = 3; valid = 1; }
+    uint32_t nl = (b == '\n') ? 1u : 0u;
+    return (uint8_t)(code | (valid << 2) | (nl << 3));
+}
+
+__device__ __forceinline__ void lut_init(uint8_t* lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = nt4_entry((uint32_t)i);
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint64_t hash64(uint64_t x, uint64_t m) {
+    x = (~x + (x << 21)) & m;
+    x ^= x >> 24;
+    x = (x + (x << 3) + (x << 8)) & m;
+    x ^= x >> 14;
+    x = (x + (x << 2) + (x << 4)) & m;
+    x ^= x >> 28;
+    x = (x + (x << 31)) & m;
+    return x;
+}
+
+// Reverse complement of the k bases held in the low 2k bits of f (oldest base highest).
+__device__ __forceinline__ uint64_t revcomp2k(uint64_t f, uint32_t k) {
+    uint64_t y = __brevll(~f);
+    y = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+    return y >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t fmix64(uint64_t h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+// k1 is the seed-independent half of the work: mix the 8-byte key once, reuse for all seeds.
+__device__ __forceinline__ uint64_t murmur3_k1(uint64_t key) {
+    uint64_t k1 = key * 0x87c37b91114253d5ULL;
+    return rotl64(k1, 31) * 0x4cf5ad432745937fULL;
+}
+__device__ __forceinline__ uint64_t murmur3_sum_from_k1(uint64_t k1, uint32_t seed) {
+    uint64_t h1 = seed, h2 = seed;
+    h1 ^= k1;
+    h1 ^= 8;
+    h2 ^= 8;
+    h1 += h2;
+    h2 += h1;
+    h1 = fmix64(h1);
+    h2 = fmix64(h2);
+    h1 += h2;
+    h2 += h1;
+    return h1 + h2;
+}
+
+// a % d for a fixed d, exact for all 64-bit a (Lemire fastmod with a 128-bit magic M = floor((2^128-1)/d)+1).
+struct FastMod64 {
+    uint64_t m_hi, m_lo, d;
+};
+__device__ __forceinline__ uint64_t fastmod64(uint64_t a, const FastMod64& f) {
+    // lowbits = (M * a) mod 2^128
+    uint64_t lb_lo = f.m_lo * a;
+    uint64_t lb_hi = __umul64hi(f.m_lo, a) + f.m_hi * a;
+    // result = (lowbits * d) >> 128
+    uint64_t t_hi = __umul64hi(lb_lo, f.d);
+    uint64_t u_lo = lb_hi * f.d;
+    uint64_t u_hi = __umul64hi(lb_hi, f.d);
+    uint64_t s = t_hi + u_lo;
+    return u_hi + (s < t_hi ? 1ULL : 0ULL);
+}
+
+// ---- 256-bit sector load: one index bucket ---------------------------------
+__device__ __forceinline__ void ld_bucket(const uint64_t* p, uint64_t (&v)[4]) {
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets) {
+    uint64_t x = key56 * 0x9E3779B97F4A7C15ULL;
+    return __umulhi((uint32_t)(x >> 32), nbuckets);
+}
+
+// ---- the view of a staged chunk --------------------------------------------
+// `al` is the 16-byte aligned-down base; live bytes are [lo, hi) relative to it.
+// Everything outside behaves like '\n'.
+struct Chunk {
+    const uint8_t* al;
+    int64_t lo, hi;
+};
+
+struct KmerParams {
+    uint32_t k;
+    uint64_t mask;
+};
+
+// Encode one 16-byte segment to (2-bit packed, first base in the top bits; validity mask, first
+// base in bit 15).  Out-of-range bytes are invalid.
+__device__ __forceinline__ void encode_seg(const Chunk& c, int64_t off, const uint8_t* lut,
+                                           uint32_t& packed, uint32_t& vmask) {
+    packed = 0;
+    vmask = 0;
+    if (off + kSegBytes <= c.lo || off >= c.hi || off < 0) return;
+    uint4 w = ld_stream16(c.al + off);
+    uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t e = lut[(ws[i] >> (8 * j)) & 0xffu];
+            packed = (packed << 2) | (e & 3u);
+            vmask = (vmask << 1) | ((e >> 2) & 1u);
+        }
+    }
+    if (off < c.lo || off + kSegBytes > c.hi) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (off + j >= c.lo && off + j < c.hi) keep |= 1u << (15 - j);
+        vmask &= keep;
+    }
+}
+
+// ---- odd k: warp-cooperative position-parallel encoder ----------------------
+// For odd k, fwd == rev cannot happen, so "emit at i" == "the k bytes ending at i
+// are all valid".  Each lane owns 16 consecutive positions and borrows the 32 preceding bases
+// from its two left neighbours by shuffle (lanes 0/1 re-read them from memory).
+// keys[j] = hash64(canonical k-mer ending at off + j) or kNoKmer.
+__device__ __forceinline__ void encode_keys_odd(const Chunk& c, int64_t off, const KmerParams& kp,
+                                                const uint8_t* lut, uint64_t (&keys)[16]) {
+    const int lane = threadIdx.x & 31;
+    uint32_t p0, v0;
+    encode_seg(c, off, lut, p0, v0);
+    uint32_t ex = 0, exv = 0;
+    if (lane < 2) encode_seg(c, off - 32, lut, ex, exv);
+    // lane 0 holds segment (warp_off - 32), lane 1 holds segment (warp_off - 16)
+    uint32_t ex0 = __shfl_sync(kFullMask, ex, 0), exv0 = __shfl_sync(kFullMask, exv, 0);
+    uint32_t ex1 = __shfl_sync(kFullMask, ex, 1), exv1 = __shfl_sync(kFullMask, exv, 1);
+    uint32_t p1 = __shfl_up_sync(kFullMask, p0, 1), v1 = __shfl_up_sync(kFullMask, v0, 1);
+    uint32_t p2 = __shfl_up_sync(kFullMask, p0, 2), v2 = __shfl_up_sync(kFullMask, v0, 2);
+    if (lane == 0) { p1 = ex1; v1 = exv1; p2 = ex0; v2 = exv0; }
+    if (lane == 1) { p2 = ex1; v2 = exv1; }
+
+    const uint32_t k = kp.k;
+    const uint64_t kones = (1ULL << k) - 1;
+    const uint64_t V = ((uint64_t)v2 << 32) | ((uint64_t)v1 << 16) | v0;
+    uint64_t fwd = (((uint64_t)p2 << 32) | p1) & kp.mask;
+    uint64_t rev = revcomp2k(fwd, k);
+    const uint32_t top = 2 * (k - 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint64_t cb = (p0 >> (30 - 2 * j)) & 3u;
+        fwd = ((fwd << 2) | cb) & kp.mask;
+        rev = (rev >> 2) | ((3ULL ^ cb) << top);
+        bool emit = ((V >> (15 - j)) & kones) == kones;
+        uint64_t canon = fwd < rev ? fwd : rev;
+        keys[j] = emit ? hash64(canon, kp.mask) : kNoKmer;
+    }
+}
+
+// ---- any k: exact state machine with a look-back to a synchronisation point --
+// Needed for even k, where fwd == rev (a reverse-complement palindrome) skips a position
+// without advancing the run length, and the registers survive ambiguous bases (src/kmer.cpp:
+// 131-146, note `else l = 0, kmer_span = 0;` leaves kmer[] alone).  The state at the start of a
+// lane's segment is recovered exactly by scanning back to either a hard boundary ('\n' / chunk
+// edge: state zero) or 2k consecutive valid bytes none of whose k+1 clean windows is a
+// palindrome (then the run length is >= k whatever came before), and rolling forward from there.
+struct RollState {
+    uint64_t fwd, rev;
+    uint32_t run;  // saturates at k: only run >= k is ever observed
+};
+
+__device__ __forceinline__ bool roll_push(RollState& s, uint32_t e, const KmerParams& kp, uint64_t& key) {
+    if (!(e & 4u)) {
+        s.run = 0;
+        return false;
+    }
+    uint64_t cb = e & 3u;
+    s.fwd = ((s.fwd << 2) | cb) & kp.mask;
+    s.rev = (s.rev >> 2) | ((3ULL ^ cb) << (2 * (kp.k - 1)));
+    if (s.fwd == s.rev) return false;
+    if (s.run < kp.k) s.run += 1;
+    if (s.run < kp.k) return false;
+    key = hash64(s.fwd < s.rev ? s.fwd : s.rev, kp.mask);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, const uint8_t* lut) {
+    if (pos < c.lo || pos >= c.hi) return 8u;  // newline
+    return lut[c.al[pos]];
+}
+
+__device__ inline void encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
+                                       const uint8_t* lut, uint64_t (&keys)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) keys[j] = kNoKmer;
+    if (off >= c.hi || off + kSegBytes <= c.lo) return;
+    const int64_t need = 2 * (int64_t)kp.k;
+    RollState st;
+    int64_t scan_from = off;  // exclusive upper end of the region still to scan backwards
+    for (;;) {
+        // scan back for a hard boundary or `need` consecutive valid bytes
+        int64_t p = scan_from, cnt = 0, start = -1;
+        bool hard = false;
+        while (true) {
+            if (p <= c.lo) { hard = true; start = c.lo; break; }
+            uint32_t e = chunk_entry(c, p - 1, lut);
+            if (e & 8u) { hard = true; start = p; break; }
+            cnt = (e & 4u) ? cnt + 1 : 0;
+            --p;
+            if (cnt == need) { start = p; break; }
+        }
+        st.fwd = st.rev = 0;
+        st.run = 0;
+        if (hard) {
+            uint64_t key;
+            for (int64_t q = start; q < off; ++q) roll_push(st, chunk_entry(c, q, lut), kp, key);
+            break;
+        }
+        // candidate: roll through the 2k valid bytes; the last k+1 windows must not be palindromes
+        bool clean = true;
+        for (int64_t q = start; q < start + need; ++q) {
+            uint32_t e = chunk_entry(c, q, lut);
+            uint64_t cb = e & 3u;
+            st.fwd = ((st.fwd << 2) | cb) & kp.mask;
+            st.rev = (st.rev >> 2) | ((3ULL ^ cb) << (2 * (kp.k - 1)));
+            if (q - start >= (int64_t)kp.k - 1 && st.fwd == st.rev) clean = false;
+        }
+        if (clean) {
+            st.run = kp.k;
+            uint64_t key;
+            for (int64_t q = start + need; q < off; ++q) roll_push(st, chunk_entry(c, q, lut), kp, key);
+            break;
+        }
+        scan_from = start + need - 1;  // look for an earlier synchronisation point
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t e = chunk_entry(c, off + j, lut);
+        if (e & 8u) {  // hard boundary: a new read starts after it
+            st.fwd = st.rev = 0;
+            st.run = 0;
+            continue;
+        }
+        uint64_t key;
+        if (roll_push(st, e, kp, key)) keys[j] = key;
+    }
+}
+
+}  // namespace vg

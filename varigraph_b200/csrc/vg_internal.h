@@ -1,0 +1,55 @@
+// vg_internal.h -- host-visible launch interface between vg_capi.cpp and vg_kernels.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vg {
+
+struct IndexView {
+    uint64_t* slots;                // nbuckets * 4 slots of [hash:56 | count:8]; empty = ~0
+    uint32_t nbuckets;
+    uint32_t k;
+    uint64_t mask;                  // 2^(2k) - 1
+    unsigned long long* special;    // counter for the one key a slot cannot hold (k == 28 only)
+    int has_special;
+};
+
+struct CountStats {                 // lives in device memory
+    unsigned long long positions;   // emitted k-mer positions (what kmer_sketch_fastq tests against the map)
+    unsigned long long hits;        // positions whose k-mer is in the index
+};
+
+struct InsertReport {               // lives in device memory
+    unsigned long long duplicates;
+    unsigned long long failed;
+};
+
+struct CbfView {
+    uint8_t* cells;                 // m saturating u8 counters
+    uint64_t m;
+    uint64_t magic_hi, magic_lo;    // fastmod constant for % m
+    uint32_t num_hashes;            // <= 16
+    uint32_t seeds[16];             // already truncated to 32 bit, as the reference does at the call
+};
+
+int sm_count(int device);
+
+cudaError_t launch_table_fill_empty(uint64_t* slots, uint64_t nslots, cudaStream_t s);
+cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
+                          cudaStream_t s);
+cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);
+cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
+                         int ctas_per_sm, int nsm, cudaStream_t s);
+cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
+                           int out_elem_bytes, cudaStream_t s);
+cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes, uint64_t* d_out,
+                             cudaStream_t s);
+
+// d_bases: 16-byte aligned buffer holding one sequence; bytes [0, hi) are resident.  Adds every
+// k-mer that ENDS in [own_from, hi); own_from must be a multiple of the 4 KiB CTA tile.
+cudaError_t launch_cbf_add(const CbfView& cbf, uint32_t k, const uint8_t* d_bases, uint64_t hi, uint64_t own_from,
+                           unsigned long long* d_added, int nsm, cudaStream_t s);
+cudaError_t launch_cbf_query(const CbfView& cbf, const uint64_t* d_keys, uint64_t n, uint8_t* d_count,
+                             uint8_t* d_find, cudaStream_t s);
+
+}  // namespace vg
