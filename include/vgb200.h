@@ -43,6 +43,9 @@ int vg_ctx_create(int device, int buffer_mb, vg_ctx** out);
 int vg_ctx_destroy(vg_ctx* ctx);
 int vg_ctx_device(const vg_ctx* ctx);
 int vg_ctx_synchronize(vg_ctx* ctx);
+/* Run the context's kernels on the caller's stream (a cudaStream_t; NULL restores the context's
+ * own) -- the cublasSetStream convention, so a host that owns its streams can order and time them. */
+int vg_ctx_set_stream(vg_ctx* ctx, void* cuda_stream);
 
 /* ---- the index -------------------------------------------------------------------------
  * Device twin of ConstructIndex::mGraphKmerHashHapStrMap (include/construct_index.hpp:140):
@@ -109,6 +112,12 @@ int vg_cbf_add_sequence(vg_cbf* cbf, const char* host_seq, uint64_t len, uint32_
 int vg_cbf_download(vg_cbf* cbf, uint8_t* host_filter);
 /* BloomFilter::count / find for a batch (src/counting_bloom_filter.cpp:40-67); either out may be NULL. */
 int vg_cbf_query(vg_cbf* cbf, const uint64_t* host_keys, uint64_t n, uint8_t* count_out, uint8_t* find_out);
+
+/* Diagnostic: measured throughput of uniform random 32-byte sector gathers over a table of
+ * table_bytes (>> L2) with the same load shape as the index probe: the denominator of the
+ * "fraction of random-access HBM peak" figure.  No reference counterpart. */
+int vg_probe_random_sectors(vg_ctx* ctx, uint64_t table_bytes, uint32_t rounds, double* gbytes_per_s,
+                            double* sectors_per_s);
 
 /* Pinned host memory for callers that want zero-copy staging (cudaHostAlloc / cudaFreeHost). */
 int vg_host_alloc(void** out, uint64_t nbytes);

@@ -20,6 +20,7 @@
 //   ref_cbf_fill             -> src/kmer.cpp:20-52 (kmer_sketch_bf)
 //   ref_graph_*              -> src/construct_index.cpp:911 (load_index)
 //   ref_count_files          -> src/fastq_kmer.cpp:41-187 (build_fastq_index)
+//   ref_map_*                -> the same FastqKmer::build_fastq_index over a caller-supplied key set
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -146,6 +147,41 @@ double ref_count_files(void* h, const char** files, int nfiles, uint32_t threads
         for (size_t i = 0; i < g->keys.size(); ++i)
             c_out[i] = g->ci->mGraphKmerHashHapStrMap.find(g->keys[i])->second.c;
     }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- the count phase over an arbitrary key set (bench.py's reference arm) -------------------
+// The synthetic bench index is not the output of `construct`, so there is no graph.bin to load;
+// FastqKmer only needs the map (include/fastq_kmer.hpp:57-62), so build it directly.
+struct MapHolder {
+    std::unordered_map<uint64_t, kmerCovFreBitVec> map;
+    std::vector<uint64_t> keys;
+    uint32_t k;
+};
+void* ref_map_create(const uint64_t* keys, uint64_t n, uint32_t k) {
+    MapHolder* m = new MapHolder();
+    m->k = k;
+    m->keys.assign(keys, keys + n);
+    m->map.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) m->map[keys[i]];
+    return m;
+}
+void ref_map_destroy(void* h) { delete static_cast<MapHolder*>(h); }
+void ref_map_reset(void* h) {
+    for (auto& kv : static_cast<MapHolder*>(h)->map) kv.second.reset();  // as ConstructIndex::reset()
+}
+double ref_map_count_files(void* h, const char** files, int nfiles, uint32_t threads, uint8_t* c_out,
+                           uint64_t* read_bases) {
+    MapHolder* m = static_cast<MapHolder*>(h);
+    std::vector<std::string> fv;
+    for (int i = 0; i < nfiles; ++i) fv.emplace_back(files[i]);
+    FastqKmer fk(m->map, fv, m->k, threads);
+    auto t0 = std::chrono::steady_clock::now();
+    fk.build_fastq_index();
+    auto t1 = std::chrono::steady_clock::now();
+    if (read_bases) *read_bases = fk.mReadBase;
+    if (c_out)
+        for (size_t i = 0; i < m->keys.size(); ++i) c_out[i] = m->map.find(m->keys[i])->second.c;
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

@@ -164,6 +164,30 @@ class Reference:
         R.ref_count_files.restype = c_double
         R.ref_count_files.argtypes = [c_void_p, POINTER(c_char_p), c_int, c_uint32, c_void_p, POINTER(c_uint64)]
 
+        R.ref_map_create.restype = c_void_p
+        R.ref_map_create.argtypes = [c_void_p, c_uint64, c_uint32]
+        R.ref_map_destroy.argtypes = [c_void_p]
+        R.ref_map_reset.argtypes = [c_void_p]
+        R.ref_map_count_files.restype = c_double
+        R.ref_map_count_files.argtypes = [c_void_p, POINTER(c_char_p), c_int, c_uint32, c_void_p, POINTER(c_uint64)]
+
+    def map_create(self, keys: np.ndarray, k: int):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        return self.lib.ref_map_create(keys.ctypes.data, keys.size, k)
+
+    def map_destroy(self, h) -> None:
+        self.lib.ref_map_destroy(h)
+
+    def map_count_files(self, h, n: int, files, threads: int, want_counts: bool = True):
+        """FastqKmer::build_fastq_index over a caller-supplied key set -> (counts, read_bases, seconds)"""
+        arr = (c_char_p * len(files))(*[os.fsencode(f) for f in files])
+        counts = np.zeros(n, dtype=np.uint8) if want_counts else None
+        rb = c_uint64(0)
+        self.lib.ref_map_reset(h)
+        sec = self.lib.ref_map_count_files(h, arr, len(files), threads,
+                                           counts.ctypes.data if want_counts else None, byref(rb))
+        return counts, int(rb.value), float(sec)
+
     def sketch(self, seq, k: int) -> np.ndarray:
         b = _u8(seq)
         out = np.empty(max(b.size, 1), dtype=np.uint64)

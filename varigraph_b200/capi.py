@@ -38,6 +38,8 @@ def _load() -> ctypes.CDLL:
         "vg_ctx_destroy": (c_int, [c_void_p]),
         "vg_ctx_device": (c_int, [c_void_p]),
         "vg_ctx_synchronize": (c_int, [c_void_p]),
+        "vg_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
+        "vg_probe_random_sectors": (c_int, [c_void_p, c_uint64, c_uint32, P(c_double), P(c_double)]),
         "vg_index_create": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, P(c_void_p)]),
         "vg_index_destroy": (c_int, [c_void_p]),
         "vg_index_size": (c_uint64, [c_void_p]),
@@ -96,6 +98,15 @@ class Context:
 
     def synchronize(self) -> None:
         _chk(lib.vg_ctx_synchronize(self._h))
+
+    def set_stream(self, stream: int) -> None:
+        _chk(lib.vg_ctx_set_stream(self._h, c_void_p(stream)))
+
+    def probe_random_sectors(self, table_bytes: int, rounds: int = 64):
+        """-> (GB/s, sectors/s) of uniform random 32-byte gathers over a table of table_bytes."""
+        gb, sec = c_double(0), c_double(0)
+        _chk(lib.vg_probe_random_sectors(self._h, table_bytes, rounds, byref(gb), byref(sec)))
+        return float(gb.value), float(sec.value)
 
     def encode_positions(self, bases, k: int) -> np.ndarray:
         b = _as_u8(bases)

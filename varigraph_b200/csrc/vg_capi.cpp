@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -90,12 +91,18 @@ int vg_ctx_create(int device, int buffer_mb, vg_ctx** out) {
     if (prop.major < 10)
         return fail(VG_E_CUDA, "device %d is sm_%d%d; libvgb200 is built for sm_100a only", device, prop.major,
                     prop.minor);
+    if (const char* e = getenv("VG_L2_FETCH")) {  // tuning knob: L2 fetch granularity hint (32/64/128 bytes)
+        int gran = atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran));
+    }
     vg_ctx* c = new vg_ctx();
     c->device = device;
+    if (const char* e = getenv("VG_CTAS_PER_SM")) c->ctas_per_sm = atoi(e);
     c->nsm = vg::sm_count(device);
     c->chunk_bytes = (size_t)buffer_mb << 20;
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+    c->own_compute_stream = c->compute_stream;
     *out = c;
     return VG_OK;
 }
@@ -123,12 +130,56 @@ int vg_ctx_destroy(vg_ctx* c) {
         cudaEventDestroy(s.done);
     }
     cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->compute_stream);
+    cudaStreamDestroy(c->own_compute_stream);
     delete c;
     return VG_OK;
 }
 
 int vg_ctx_device(const vg_ctx* c) { return c ? c->device : -1; }
+
+int vg_ctx_set_stream(vg_ctx* c, void* cuda_stream) {
+    if (!c) return fail(VG_E_INVALID, "ctx is NULL");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->compute_stream));
+    c->compute_stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_compute_stream;
+    return VG_OK;
+}
+
+int vg_probe_random_sectors(vg_ctx* c, uint64_t table_bytes, uint32_t rounds, double* gbytes_per_s,
+                            double* sectors_per_s) {
+    if (!c) return fail(VG_E_INVALID, "ctx is NULL");
+    if (table_bytes < (1u << 20) || rounds == 0) return fail(VG_E_INVALID, "table too small or rounds == 0");
+    DeviceGuard g(c->device);
+    uint64_t nb = table_bytes / 32;
+    if (nb >= 0xffffffffull) nb = 0xfffffffeull;
+    uint64_t* table = nullptr;
+    unsigned long long* sink = nullptr;
+    CU(cudaMalloc((void**)&table, nb * 32));
+    cudaError_t e = cudaMalloc((void**)&sink, 8);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s = c->compute_stream;
+    int grid = c->nsm * 8;
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaMemsetAsync(table, 0x5a, nb * 32, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sink, 0, 8, s);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = vg::launch_random_sectors(table, (uint32_t)nb, rounds / 4 + 1, grid, sink, s);  // warm-up
+    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+    if (e == cudaSuccess) e = vg::launch_random_sectors(table, (uint32_t)nb, rounds, grid, sink, s);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(table);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(VG_E_CUDA, "vg_probe_random_sectors: %s", cudaGetErrorString(e));
+    double loads = (double)grid * vg::kCtaThreadsHost * (double)rounds * vg::probe_batch();
+    if (sectors_per_s) *sectors_per_s = loads / (ms * 1e-3);
+    if (gbytes_per_s) *gbytes_per_s = loads * 32.0 / (ms * 1e-3) / 1e9;
+    return VG_OK;
+}
 
 int vg_ctx_synchronize(vg_ctx* c) {
     if (!c) return fail(VG_E_INVALID, "ctx is NULL");

@@ -39,14 +39,16 @@ __device__ __forceinline__ void lut_init(uint8_t* lut) {
     __syncthreads();
 }
 
+// The shift-add chains of the reference are products by 2^21-1, 265, 21 and 2^31+1 (mod 2^64, then
+// masked): written as multiplies they cost two IMADs each instead of four shifts and adds.
 __device__ __forceinline__ uint64_t hash64(uint64_t x, uint64_t m) {
-    x = (~x + (x << 21)) & m;
+    x = (x * 0x1FFFFFULL - 1ULL) & m;  // ~x + (x << 21)
     x ^= x >> 24;
-    x = (x + (x << 3) + (x << 8)) & m;
+    x = (x * 265ULL) & m;              // x + (x << 3) + (x << 8)
     x ^= x >> 14;
-    x = (x + (x << 2) + (x << 4)) & m;
+    x = (x * 21ULL) & m;               // x + (x << 2) + (x << 4)
     x ^= x >> 28;
-    x = (x + (x << 31)) & m;
+    x = (x * 0x80000001ULL) & m;       // x + (x << 31)
     return x;
 }
 
@@ -165,37 +167,71 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, int64_t off, const ui
 // For odd k, fwd == rev cannot happen, so "emit at i" == "the k bytes ending at i
 // are all valid".  Each lane owns 16 consecutive positions and borrows the 32 preceding bases
 // from its two left neighbours by shuffle (lanes 0/1 re-read them from memory).
-// keys[j] = hash64(canonical k-mer ending at off + j) or kNoKmer.
-__device__ __forceinline__ void encode_keys_odd(const Chunk& c, int64_t off, const KmerParams& kp,
-                                                const uint8_t* lut, uint64_t (&keys)[16]) {
-    const int lane = threadIdx.x & 31;
-    uint32_t p0, v0;
-    encode_seg(c, off, lut, p0, v0);
-    uint32_t ex = 0, exv = 0;
-    if (lane < 2) encode_seg(c, off - 32, lut, ex, exv);
-    // lane 0 holds segment (warp_off - 32), lane 1 holds segment (warp_off - 16)
-    uint32_t ex0 = __shfl_sync(kFullMask, ex, 0), exv0 = __shfl_sync(kFullMask, exv, 0);
-    uint32_t ex1 = __shfl_sync(kFullMask, ex, 1), exv1 = __shfl_sync(kFullMask, exv, 1);
-    uint32_t p1 = __shfl_up_sync(kFullMask, p0, 1), v1 = __shfl_up_sync(kFullMask, v0, 1);
-    uint32_t p2 = __shfl_up_sync(kFullMask, p0, 2), v2 = __shfl_up_sync(kFullMask, v0, 2);
-    if (lane == 0) { p1 = ex1; v1 = exv1; p2 = ex0; v2 = exv0; }
-    if (lane == 1) { p2 = ex1; v2 = exv1; }
+// Warp-cooperative set-up, then per-lane rolling a few positions at a time so that only one probe
+// batch of keys is live at once (the sector loads in flight per lane are the register budget).
+struct OddEncoder {
+    uint64_t fwd, rev;
+    uint32_t p0;     // own 16 bases, 2 bits each, first base in the top bits
+    uint32_t all_k;  // bit (15 - j): the k bytes ending at own position j are all valid
 
-    const uint32_t k = kp.k;
-    const uint64_t kones = (1ULL << k) - 1;
-    const uint64_t V = ((uint64_t)v2 << 32) | ((uint64_t)v1 << 16) | v0;
-    uint64_t fwd = (((uint64_t)p2 << 32) | p1) & kp.mask;
-    uint64_t rev = revcomp2k(fwd, k);
-    const uint32_t top = 2 * (k - 1);
+    __device__ __forceinline__ void init(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        const int lane = threadIdx.x & 31;
+        uint32_t v0;
+        encode_seg(c, off, lut, p0, v0);
+        uint32_t ex = 0, exv = 0;
+        if (lane < 2) encode_seg(c, off - 32, lut, ex, exv);
+        // lane 0 holds segment (warp_off - 32), lane 1 holds segment (warp_off - 16)
+        uint32_t ex0 = __shfl_sync(kFullMask, ex, 0), exv0 = __shfl_sync(kFullMask, exv, 0);
+        uint32_t ex1 = __shfl_sync(kFullMask, ex, 1), exv1 = __shfl_sync(kFullMask, exv, 1);
+        uint32_t p1 = __shfl_up_sync(kFullMask, p0, 1), v1 = __shfl_up_sync(kFullMask, v0, 1);
+        uint32_t p2 = __shfl_up_sync(kFullMask, p0, 2), v2 = __shfl_up_sync(kFullMask, v0, 2);
+        if (lane == 0) { p1 = ex1; v1 = exv1; p2 = ex0; v2 = exv0; }
+        if (lane == 1) { p2 = ex1; v2 = exv1; }
+        // V: validity of the 48 bases in view, first base in bit 47.  f(n)[i] = bits i..i+n-1 all
+        // set = "the n bytes ending at the base of bit i are valid"; f(a+b) = f(a) & (f(b) >> a),
+        // so f(k) falls out of the binary decomposition of k.
+        const uint64_t V = ((uint64_t)v2 << 32) | ((uint64_t)v1 << 16) | v0;
+        uint64_t pw = V, acc = ~0ULL;
+        uint32_t have = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        uint64_t cb = (p0 >> (30 - 2 * j)) & 3u;
-        fwd = ((fwd << 2) | cb) & kp.mask;
-        rev = (rev >> 2) | ((3ULL ^ cb) << top);
-        bool emit = ((V >> (15 - j)) & kones) == kones;
-        uint64_t canon = fwd < rev ? fwd : rev;
-        keys[j] = emit ? hash64(canon, kp.mask) : kNoKmer;
+        for (int bit = 0; bit < 5; ++bit) {
+            if (kp.k & (1u << bit)) {
+                acc &= pw >> have;
+                have += 1u << bit;
+            }
+            pw &= pw >> (1u << bit);
+        }
+        all_k = (uint32_t)acc & 0xffffu;
+        fwd = (((uint64_t)p2 << 32) | p1) & kp.mask;
+        rev = revcomp2k(fwd, kp.k);
     }
+
+    // Consumes the next N own positions: keys[j] = hash64(canonical k-mer ending there); returns the
+    // N-bit emit mask (bit j: the reference encoder emits; keys[j] is meaningless where it does not).
+    template <int N>
+    __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N]) {
+        const uint32_t top = 2 * (kp.k - 1);
+        uint32_t emit = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            uint64_t cb = p0 >> 30;
+            p0 <<= 2;
+            fwd = ((fwd << 2) | cb) & kp.mask;
+            rev = (rev >> 2) | ((3ULL ^ cb) << top);
+            keys[j] = hash64(fwd < rev ? fwd : rev, kp.mask);
+            emit |= ((all_k >> 15) & 1u) << j;
+            all_k <<= 1;
+        }
+        return emit;
+    }
+};
+
+// Whole segment at once (used where register pressure does not matter).
+__device__ __forceinline__ uint32_t encode_keys_odd(const Chunk& c, int64_t off, const KmerParams& kp,
+                                                    const uint8_t* lut, uint64_t (&keys)[16]) {
+    OddEncoder enc;
+    enc.init(c, off, kp, lut);
+    return enc.next<16>(kp, keys);
 }
 
 // ---- any k: exact state machine with a look-back to a synchronisation point --
@@ -230,11 +266,11 @@ __device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, con
     return lut[c.al[pos]];
 }
 
-__device__ inline void encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
-                                       const uint8_t* lut, uint64_t (&keys)[16]) {
+__device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
+                                           const uint8_t* lut, uint64_t (&keys)[16]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) keys[j] = kNoKmer;
-    if (off >= c.hi || off + kSegBytes <= c.lo) return;
+    for (int j = 0; j < 16; ++j) keys[j] = 0;
+    if (off >= c.hi || off + kSegBytes <= c.lo) return 0;
     const int64_t need = 2 * (int64_t)kp.k;
     RollState st;
     int64_t scan_from = off;  // exclusive upper end of the region still to scan backwards
@@ -274,6 +310,7 @@ __device__ inline void encode_keys_any(const Chunk& c, int64_t off, const KmerPa
         }
         scan_from = start + need - 1;  // look for an earlier synchronisation point
     }
+    uint32_t emit = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         uint32_t e = chunk_entry(c, off + j, lut);
@@ -283,8 +320,12 @@ __device__ inline void encode_keys_any(const Chunk& c, int64_t off, const KmerPa
             continue;
         }
         uint64_t key;
-        if (roll_push(st, e, kp, key)) keys[j] = key;
+        if (roll_push(st, e, kp, key)) {
+            keys[j] = key;
+            emit |= 1u << j;
+        }
     }
+    return emit;
 }
 
 }  // namespace vg

@@ -24,6 +24,7 @@ struct DeviceMisc {  // small device-resident scalars of one index
     unsigned long long special;
 };
 
+constexpr int kCtaThreadsHost = 256;                // == kCtaThreads in vg_device.cuh
 constexpr uint64_t kTilePieceBytes = 64ull << 20;  // multiple of the 4 KiB CTA tile
 
 int fail(int code, const char* fmt, ...);
@@ -33,10 +34,11 @@ int fail(int code, const char* fmt, ...);
 struct vg_ctx {
     int device = 0;
     int nsm = 148;
-    int ctas_per_sm = 4;
+    int ctas_per_sm = 0;  // 0: ask the occupancy calculator
     size_t chunk_bytes = 64u << 20;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t compute_stream = nullptr;
+    cudaStream_t own_compute_stream = nullptr;
     std::vector<vg::StageSlot> ring;
     int next_slot = 0;
 };

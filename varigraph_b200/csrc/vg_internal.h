@@ -52,4 +52,8 @@ cudaError_t launch_cbf_add(const CbfView& cbf, uint32_t k, const uint8_t* d_base
 cudaError_t launch_cbf_query(const CbfView& cbf, const uint64_t* d_keys, uint64_t n, uint8_t* d_count,
                              uint8_t* d_find, cudaStream_t s);
 
+cudaError_t launch_random_sectors(const uint64_t* table, uint32_t nbuckets, uint32_t rounds, int grid,
+                                  unsigned long long* sink, cudaStream_t s);
+int probe_batch();
+
 }  // namespace vg

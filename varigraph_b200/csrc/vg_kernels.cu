@@ -10,6 +10,8 @@
 // Replaces (does not port) src/kmer.cu:39-69, src/fastq_kmer.cu:99-162 (sort + reduce_by_key +
 // host map probes) and src/counting_bloom_filter.cu:5-104 of the reference; results follow the
 // reference CPU path src/kmer.cpp:110-149 + src/fastq_kmer.cpp:126-141.
+#include <cstdlib>
+
 #include "vg_device.cuh"
 #include "vg_internal.h"
 
@@ -75,7 +77,8 @@ __device__ __forceinline__ void slot_sat_add(uint64_t* p, uint64_t seen, uint32_
     }
 }
 
-// key must not be kKey56Max (callers peel that one off), so an empty slot never matches.
+// Slot match for a lookup: key must not be kKey56Max (callers peel that one off), so an empty slot
+// (all ones) never matches.  `seen` gets the matching slot's value.
 __device__ __forceinline__ int match_slot(const uint64_t (&v)[4], uint64_t key, bool& saw_empty, uint64_t& seen) {
     int hs = -1;
     saw_empty = false;
@@ -87,60 +90,104 @@ __device__ __forceinline__ int match_slot(const uint64_t (&v)[4], uint64_t key, 
     return hs;
 }
 
-constexpr int kProbeBatch = 8;  // independent 32-byte sector loads in flight per lane
+constexpr int kProbeBatch = 8;  // sector loads in flight per lane in the microbenchmark and default kernel
 
 // All 32 lanes call this together (ballot / match inside).
-__device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint64_t (&keys)[16],
-                                                uint32_t& n_pos, uint32_t& n_hit) {
-#pragma unroll
-    for (int g = 0; g < 16; g += kProbeBatch) {
-        uint64_t v[kProbeBatch][4];
-        uint32_t bk[kProbeBatch];
+// K1 hands over 8 keys and their emit mask; K2 probes one 32-byte bucket per key with 8 sector
+// loads in flight per lane; K3 adds to the 8-bit counter in the matched slot.  The CAS of a
+// position is issued as soon as its slot is matched but its result is only checked after the
+// whole batch, so the round trips overlap instead of serialising.
+// meta[b]: bit 31 CAS issued, bits 16-23 count seen, bits 8-9 slot in bucket, bits 0-7 amount.
+template <bool kK28, int kBatch>
+__device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint64_t (&keys)[kBatch], uint32_t emit,
+                                                uint32_t& n_hit) {
+    constexpr int kProbeBatch = kBatch;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t bk[kProbeBatch], meta[kProbeBatch];
+    uint64_t prev[kProbeBatch];
+    uint32_t havem = emit & ((1u << kProbeBatch) - 1);
+    if (kK28) {
 #pragma unroll
         for (int b = 0; b < kProbeBatch; ++b) {
-            uint64_t key = keys[g + b];
-            bool have = key != kNoKmer && key != kKey56Max;
-            bk[b] = bucket_of(key, ix.nbuckets);
-            if (have) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
+            if (((havem >> b) & 1u) && keys[b] == kKey56Max) {  // the hash no slot can hold
+                havem &= ~(1u << b);
+                if (ix.has_special) {
+                    atomicAdd(ix.special, 1ull);
+                    n_hit += 1;
+                }
+            }
+        }
+    }
+    {
+        uint64_t v[kProbeBatch][4];
+#pragma unroll
+        for (int b = 0; b < kProbeBatch; ++b) {
+            bk[b] = bucket_of(keys[b], ix.nbuckets);
+            if ((havem >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
         }
 #pragma unroll
         for (int b = 0; b < kProbeBatch; ++b) {
-            uint64_t key = keys[g + b];
-            bool emitted = key != kNoKmer;
-            bool have = emitted && key != kKey56Max;
-            n_pos += emitted ? 1u : 0u;
-            if (emitted && !have && ix.has_special) {  // k == 28 corner: the all-ones hash
-                atomicAdd(ix.special, 1ull);
-                n_hit += 1;
-            }
-            int hs = -1;
-            bool saw_empty = false;
-            uint64_t seen = 0;
-            if (have) hs = match_slot(v[b], key, saw_empty, seen);
-            bool more = have && hs < 0 && !saw_empty;  // bucket full, key may have spilled over
+            const uint64_t key = keys[b];
+            const bool have = (havem >> b) & 1u;
+            const uint32_t want_hi = (uint32_t)(key >> 24);
+            const uint32_t want_lo = (uint32_t)(key << 8);
+            // slot == key<<8 | count  <=>  high words equal and low words differ only in the count byte
+            const bool m0 = (uint32_t)(v[b][0] >> 32) == want_hi && (((uint32_t)v[b][0] ^ want_lo) < 256u);
+            const bool m1 = (uint32_t)(v[b][1] >> 32) == want_hi && (((uint32_t)v[b][1] ^ want_lo) < 256u);
+            const bool m2 = (uint32_t)(v[b][2] >> 32) == want_hi && (((uint32_t)v[b][2] ^ want_lo) < 256u);
+            const bool m3 = (uint32_t)(v[b][3] >> 32) == want_hi && (((uint32_t)v[b][3] ^ want_lo) < 256u);
+            // insertion fills a bucket front to back, so "bucket not full" == "last slot empty"
+            const bool not_full = v[b][3] == kSlotEmpty;
+            bool hit = have && (m0 || m1 || m2 || m3);
+            uint32_t hs = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
+            uint32_t cnt = (m1 ? (uint32_t)v[b][1] : (m2 ? (uint32_t)v[b][2] : (m3 ? (uint32_t)v[b][3] : (uint32_t)v[b][0]))) & 0xffu;
+            bool more = have && !hit && !not_full;  // bucket full: the key may have spilled over
             while (__any_sync(kFullMask, more)) {
                 if (more) {
                     bk[b] = (bk[b] + 1 == ix.nbuckets) ? 0 : bk[b] + 1;
-                    ld_bucket(ix.slots + 4ull * bk[b], v[b]);
-                    hs = match_slot(v[b], key, saw_empty, seen);
-                    more = hs < 0 && !saw_empty;
+                    uint64_t w[4];
+                    ld_bucket(ix.slots + 4ull * bk[b], w);
+                    bool se;
+                    uint64_t sv = 0;
+                    int h2 = match_slot(w, key, se, sv);
+                    if (h2 >= 0) { hit = true; hs = (uint32_t)h2; cnt = (uint32_t)sv & 0xffu; }
+                    more = h2 < 0 && !se;
                 }
             }
-            bool hit = hs >= 0;
-            uint64_t slot = 4ull * bk[b] + (uint32_t)(hit ? hs : 0);
-            uint32_t hm = __ballot_sync(kFullMask, hit);
+            meta[b] = 0;
+            const uint32_t hm = __ballot_sync(kFullMask, hit);
             if (hit) {
                 n_hit += 1;
-                uint32_t peers = (hm & (hm - 1)) ? __match_any_sync(hm, slot) : hm;
-                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-                    slot_sat_add(ix.slots + slot, seen, (uint32_t)__popc(peers));
+                const uint64_t slot = 4ull * bk[b] + hs;
+                const uint32_t peers = (hm & (hm - 1)) ? __match_any_sync(hm, slot) : hm;  // warp-aggregate
+                if ((uint32_t)(__ffs(peers) - 1) == lane && cnt != 255u)
+                    meta[b] = 0x80000000u | (cnt << 16) | (hs << 8) | (uint32_t)__popc(peers);
             }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kProbeBatch; ++b) {
+        if (meta[b] & 0x80000000u) {
+            const uint32_t cnt = (meta[b] >> 16) & 0xffu;
+            const uint64_t seen = (keys[b] << 8) | cnt;
+            const uint32_t add = min(meta[b] & 0xffu, 255u - cnt);
+            prev[b] = atomicCAS((unsigned long long*)(ix.slots + 4ull * bk[b] + ((meta[b] >> 8) & 3u)), seen, seen + add);
+        }
+    }
+    // verify; a lost race (or a key this lane hit twice in the batch) retries here
+#pragma unroll
+    for (int b = 0; b < kProbeBatch; ++b) {
+        if (meta[b] & 0x80000000u) {
+            const uint64_t seen = (keys[b] << 8) | ((meta[b] >> 16) & 0xffu);
+            if (prev[b] != seen)
+                slot_sat_add(ix.slots + 4ull * bk[b] + ((meta[b] >> 8) & 3u), prev[b], meta[b] & 0xffu);
         }
     }
 }
 
-template <bool kOdd>
-__global__ void __launch_bounds__(kCtaThreads) count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
+template <bool kOdd, bool kK28, int kBatch>
+__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
+count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
     __shared__ uint8_t lut[256];
     __shared__ unsigned long long blk[2];
     lut_init(lut);
@@ -150,10 +197,29 @@ __global__ void __launch_bounds__(kCtaThreads) count_kernel(IndexView ix, Chunk 
     uint32_t n_pos = 0, n_hit = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = t * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
-        uint64_t keys[16];
-        if (kOdd) encode_keys_odd(c, off, kp, lut, keys);
-        else encode_keys_any(c, off, kp, lut, keys);
-        probe_and_count(ix, keys, n_pos, n_hit);
+        if (kOdd) {
+            OddEncoder enc;
+            enc.init(c, off, kp, lut);
+            // rolled on purpose: one probe batch of registers, and a loop body that stays in the I-cache
+#pragma unroll 1
+            for (int part = 0; part < 16 / kBatch; ++part) {
+                uint64_t keys[kBatch];
+                uint32_t emit = enc.next<kBatch>(kp, keys);
+                n_pos += __popc(emit);
+                probe_and_count<kK28, kBatch>(ix, keys, emit, n_hit);
+            }
+        } else {
+            uint64_t k16[16];
+            uint32_t emit = encode_keys_any(c, off, kp, lut, k16);
+            n_pos += __popc(emit);
+#pragma unroll
+            for (int part = 0; part < 16 / kBatch; ++part) {
+                uint64_t keys[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) keys[j] = k16[part * kBatch + j];
+                probe_and_count<kK28, kBatch>(ix, keys, (emit >> (part * kBatch)) & ((1u << kBatch) - 1), n_hit);
+            }
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -210,13 +276,12 @@ __global__ void __launch_bounds__(kCtaThreads) positions_kernel(KmerParams kp, C
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = t * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         uint64_t keys[16];
-        if (kOdd) encode_keys_odd(c, off, kp, lut, keys);
-        else encode_keys_any(c, off, kp, lut, keys);
+        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, lut, keys) : encode_keys_any(c, off, kp, lut, keys);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             int64_t p = off + j;
             if (p >= c.lo && p < c.hi)
-                out[p - c.lo] = keys[j] == kNoKmer ? kNoKmer : ((keys[j] << 8) | kp.k);
+                out[p - c.lo] = ((emit >> j) & 1u) ? ((keys[j] << 8) | kp.k) : kNoKmer;
         }
     }
 }
@@ -246,12 +311,11 @@ __global__ void __launch_bounds__(kCtaThreads) cbf_add_kernel(CbfView cbf, KmerP
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         uint64_t keys[16];
-        if (kOdd) encode_keys_odd(c, off, kp, lut, keys);
-        else encode_keys_any(c, off, kp, lut, keys);
+        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, lut, keys) : encode_keys_any(c, off, kp, lut, keys);
+        n += __popc(emit);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            if (keys[j] == kNoKmer) continue;
-            ++n;
+            if (!((emit >> j) & 1u)) continue;
             uint64_t k1 = murmur3_k1((keys[j] << 8) | kp.k);
             for (uint32_t h = 0; h < cbf.num_hashes; ++h)
                 cell_sat_inc(cbf.cells, fastmod64(murmur3_sum_from_k1(k1, cbf.seeds[h]), fm));
@@ -278,6 +342,29 @@ __global__ void cbf_query_kernel(CbfView cbf, const uint64_t* __restrict__ keys,
 }
 
 // ---------------------------------------------------------------------------
+// roofline denominator: uniform random 32-byte sector gathers over a table >> L2
+// (the "random-access HBM peak" BASELINE.json's metric names).  Same load
+// instruction and the same number of loads in flight per lane as probe_and_count.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads) random_sector_kernel(const uint64_t* table, uint32_t nbuckets,
+                                                                  uint32_t rounds, unsigned long long* sink) {
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint64_t v[kProbeBatch][4];
+#pragma unroll
+        for (int b = 0; b < kProbeBatch; ++b) {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;  // xorshift64*
+            uint32_t bk = __umulhi((uint32_t)((x * 0x2545F4914F6CDD1DULL) >> 32), nbuckets);
+            ld_bucket(table + 4ull * bk, v[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < kProbeBatch; ++b) acc ^= v[b][0] ^ v[b][1] ^ v[b][2] ^ v[b][3];
+    }
+    if (acc == 0x0123456789abcdefULL) atomicAdd(sink, 1ull);
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 static inline Chunk make_chunk(const uint8_t* p, uint64_t nbytes) {
@@ -294,6 +381,17 @@ static inline unsigned grid_1d(uint64_t n, unsigned block, unsigned cap) {
     uint64_t g = (n + block - 1) / block;
     if (g < 1) g = 1;
     return (unsigned)(g > cap ? cap : g);
+}
+
+// Tuning knob (not a fallback: every variant is the same CUDA path): VG_COUNT_BATCH=4|8 picks how
+// many sector loads each lane keeps in flight (and with it registers / CTAs per SM).
+int count_variant() {
+    static int v = [] {
+        const char* e = getenv("VG_COUNT_BATCH");
+        int x = e ? atoi(e) : 8;
+        return x == 4 ? 4 : 8;
+    }();
+    return v;
 }
 
 int sm_count(int device) {
@@ -328,10 +426,26 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
     if (nbytes == 0) return cudaSuccess;
     Chunk c = make_chunk(d_bases, nbytes);
     int64_t ntiles = tiles_for(c);
-    int64_t grid = (int64_t)nsm * ctas_per_sm;
+    // persistent grid: exactly the CTAs that are resident at once, each striding over the tiles
+    using KernelT = void (*)(IndexView, Chunk, int64_t, CountStats*);
+    KernelT kern = (ix.k & 1) ? (count_variant() == 4 ? (KernelT)count_kernel<true, false, 4> : (KernelT)count_kernel<true, false, 8>)
+                   : (ix.k == 28 ? (KernelT)count_kernel<false, true, 4> : (KernelT)count_kernel<false, false, 4>);
+    int occ = 0;
+    if (ctas_per_sm <= 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1) occ = 2;
+    } else {
+        occ = ctas_per_sm;
+    }
+    int64_t grid = (int64_t)nsm * occ;
     if (grid > ntiles) grid = ntiles;
-    if (ix.k & 1) count_kernel<true><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
-    else count_kernel<false><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
+    if (ix.k & 1) {
+        if (count_variant() == 4) count_kernel<true, false, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
+        else count_kernel<true, false, 8><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
+    } else if (ix.k == 28) {
+        count_kernel<false, true, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
+    } else {
+        count_kernel<false, false, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
+    }
     return cudaGetLastError();
 }
 
@@ -370,6 +484,13 @@ cudaError_t launch_cbf_add(const CbfView& cbf, uint32_t k, const uint8_t* d_base
     else cbf_add_kernel<false><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
     return cudaGetLastError();
 }
+
+cudaError_t launch_random_sectors(const uint64_t* table, uint32_t nbuckets, uint32_t rounds, int grid,
+                                  unsigned long long* sink, cudaStream_t s) {
+    random_sector_kernel<<<(unsigned)grid, kCtaThreads, 0, s>>>(table, nbuckets, rounds, sink);
+    return cudaGetLastError();
+}
+int probe_batch() { return kProbeBatch; }
 
 cudaError_t launch_cbf_query(const CbfView& cbf, const uint64_t* d_keys, uint64_t n, uint8_t* d_count,
                              uint8_t* d_find, cudaStream_t s) {
