@@ -56,6 +56,8 @@ int vg_index_create(vg_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t k, d
 int vg_index_destroy(vg_index* ix);
 uint64_t vg_index_size(const vg_index* ix);          /* n */
 uint64_t vg_index_table_bytes(const vg_index* ix);   /* bytes of the slot table in HBM */
+uint32_t vg_index_partitions(const vg_index* ix);    /* table slices of the partitioned probe, 0 = direct */
+uint64_t vg_index_launches(const vg_index* ix);      /* kernels launched for this index so far */
 
 /* ---- one sample's count phase ----------------------------------------------------------
  * Together these replace FastqKmer::build_fastq_index (src/fastq_kmer.cpp:41-187) /

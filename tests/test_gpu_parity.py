@@ -208,6 +208,100 @@ def test_index_rejects_bad_keys(ctx, vglib):
     ix.close()
 
 
+# ---- partitioned probing (scatter by table slice, probe slice by slice) -------------------------
+@pytest.fixture
+def force_partition(monkeypatch):
+    """Drive tiny tables through the partitioned path: 4 KiB slices, small rounds, no slack."""
+    def _set(slice_bytes=16384, round_keys=65536, slack=64):
+        monkeypatch.setenv("VG_PARTITION", "1")
+        monkeypatch.setenv("VG_SLICE_BYTES", str(slice_bytes))
+        monkeypatch.setenv("VG_ROUND_KEYS", str(round_keys))
+        monkeypatch.setenv("VG_PART_SLACK", str(slack))
+    return _set
+
+
+@pytest.mark.parametrize("k", [27, 28, 16, 21])
+def test_partitioned_matches_oracle(ctx, vglib, oracle, force_partition, k):
+    force_partition()
+    g = synth.make_genome(120_000, seed=k)
+    lines = synth.random_reads_lines(6000, 150, g, seed=k + 1)
+    pos = oracle.positions(g[:50_000], k)
+    keys = np.unique(pos[pos != NOKMER])
+    ix = vglib.Index(ctx, keys, k)
+    assert ix.partitions >= 8
+    ix.begin()
+    ix.submit(lines)           # 906 KB of bases: many rounds of 64 Ki keys
+    counts, positions, hits = ix.end()
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    assert (positions, hits) == (wpos, whits)
+    assert np.array_equal(counts, want)
+    ix.close()
+
+
+def test_partitioned_golden_tiny_and_files(ctx, vglib, force_partition, tmp_path):
+    force_partition(slice_bytes=4096, round_keys=32768)
+    t = helpers.tiny()
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    assert ix.partitions >= 4
+    ix.begin()
+    ix.submit(t["lines"])
+    counts, _, hits = ix.end()
+    assert np.array_equal(counts, t["counts"]) and hits == int(t["counts"].astype(np.int64).sum())
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    ix.begin()
+    rb = ix.count_files([f1, f2], threads=2)
+    counts2, _, _ = ix.end()
+    assert rb == t["read_bases"] and np.array_equal(counts2, t["counts"])
+    ix.close()
+
+
+def test_partitioned_overflow_and_saturation(ctx, vglib, oracle, force_partition):
+    """Skewed rounds (identical reads) overflow their partition buffers: still exact, still saturating."""
+    force_partition(slice_bytes=4096, round_keys=16384, slack=0)
+    k = 27
+    g = synth.make_genome(3000, seed=9)
+    buf = (g[100:250].tobytes() + b"\n") * 700 + (b"AC" * 75 + b"\n") * 40 + (g[500:650].tobytes() + b"\n") * 254
+    pos = oracle.positions(buf + g.tobytes(), k)
+    keys = np.unique(pos[pos != NOKMER])
+    ix = vglib.Index(ctx, keys, k)
+    assert ix.partitions >= 2
+    ix.begin()
+    ix.submit(buf)
+    counts, positions, hits = ix.end()
+    want, wpos, whits = oracle.count_lines(keys, buf, k)
+    assert counts.max() == 255 and (counts == 254).any()
+    assert np.array_equal(counts, want) and (positions, hits) == (wpos, whits)
+    ix.close()
+
+
+def test_partitioned_equals_direct_at_scale(vglib, monkeypatch):
+    """A table far larger than L2: the default (partitioned) path and forced direct probing agree."""
+    import torch
+    k = 27
+    g = synth.make_genome(12_000_000, seed=31)
+    c = vglib.Context(0, buffer_mb=16)
+    dev_g = torch.from_numpy(g).cuda()
+    allk = torch.empty(g.size, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    c.encode_positions_device(dev_g.data_ptr(), g.size, k, allk.data_ptr())
+    c.synchronize()
+    keys = torch.unique(allk[allk != -1]).cpu().numpy().view(np.uint64)   # ~12M keys -> ~240 MB table
+    lines = synth.random_reads_lines(300_000, 150, g, seed=32)
+    res = []
+    for mode in ("auto", "0"):
+        if mode == "0":
+            monkeypatch.setenv("VG_PARTITION", "0")
+        ix = vglib.Index(c, keys, k)
+        assert (ix.partitions > 0) == (mode == "auto")
+        ix.begin()
+        ix.submit(lines)
+        res.append(ix.end())
+        ix.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+    assert res[0][2] > 0
+    c.close()
+
+
 # ---- the file-level entry point (FastqKmerKernel::build_fastq_index_kernel) ----------------------
 @pytest.mark.parametrize("gz", [True, False])
 def test_count_files_golden_tiny(ctx, vglib, tmp_path, gz):

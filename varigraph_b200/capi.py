@@ -44,6 +44,8 @@ def _load() -> ctypes.CDLL:
         "vg_index_destroy": (c_int, [c_void_p]),
         "vg_index_size": (c_uint64, [c_void_p]),
         "vg_index_table_bytes": (c_uint64, [c_void_p]),
+        "vg_index_partitions": (c_uint32, [c_void_p]),
+        "vg_index_launches": (c_uint64, [c_void_p]),
         "vg_count_begin": (c_int, [c_void_p]),
         "vg_count_submit": (c_int, [c_void_p, c_void_p, c_uint64]),
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
@@ -145,6 +147,14 @@ class Index:
     @property
     def table_bytes(self) -> int:
         return int(lib.vg_index_table_bytes(self._h))
+
+    @property
+    def partitions(self) -> int:
+        return int(lib.vg_index_partitions(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.vg_index_launches(self._h))
 
     def begin(self) -> None:
         _chk(lib.vg_count_begin(self._h))

@@ -53,6 +53,93 @@ struct DeviceGuard {
     }
 };
 
+// ---- partitioned probing: set-up, scatter, flush ---------------------------------------------
+// Used when the slot table is much larger than L2 (direct probing then pays one random DRAM
+// access per k-mer) and the partition count stays within what one CTA tile can scatter well.
+// VG_PARTITION=0 forces direct probing, =1 forces partitioning; VG_SLICE_BYTES / VG_ROUND_KEYS /
+// VG_PART_SLACK tune it (the tests use them to drive tiny tables through every branch).
+static int part_setup(vg_index* ix) {
+    vg_ctx* c = ix->ctx;
+    const char* env = getenv("VG_PARTITION");
+    const int force = env ? atoi(env) : -1;
+    if (force == 0) return VG_OK;
+    const uint64_t table_bytes = 32ull * ix->view.nbuckets;
+    uint64_t slice_bytes = 32ull << 20;
+    if (const char* e = getenv("VG_SLICE_BYTES")) slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
+    uint32_t shift = 0;
+    while ((32ull << (shift + 1)) <= slice_bytes) ++shift;  // buckets per slice = 2^shift
+    const uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
+    if (force != 1 && table_bytes < (96ull << 20)) return VG_OK;  // the table itself lives in L2
+    if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
+    uint64_t round_keys = 256ull << 20, slack = 65536;
+    if (const char* e = getenv("VG_ROUND_KEYS")) round_keys = strtoull(e, nullptr, 10) >= 4096 ? strtoull(e, nullptr, 10) : round_keys;
+    if (const char* e = getenv("VG_PART_SLACK")) slack = strtoull(e, nullptr, 10);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    while (round_keys > (8u << 20) && round_keys * 8 * 9 / 4 > free_b / 3) round_keys >>= 1;
+    round_keys &= ~4095ull;
+    PartState& ps = ix->part;
+    ps.view.P = (uint32_t)P;
+    ps.view.shift = shift;
+    ps.view.cap = (round_keys / P) * 5 / 4 + slack;
+    ps.view.ovf_cap = round_keys;
+    ps.round_keys = round_keys;
+    cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.overflow, ps.view.ovf_cap * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, (P + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), c->compute_stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, (P + 1) * sizeof(unsigned long long), c->compute_stream);
+    if (e != cudaSuccess) {  // not enough memory for the key buffers: fall back to direct probing
+        cudaFree(ps.view.keybuf);
+        cudaFree(ps.view.overflow);
+        cudaFree(ps.view.cursor);
+        cudaFree(ps.view.ctr);
+        ps = PartState();
+        cudaGetLastError();
+        return VG_OK;
+    }
+    ps.enabled = true;
+    return VG_OK;
+}
+
+static int part_flush(vg_index* ix, cudaStream_t s) {
+    PartState& ps = ix->part;
+    if (!ps.enabled || ps.pending == 0) return VG_OK;
+    CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+    ix->launches += ps.view.P + 2;
+    ps.pending = 0;
+    return VG_OK;
+}
+
+// Count every k-mer of a device-resident chunk on stream s (direct or partitioned).
+static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nbytes, cudaStream_t s) {
+    vg_ctx* c = ix->ctx;
+    PartState& ps = ix->part;
+    if (!ps.enabled) {
+        CU(vg::launch_count(ix->view, d_bases, nbytes, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, s));
+        ix->launches += 1;
+        return VG_OK;
+    }
+    const int64_t tile_bytes = 4096;
+    const int64_t T = vg::chunk_tiles(d_bases, nbytes);
+    int64_t t = 0;
+    while (t < T) {
+        int64_t room = (int64_t)((ps.round_keys - ps.pending) / tile_bytes);
+        if (room < 64 && ps.pending) {
+            int rc = part_flush(ix, s);
+            if (rc) return rc;
+            room = (int64_t)(ps.round_keys / tile_bytes);
+        }
+        const int64_t nt = std::min<int64_t>(T - t, room);
+        CU(vg::launch_scatter(ix->view, ps.view, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s));
+        ix->launches += 1;
+        ps.pending += (uint64_t)nt * tile_bytes;
+        t += nt;
+    }
+    return VG_OK;
+}
+
 // Enqueue one staged piece that already sits in ring slot `si`'s pinned buffer (or at `src`).
 int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
     vg_ctx* c = ix->ctx;
@@ -60,10 +147,10 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
     CU(cudaMemcpyAsync(sl.d_buf, src, len, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(sl.copied, c->copy_stream));
     CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
-    CU(vg::launch_count(ix->view, sl.d_buf, len, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, c->compute_stream));
+    int rc = count_device_chunk(ix, sl.d_buf, len, c->compute_stream);
+    if (rc) return rc;
     CU(cudaEventRecord(sl.done, c->compute_stream));
     sl.busy = true;
-    ix->launches += 1;
     return VG_OK;
 }
 
@@ -196,7 +283,7 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     if (!c || !out || (!keys && n)) return fail(VG_E_INVALID, "vg_index_create: NULL argument");
     *out = nullptr;
     if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28 (reference asserts k<=28, src/kmer.cpp:124)", k);
-    if (load_factor <= 0) load_factor = 0.4;
+    if (load_factor <= 0) load_factor = 0.3;
     if (load_factor > 0.9) return fail(VG_E_INVALID, "load_factor %.3f > 0.9", load_factor);
     DeviceGuard g(c->device);
     uint64_t nb64 = (uint64_t)((double)n / (4.0 * load_factor)) + 1;
@@ -257,6 +344,8 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     if (misc.report.failed) return bail(fail(VG_E_NOMEM, "index build: %llu keys found no slot", misc.report.failed));
     ix->duplicates = misc.report.duplicates;
 #undef CUB
+    int prc = part_setup(ix);
+    if (prc != VG_OK) return bail(prc);
     *out = ix;
     return VG_OK;
 }
@@ -269,11 +358,17 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->d_key56);
     cudaFree(ix->d_counts);
     cudaFree(ix->d_misc);
+    cudaFree(ix->part.view.keybuf);
+    cudaFree(ix->part.view.overflow);
+    cudaFree(ix->part.view.cursor);
+    cudaFree(ix->part.view.ctr);
     delete ix;
     return VG_OK;
 }
 
 uint64_t vg_index_size(const vg_index* ix) { return ix ? ix->n : 0; }
+uint32_t vg_index_partitions(const vg_index* ix) { return ix && ix->part.enabled ? ix->part.view.P : 0; }
+uint64_t vg_index_launches(const vg_index* ix) { return ix ? ix->launches : 0; }
 uint64_t vg_index_table_bytes(const vg_index* ix) { return ix ? 32ull * ix->view.nbuckets : 0; }
 
 // ---------------------------------------------------------------------------
@@ -285,6 +380,10 @@ int vg_count_begin(vg_index* ix) {
     DeviceGuard g(c->device);
     CU(vg::launch_clear_counts(ix->view, c->compute_stream));
     CU(cudaMemsetAsync(&ix->d_misc->stats, 0, sizeof(vg::CountStats), c->compute_stream));
+    if (ix->part.enabled) {
+        CU(cudaMemsetAsync(ix->part.view.cursor, 0, (ix->part.view.P + 1) * sizeof(unsigned long long), c->compute_stream));
+        ix->part.pending = 0;
+    }
     ix->counting = true;
     return VG_OK;
 }
@@ -303,9 +402,9 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
         CU(cudaEventDestroy(ev));
         ix->foreign_streams = true;
     }
-    CU(vg::launch_count(ix->view, (const uint8_t*)dev_bases, nbytes, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, s));
-    ix->launches += 1;
-    return VG_OK;
+    if (ix->part.enabled && s != c->compute_stream)
+        return fail(VG_E_INVALID, "a partitioned index counts on the context stream only: use vg_ctx_set_stream");
+    return count_device_chunk(ix, (const uint8_t*)dev_bases, nbytes, s);
 }
 
 int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
@@ -351,6 +450,10 @@ int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits) {
     DeviceGuard g(c->device);
     if (ix->foreign_streams) CU(cudaDeviceSynchronize());
     CU(cudaStreamSynchronize(c->copy_stream));
+    {
+        int frc = part_flush(ix, c->compute_stream);
+        if (frc) return frc;
+    }
     CU(cudaStreamSynchronize(c->compute_stream));
     vg::CountStats st;
     CU(cudaMemcpy(&st, &ix->d_misc->stats, sizeof st, cudaMemcpyDeviceToHost));
@@ -365,6 +468,10 @@ int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* c
     vg_ctx* c = ix->ctx;
     DeviceGuard g(c->device);
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
+    {
+        int frc = part_flush(ix, c->compute_stream);
+        if (frc) return frc;
+    }
     if (cuda_stream) {  // counting kernels submitted through the context must finish first
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->compute_stream));

@@ -43,8 +43,17 @@ struct vg_ctx {
     int next_slot = 0;
 };
 
+// Host-side state of the partitioned probing path of one index.
+struct PartState {
+    bool enabled = false;
+    vg::PartView view{};
+    uint64_t round_keys = 0;   // keys a round may accumulate before it must be probed
+    uint64_t pending = 0;      // upper bound of keys scattered since the last probe pass
+};
+
 struct vg_index {
     vg_ctx* ctx = nullptr;
+    PartState part;
     uint64_t n = 0;
     vg::IndexView view{};
     uint64_t* d_key56 = nullptr;   // key order given at create, hash only (key >> 8)

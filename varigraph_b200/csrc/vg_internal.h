@@ -24,6 +24,22 @@ struct InsertReport {               // lives in device memory
     unsigned long long failed;
 };
 
+// Partitioned probing ("accumulate, then probe one L2-sized slice of the table at a time").
+// Keys of a round are scattered by table slice (partition = home bucket >> shift); each slice
+// is then streamed into L2 once and probed by all of its keys, so index probes and counter
+// updates hit L2 instead of paying one random DRAM access each.
+struct PartView {
+    uint64_t* keybuf;               // P partitions x cap hashes (key >> 8)
+    uint64_t* overflow;             // keys whose partition was full (probed directly afterwards)
+    unsigned long long* cursor;     // P fill counts, then the overflow count at [P]
+    uint32_t P;
+    uint32_t shift;                 // partition = bucket >> shift
+    uint64_t cap;                   // capacity of one partition
+    uint64_t ovf_cap;
+    uint32_t* ctr;                  // 2 x (4 << shift) u32 side counters: hits of the slice being probed
+};
+constexpr uint32_t kMaxPartitions = 256;
+
 struct CbfView {
     uint8_t* cells;                 // m saturating u8 counters
     uint64_t m;
@@ -40,6 +56,13 @@ cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
                          int ctas_per_sm, int nsm, cudaStream_t s);
+// Scatter the k-mers ending in tiles [first_tile, first_tile + ntiles) of the chunk (d_bases, nbytes)
+// into the partition buffers; launch_probe_partitions then probes every partition and resets them.
+cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_t* d_bases, uint64_t nbytes,
+                           int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm, cudaStream_t s);
+cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
+                                    cudaStream_t s);
+int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
                            int out_elem_bytes, cudaStream_t s);
 cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes, uint64_t* d_out,

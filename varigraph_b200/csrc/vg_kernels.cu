@@ -92,23 +92,34 @@ __device__ __forceinline__ int match_slot(const uint64_t (&v)[4], uint64_t key, 
 
 constexpr int kProbeBatch = 8;  // sector loads in flight per lane in the microbenchmark and default kernel
 
+template <int N, typename T>
+__device__ __forceinline__ T pick(const T (&a)[N], uint32_t i) {  // a[i] without local memory
+    T r = a[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) r = (i == (uint32_t)j) ? a[j] : r;
+    return r;
+}
+
 // All 32 lanes call this together (ballot / match inside).
-// K1 hands over 8 keys and their emit mask; K2 probes one 32-byte bucket per key with 8 sector
-// loads in flight per lane; K3 adds to the 8-bit counter in the matched slot.  The CAS of a
-// position is issued as soon as its slot is matched but its result is only checked after the
-// whole batch, so the round trips overlap instead of serialising.
-// meta[b]: bit 31 CAS issued, bits 16-23 count seen, bits 8-9 slot in bucket, bits 0-7 amount.
+// K1 hands over kBatch keys and their emit mask; K2 probes one 32-byte bucket per key with kBatch
+// sector loads in flight per lane; K3 adds to the 8-bit counter in the matched slot.
+//  * A key whose home bucket is full and holds no match may have spilled into the next bucket.
+//    That is rare per key but near-certain per warp, so those probes are finished in ONE
+//    out-of-line loop per batch instead of one warp-wide loop per position.
+//  * The CAS of a position is issued as soon as the batch is matched; its result is only checked
+//    after all of them are in flight, so the round trips overlap instead of serialising.
+// st[b]: bit 31 hit, bits 16-23 count seen, bits 8-9 slot in bucket; later bit 30 CAS issued and
+// bits 0-7 the amount to add.
 template <bool kK28, int kBatch>
 __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint64_t (&keys)[kBatch], uint32_t emit,
                                                 uint32_t& n_hit) {
-    constexpr int kProbeBatch = kBatch;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t bk[kProbeBatch], meta[kProbeBatch];
-    uint64_t prev[kProbeBatch];
-    uint32_t havem = emit & ((1u << kProbeBatch) - 1);
+    uint32_t bk[kBatch], st[kBatch];
+    uint64_t prev[kBatch];
+    uint32_t havem = emit & ((1u << kBatch) - 1);
     if (kK28) {
 #pragma unroll
-        for (int b = 0; b < kProbeBatch; ++b) {
+        for (int b = 0; b < kBatch; ++b) {
             if (((havem >> b) & 1u) && keys[b] == kKey56Max) {  // the hash no slot can hold
                 havem &= ~(1u << b);
                 if (ix.has_special) {
@@ -118,15 +129,16 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
             }
         }
     }
+    uint32_t pend = 0;  // positions whose search continues in the next bucket
     {
-        uint64_t v[kProbeBatch][4];
+        uint64_t v[kBatch][4];
 #pragma unroll
-        for (int b = 0; b < kProbeBatch; ++b) {
+        for (int b = 0; b < kBatch; ++b) {
             bk[b] = bucket_of(keys[b], ix.nbuckets);
             if ((havem >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
         }
 #pragma unroll
-        for (int b = 0; b < kProbeBatch; ++b) {
+        for (int b = 0; b < kBatch; ++b) {
             const uint64_t key = keys[b];
             const bool have = (havem >> b) & 1u;
             const uint32_t want_hi = (uint32_t)(key >> 24);
@@ -137,50 +149,62 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
             const bool m2 = (uint32_t)(v[b][2] >> 32) == want_hi && (((uint32_t)v[b][2] ^ want_lo) < 256u);
             const bool m3 = (uint32_t)(v[b][3] >> 32) == want_hi && (((uint32_t)v[b][3] ^ want_lo) < 256u);
             // insertion fills a bucket front to back, so "bucket not full" == "last slot empty"
-            const bool not_full = v[b][3] == kSlotEmpty;
-            bool hit = have && (m0 || m1 || m2 || m3);
-            uint32_t hs = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
-            uint32_t cnt = (m1 ? (uint32_t)v[b][1] : (m2 ? (uint32_t)v[b][2] : (m3 ? (uint32_t)v[b][3] : (uint32_t)v[b][0]))) & 0xffu;
-            bool more = have && !hit && !not_full;  // bucket full: the key may have spilled over
-            while (__any_sync(kFullMask, more)) {
-                if (more) {
-                    bk[b] = (bk[b] + 1 == ix.nbuckets) ? 0 : bk[b] + 1;
-                    uint64_t w[4];
-                    ld_bucket(ix.slots + 4ull * bk[b], w);
-                    bool se;
-                    uint64_t sv = 0;
-                    int h2 = match_slot(w, key, se, sv);
-                    if (h2 >= 0) { hit = true; hs = (uint32_t)h2; cnt = (uint32_t)sv & 0xffu; }
-                    more = h2 < 0 && !se;
-                }
-            }
-            meta[b] = 0;
-            const uint32_t hm = __ballot_sync(kFullMask, hit);
-            if (hit) {
-                n_hit += 1;
-                const uint64_t slot = 4ull * bk[b] + hs;
-                const uint32_t peers = (hm & (hm - 1)) ? __match_any_sync(hm, slot) : hm;  // warp-aggregate
-                if ((uint32_t)(__ffs(peers) - 1) == lane && cnt != 255u)
-                    meta[b] = 0x80000000u | (cnt << 16) | (hs << 8) | (uint32_t)__popc(peers);
-            }
+            const bool full = v[b][3] != kSlotEmpty;
+            const bool hit = have && (m0 || m1 || m2 || m3);
+            const uint32_t hs = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
+            const uint32_t lo = m1 ? (uint32_t)v[b][1] : (m2 ? (uint32_t)v[b][2] : (m3 ? (uint32_t)v[b][3] : (uint32_t)v[b][0]));
+            st[b] = hit ? (0x80000000u | ((lo & 0xffu) << 16) | (hs << 8)) : 0u;
+            if (have && !hit && full) pend |= 1u << b;
         }
     }
+    while (__any_sync(kFullMask, pend != 0)) {
+        if (pend) {
+            const uint32_t b = (uint32_t)__ffs(pend) - 1;
+            const uint64_t key = pick<kBatch>(keys, b);
+            uint32_t nb = pick<kBatch>(bk, b) + 1;
+            if (nb == ix.nbuckets) nb = 0;
+            uint64_t w[4];
+            ld_bucket(ix.slots + 4ull * nb, w);
+            bool saw_empty;
+            uint64_t sv = 0;
+            const int h2 = match_slot(w, key, saw_empty, sv);
+            const uint32_t ns = h2 >= 0 ? (0x80000000u | (((uint32_t)sv & 0xffu) << 16) | ((uint32_t)h2 << 8)) : 0u;
 #pragma unroll
-    for (int b = 0; b < kProbeBatch; ++b) {
-        if (meta[b] & 0x80000000u) {
-            const uint32_t cnt = (meta[b] >> 16) & 0xffu;
-            const uint64_t seen = (keys[b] << 8) | cnt;
-            const uint32_t add = min(meta[b] & 0xffu, 255u - cnt);
-            prev[b] = atomicCAS((unsigned long long*)(ix.slots + 4ull * bk[b] + ((meta[b] >> 8) & 3u)), seen, seen + add);
+            for (int j = 0; j < kBatch; ++j) {
+                if (b == (uint32_t)j) {
+                    bk[j] = nb;
+                    st[j] = ns;
+                }
+            }
+            if (h2 >= 0 || saw_empty) pend &= pend - 1;  // resolved; otherwise keep walking
+        }
+    }
+    // K3: warp-aggregated saturating add; one CAS per distinct slot per position step
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+        const bool hit = st[b] >> 31;
+        const uint32_t hm = __ballot_sync(kFullMask, hit);
+        if (hit) {
+            n_hit += 1;
+            const uint32_t hs = (st[b] >> 8) & 3u, cnt = (st[b] >> 16) & 0xffu;
+            const uint64_t slot = 4ull * bk[b] + hs;
+            const uint32_t peers = (hm & (hm - 1)) ? __match_any_sync(hm, slot) : hm;
+            st[b] &= ~0x400000ffu;
+            if ((uint32_t)(__ffs(peers) - 1) == lane && cnt != 255u) {
+                const uint32_t add = min((uint32_t)__popc(peers), 255u - cnt);
+                const uint64_t seen = (keys[b] << 8) | cnt;
+                prev[b] = atomicCAS((unsigned long long*)(ix.slots + slot), seen, seen + add);
+                st[b] |= 0x40000000u | (uint32_t)__popc(peers);
+            }
         }
     }
     // verify; a lost race (or a key this lane hit twice in the batch) retries here
 #pragma unroll
-    for (int b = 0; b < kProbeBatch; ++b) {
-        if (meta[b] & 0x80000000u) {
-            const uint64_t seen = (keys[b] << 8) | ((meta[b] >> 16) & 0xffu);
+    for (int b = 0; b < kBatch; ++b) {
+        if (st[b] & 0x40000000u) {
+            const uint64_t seen = (keys[b] << 8) | ((st[b] >> 16) & 0xffu);
             if (prev[b] != seen)
-                slot_sat_add(ix.slots + 4ull * bk[b] + ((meta[b] >> 8) & 3u), prev[b], meta[b] & 0xffu);
+                slot_sat_add(ix.slots + 4ull * bk[b] + ((st[b] >> 8) & 3u), prev[b], st[b] & 0xffu);
         }
     }
 }
@@ -235,6 +259,327 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
         atomicAdd(&stats->positions, blk[0]);
         atomicAdd(&stats->hits, blk[1]);
     }
+}
+
+// ---------------------------------------------------------------------------
+// partitioned probing: scatter by table slice, then probe slice by slice out of L2
+// ---------------------------------------------------------------------------
+constexpr int kTileKeys = kCtaThreads * kSegBytes;  // at most one key per byte of a CTA tile
+
+struct ScatterSmem {
+    uint64_t key[kTileKeys];
+    uint16_t pid[kTileKeys];
+    uint32_t hist[kMaxPartitions];
+    uint32_t off[kMaxPartitions];
+    uint32_t fit[kMaxPartitions];
+    unsigned long long base[kMaxPartitions];
+    uint32_t total;
+    uint8_t lut[256];
+};
+
+template <bool kOdd, bool kK28>
+__global__ void __launch_bounds__(kCtaThreads, 3)
+scatter_kernel(IndexView ix, PartView pv, Chunk c, int64_t first_tile, int64_t ntiles, CountStats* stats) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
+    __shared__ unsigned long long blk_pos;
+    lut_init(sm.lut);
+    if (threadIdx.x == 0) blk_pos = 0;
+    KmerParams kp{ix.k, ix.mask};
+    const uint32_t P = pv.P;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t n_pos = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sm.hist[i] = 0;
+        __syncthreads();
+        // phase 1: encode; rank every emitted key inside its partition (order within a tile is free)
+        const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
+        uint64_t keys[16];
+        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, sm.lut, keys) : encode_keys_any(c, off, kp, sm.lut, keys);
+        n_pos += __popc(emit);
+        uint32_t where[16];  // partition << 12 | rank
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            where[j] = 0;
+            if ((emit >> j) & 1u) {
+                if (kK28 && keys[j] == kKey56Max) {  // the hash no slot can hold: counted beside the table
+                    emit &= ~(1u << j);
+                    if (ix.has_special) {
+                        atomicAdd(ix.special, 1ull);
+                        atomicAdd(&stats->hits, 1ull);
+                    }
+                    continue;
+                }
+                const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
+                where[j] = (p << 12) | atomicAdd(&sm.hist[p], 1u);
+            }
+        }
+        __syncthreads();
+        // phase 2: offsets inside the tile (warp 0) and space in the global partition buffers
+        if (warp == 0) {
+            uint32_t loc[kMaxPartitions / 32], sum = 0;
+#pragma unroll
+            for (int i = 0; i < (int)(kMaxPartitions / 32); ++i) {
+                const uint32_t idx = lane * (kMaxPartitions / 32) + i;
+                loc[i] = sum;
+                sum += idx < P ? sm.hist[idx] : 0u;
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(kFullMask, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            const uint32_t excl = incl - sum;
+#pragma unroll
+            for (int i = 0; i < (int)(kMaxPartitions / 32); ++i) {
+                const uint32_t idx = lane * (kMaxPartitions / 32) + i;
+                if (idx < P) sm.off[idx] = excl + loc[i];
+            }
+            if (lane == 31) sm.total = incl;
+        }
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+            const uint32_t cnt = sm.hist[i];
+            unsigned long long b = 0;
+            uint32_t fit = 0;
+            if (cnt) {
+                b = atomicAdd(&pv.cursor[i], (unsigned long long)cnt);
+                fit = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)cnt, pv.cap - b);
+            }
+            sm.base[i] = b;
+            sm.fit[i] = fit;
+        }
+        __syncthreads();
+        // phase 3: tile-local sort by partition in shared memory
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if ((emit >> j) & 1u) {
+                const uint32_t p = where[j] >> 12;
+                const uint32_t dst = sm.off[p] + (where[j] & 0xfffu);
+                sm.key[dst] = keys[j];
+                sm.pid[dst] = (uint16_t)p;
+            }
+        }
+        __syncthreads();
+        // phase 4: coalesced copy-out, partition runs are contiguous on both sides
+        const uint32_t total = sm.total;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t p = sm.pid[i];
+            const uint32_t r = i - sm.off[p];
+            const uint64_t key = sm.key[i];
+            if (r < sm.fit[p]) {
+                pv.keybuf[(uint64_t)p * pv.cap + sm.base[p] + r] = key;
+            } else {  // partition full: an adversarial or very skewed round; still counted exactly
+                const unsigned long long o = atomicAdd(&pv.cursor[P], 1ull);
+                if (o < pv.ovf_cap) pv.overflow[o] = key;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_pos += __shfl_xor_sync(kFullMask, n_pos, d);
+    if (lane == 0 && n_pos) atomicAdd(&blk_pos, (unsigned long long)n_pos);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_pos) atomicAdd(&stats->positions, blk_pos);
+}
+
+__device__ __forceinline__ uint64_t ld_key_stream(const uint64_t* p) {
+    uint64_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+
+// K2 + K3 of the partitioned path.  All probes of a key list fall into one L2-resident slice of the
+// table [b0, b1), so a hit is recorded with a fire-and-forget 32-bit reduction into the slice's
+// side counters (also L2-resident) instead of a CAS round trip; retire_slice folds them into the
+// saturating 8-bit slot counters once the slice has been probed by every key of the round.
+// A hit outside the slice (a key that spilled over the slice edge) takes the CAS path.
+template <int kBatch>
+__device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_t (&keys)[kBatch], uint32_t emit,
+                                              uint32_t b0, uint32_t b1, uint32_t* ctr, uint32_t& n_hit) {
+    uint32_t bk[kBatch], st[kBatch];  // st: bit 31 hit, bit 30 counter already saturated, bits 0-1 slot
+    uint32_t pend = 0;                // positions whose search continues in the next bucket
+    {
+        uint64_t v[kBatch][4];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            bk[b] = bucket_of(keys[b], ix.nbuckets);
+            if ((emit >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const uint64_t key = keys[b];
+            const bool have = (emit >> b) & 1u;
+            const uint32_t want_hi = (uint32_t)(key >> 24);
+            const uint32_t want_lo = (uint32_t)(key << 8);
+            const uint32_t d0 = (uint32_t)v[b][0] ^ want_lo, d1 = (uint32_t)v[b][1] ^ want_lo;
+            const uint32_t d2 = (uint32_t)v[b][2] ^ want_lo, d3 = (uint32_t)v[b][3] ^ want_lo;
+            const bool m0 = (uint32_t)(v[b][0] >> 32) == want_hi && d0 < 256u;
+            const bool m1 = (uint32_t)(v[b][1] >> 32) == want_hi && d1 < 256u;
+            const bool m2 = (uint32_t)(v[b][2] >> 32) == want_hi && d2 < 256u;
+            const bool m3 = (uint32_t)(v[b][3] >> 32) == want_hi && d3 < 256u;
+            const bool full = v[b][3] != kSlotEmpty;  // buckets fill front to back
+            const bool hit = have && (m0 || m1 || m2 || m3);
+            const uint32_t hs = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
+            const uint32_t cnt = m1 ? d1 : (m2 ? d2 : (m3 ? d3 : d0));  // want_lo's low byte is 0: d == count
+            st[b] = hit ? (0x80000000u | (cnt == 255u ? 0x40000000u : 0u) | hs) : 0u;
+            if (have && !hit && full) pend |= 1u << b;
+        }
+    }
+    while (__any_sync(kFullMask, pend != 0)) {
+        if (pend) {
+            const uint32_t b = (uint32_t)__ffs(pend) - 1;
+            const uint64_t key = pick<kBatch>(keys, b);
+            uint32_t nb = pick<kBatch>(bk, b) + 1;
+            if (nb == ix.nbuckets) nb = 0;
+            uint64_t w[4];
+            ld_bucket(ix.slots + 4ull * nb, w);
+            bool saw_empty;
+            uint64_t sv = 0;
+            const int h2 = match_slot(w, key, saw_empty, sv);
+            const uint32_t ns = h2 >= 0 ? (0x80000000u | (((uint32_t)sv & 0xffu) == 255u ? 0x40000000u : 0u) | (uint32_t)h2) : 0u;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                if (b == (uint32_t)j) {
+                    bk[j] = nb;
+                    st[j] = ns;
+                }
+            }
+            if (h2 >= 0 || saw_empty) pend &= pend - 1;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+        if (st[b] >> 31) {
+            n_hit += 1;
+            if (!(st[b] & 0x40000000u)) {  // saturation is absorbing: nothing left to add
+                const uint32_t hs = st[b] & 3u;
+                if (bk[b] >= b0 && bk[b] < b1) {
+                    atomicAdd(ctr + (size_t)(bk[b] - b0) * 4 + hs, 1u);  // result unused: a RED, no round trip
+                } else {
+                    uint64_t* p = ix.slots + 4ull * bk[b] + hs;
+                    slot_sat_add(p, *(volatile uint64_t*)p, 1u);
+                }
+            }
+        }
+    }
+}
+
+// Folds the side counters of slice [b0, b1) into its slots: count = min(255, count + hits).
+// One bucket (32-byte sector of slots + 16 bytes of counters) per thread and step; plain stores are
+// safe because nothing else touches a slice while it is retired (the sweep needs >= 3 slices, so a
+// key spilling over the table's end never lands in the slice being retired).
+__device__ __forceinline__ void retire_slice(const IndexView& ix, uint32_t b0, uint32_t b1, uint32_t* ctr) {
+    const uint64_t nb = b1 - b0;
+    uint64_t* slots = ix.slots + 4ull * b0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) {
+        const uint4 c = *reinterpret_cast<const uint4*>(ctr + 4 * i);
+        if (c.x | c.y | c.z | c.w) {
+            uint64_t v[4];
+            ld_bucket(slots + 4 * i, v);
+            const uint32_t cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t cnt = (uint32_t)(v[j] & 0xffu);
+                v[j] = (v[j] & ~0xffULL) | (uint64_t)min(255u, cnt + min(cs[j], 255u));
+            }
+            asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(slots + 4 * i), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+            *reinterpret_cast<uint4*>(ctr + 4 * i) = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// One step of the partition sweep: retire the previous slice [r0, r1) (its side counters are in
+// ctr_prev), pull slice [b0, b1) into L2 with sequential prefetches, then probe the slice's key
+// list into ctr_cur.  Either part may be empty.
+template <int kBatch>
+__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
+probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsigned long long* count_ptr, uint64_t cap,
+                   uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0, uint32_t r1, uint32_t* ctr_prev,
+                   CountStats* stats) {
+    __shared__ unsigned long long blk_hit;
+    if (threadIdx.x == 0) blk_hit = 0;
+    {
+        const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const uint64_t gsz = (uint64_t)gridDim.x * blockDim.x;
+        const char* tbl = (const char*)ix.slots;
+        for (uint64_t line = (uint64_t)b0 * 32 / 128 + gtid; line * 128 < (uint64_t)b1 * 32; line += gsz)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + line * 128));
+    }
+    if (r1 > r0) retire_slice(ix, r0, r1, ctr_prev);
+    __syncthreads();
+    const uint64_t n = b1 > b0 ? min((uint64_t)*count_ptr, cap) : 0;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr uint64_t kPerWarp = 32ull * kBatch;
+    uint32_t n_hit = 0;
+    uint64_t keys[kBatch], next[kBatch];
+    auto fetch = [&](uint64_t base, uint64_t (&dst)[kBatch]) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const uint64_t idx = base + (uint64_t)b * 32 + lane;
+            dst[b] = 0;
+            if (idx < n) {
+                dst[b] = ld_key_stream(list + idx);
+                e |= 1u << b;
+            }
+        }
+        return e;
+    };
+    uint64_t base = warp_gid * kPerWarp;
+    uint32_t emit = base < n ? fetch(base, keys) : 0u;
+    for (; base < n; base += nwarps * kPerWarp) {
+        // the next batch of keys streams in from HBM while this one is probed out of L2
+        const uint64_t nbase = base + nwarps * kPerWarp;
+        const uint32_t nemit = nbase < n ? fetch(nbase, next) : 0u;
+        probe_and_red<kBatch>(ix, keys, emit, b0, b1, ctr_cur, n_hit);
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) keys[b] = next[b];
+        emit = nemit;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_hit += __shfl_xor_sync(kFullMask, n_hit, d);
+    if (lane == 0 && n_hit) atomicAdd(&blk_hit, (unsigned long long)n_hit);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_hit) atomicAdd(&stats->hits, blk_hit);
+}
+
+// The overflow list (keys whose partition buffer was full) is probed directly, CAS path.
+template <int kBatch>
+__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
+probe_list_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsigned long long* count_ptr, uint64_t cap,
+                  CountStats* stats) {
+    __shared__ unsigned long long blk_hit;
+    if (threadIdx.x == 0) blk_hit = 0;
+    __syncthreads();
+    const uint64_t n = min((uint64_t)*count_ptr, cap);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr uint64_t kPerWarp = 32ull * kBatch;
+    uint32_t n_hit = 0;
+    for (uint64_t base = warp_gid * kPerWarp; base < n; base += nwarps * kPerWarp) {
+        uint64_t keys[kBatch];
+        uint32_t emit = 0;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const uint64_t idx = base + (uint64_t)b * 32 + lane;
+            keys[b] = 0;
+            if (idx < n) {
+                keys[b] = ld_key_stream(list + idx);
+                emit |= 1u << b;
+            }
+        }
+        probe_and_count<false, kBatch>(ix, keys, emit, n_hit);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_hit += __shfl_xor_sync(kFullMask, n_hit, d);
+    if (lane == 0 && n_hit) atomicAdd(&blk_hit, (unsigned long long)n_hit);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_hit) atomicAdd(&stats->hits, blk_hit);
 }
 
 // ---------------------------------------------------------------------------
@@ -447,6 +792,64 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
         count_kernel<false, false, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
     }
     return cudaGetLastError();
+}
+
+int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes) { return tiles_for(make_chunk(d_bases, nbytes)); }
+
+cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_t* d_bases, uint64_t nbytes,
+                           int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm, cudaStream_t s) {
+    if (ntiles <= 0) return cudaSuccess;
+    Chunk c = make_chunk(d_bases, nbytes);
+    using KernelT = void (*)(IndexView, PartView, Chunk, int64_t, int64_t, CountStats*);
+    KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true, false>
+                              : (ix.k == 28 ? (KernelT)scatter_kernel<false, true> : (KernelT)scatter_kernel<false, false>);
+    static bool attr_set[3] = {false, false, false};
+    const int which = (ix.k & 1) ? 0 : (ix.k == 28 ? 1 : 2);
+    const size_t smem = sizeof(ScatterSmem);
+    if (!attr_set[which]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[which] = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t grid = (int64_t)nsm * occ;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, kCtaThreads, smem, s>>>(ix, pv, c, first_tile, ntiles, d_stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
+                                    cudaStream_t s) {
+    const bool b4 = count_variant() == 4;
+    int occ = 0;
+    auto slice = [&](uint32_t p, uint32_t& b0, uint32_t& b1) {
+        b0 = p << pv.shift;
+        const uint64_t e = ((uint64_t)(p + 1)) << pv.shift;
+        b1 = (uint32_t)(e > ix.nbuckets ? ix.nbuckets : e);
+    };
+    const size_t ctr_elems = (size_t)4 << pv.shift;
+    // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice
+    for (uint32_t p = 0; p <= pv.P; ++p) {
+        uint32_t b0 = 0, b1 = 0, r0 = 0, r1 = 0;
+        if (p < pv.P) slice(p, b0, b1);
+        if (p > 0) slice(p - 1, r0, r1);
+        uint32_t* cur = pv.ctr + (size_t)(p & 1) * ctr_elems;
+        uint32_t* prv = pv.ctr + (size_t)((p + 1) & 1) * ctr_elems;
+        const uint64_t* list = pv.keybuf + (uint64_t)(p < pv.P ? p : 0) * pv.cap;
+        const unsigned long long* cnt = pv.cursor + (p < pv.P ? p : 0);
+        if (b4) {
+            if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<4>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
+            probe_slice_kernel<4><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+        } else {
+            if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<8>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
+            probe_slice_kernel<8><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+        }
+    }
+    probe_list_kernel<4><<<(unsigned)(nsm * 3), kCtaThreads, 0, s>>>(ix, pv.overflow, pv.cursor + pv.P, pv.ovf_cap, d_stats);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(pv.cursor, 0, (pv.P + 1) * sizeof(unsigned long long), s);
 }
 
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
