@@ -447,3 +447,64 @@ def test_full_size_properties(vglib):
     assert np.array_equal(cs, want) and (ps, hs) == (wp, wh)
     ix.close()
     c.close()
+
+
+# ---- T3: the drop-in binary (reference host code + our FastqKmerKernel / BloomFilterKernel) ----
+def _run(cmd, cwd):
+    import subprocess
+    r = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stderr
+
+
+def _integrated():
+    from tests import oracle_binding as ob
+    b200 = os.path.join(ob.ORACLE_DIR, "_ref", "varigraph_b200")
+    if not (os.path.exists(b200) and os.path.exists(ob.REF_BIN)):
+        pytest.skip("oracle/_ref binaries not built (no /root/reference on the build machine)")
+    return ob.REF_BIN, b200
+
+
+def test_genotype_vcf_identical_to_reference(tmp_path):
+    """Same graph.bin, same FASTQ: `varigraph genotype` (reference CPU) vs the drop-in on the GPU
+    must write byte-identical VCFs (SURVEY F4 envelope: -m rec, 11 haplotypes <= -n 15)."""
+    ref_bin, b200 = _integrated()
+    t = helpers.tiny()
+    (tmp_path / "graph.bin").write_bytes(t["graph_bin"])
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    (tmp_path / "samples.cfg").write_text(f"S0 {f1} {f2}\n")
+    out = {}
+    for name, exe, extra in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", "0", "--buffer", "1"])):
+        d = tmp_path / name
+        d.mkdir()
+        log = _run([exe, "genotype", "--load-graph", str(tmp_path / "graph.bin"), "-s", str(tmp_path / "samples.cfg"),
+                    "-t", "4"] + extra, cwd=str(d))
+        with gzip.open(d / "S0.varigraph.vcf.gz", "rb") as f:
+            out[name] = f.read()
+        if name == "gpu":
+            assert "Collecting kmers from read on GPU" in log
+    assert out["gpu"] == out["cpu"]
+    assert out["gpu"] == t["vcf"]  # and equal to the committed golden VCF
+
+
+def test_construct_on_gpu_then_identical_genotypes(tmp_path):
+    """`construct` with the CBF filled on the device, then both binaries genotype from that graph."""
+    ref_bin, b200 = _integrated()
+    t = helpers.tiny()
+    fa, vcf = tmp_path / "ref.fa", tmp_path / "var.vcf"
+    synth.write_fasta(str(fa), t["genome"])
+    synth.write_vcf(str(vcf), t["variants"], len(t["genome"]))
+    log = _run([b200, "construct", "-r", str(fa), "-v", str(vcf), "--save-graph", str(tmp_path / "g.bin"), "-t", "4",
+                "--gpu", "0", "--buffer", "1"], cwd=str(tmp_path))
+    assert "on GPU" in log and os.path.getsize(tmp_path / "g.bin") > 10_000
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    (tmp_path / "samples.cfg").write_text(f"S0 {f1} {f2}\n")
+    out = {}
+    for name, exe, extra in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", "0"])):
+        d = tmp_path / name
+        d.mkdir()
+        _run([exe, "genotype", "--load-graph", str(tmp_path / "g.bin"), "-s", str(tmp_path / "samples.cfg"), "-t", "4"] + extra,
+             cwd=str(d))
+        with gzip.open(d / "S0.varigraph.vcf.gz", "rb") as f:
+            out[name] = f.read()
+    assert out["gpu"] == out["cpu"] and out["gpu"].count(b"\n") > 50

@@ -71,28 +71,25 @@ static int part_setup(vg_index* ix) {
     const uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
     if (force != 1 && table_bytes < (96ull << 20)) return VG_OK;  // the table itself lives in L2
     if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
-    uint64_t round_keys = 256ull << 20, slack = 65536;
+    uint64_t round_keys = 1024ull << 20, slack = 65536;
     if (const char* e = getenv("VG_ROUND_KEYS")) round_keys = strtoull(e, nullptr, 10) >= 4096 ? strtoull(e, nullptr, 10) : round_keys;
     if (const char* e = getenv("VG_PART_SLACK")) slack = strtoull(e, nullptr, 10);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    while (round_keys > (8u << 20) && round_keys * 8 * 9 / 4 > free_b / 3) round_keys >>= 1;
+    while (round_keys > (8u << 20) && round_keys * 10 > free_b / 4) round_keys >>= 1;  // 10 B/key, <= 1/4 of free HBM
     round_keys &= ~4095ull;
     PartState& ps = ix->part;
     ps.view.P = (uint32_t)P;
     ps.view.shift = shift;
     ps.view.cap = (round_keys / P) * 5 / 4 + slack;
-    ps.view.ovf_cap = round_keys;
     ps.round_keys = round_keys;
     cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.overflow, ps.view.ovf_cap * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, (P + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), c->compute_stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, (P + 1) * sizeof(unsigned long long), c->compute_stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), c->compute_stream);
     if (e != cudaSuccess) {  // not enough memory for the key buffers: fall back to direct probing
         cudaFree(ps.view.keybuf);
-        cudaFree(ps.view.overflow);
         cudaFree(ps.view.cursor);
         cudaFree(ps.view.ctr);
         ps = PartState();
@@ -107,7 +104,7 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     PartState& ps = ix->part;
     if (!ps.enabled || ps.pending == 0) return VG_OK;
     CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
-    ix->launches += ps.view.P + 2;
+    ix->launches += ps.view.P + 1;
     ps.pending = 0;
     return VG_OK;
 }
@@ -359,7 +356,6 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->d_counts);
     cudaFree(ix->d_misc);
     cudaFree(ix->part.view.keybuf);
-    cudaFree(ix->part.view.overflow);
     cudaFree(ix->part.view.cursor);
     cudaFree(ix->part.view.ctr);
     delete ix;
@@ -381,7 +377,7 @@ int vg_count_begin(vg_index* ix) {
     CU(vg::launch_clear_counts(ix->view, c->compute_stream));
     CU(cudaMemsetAsync(&ix->d_misc->stats, 0, sizeof(vg::CountStats), c->compute_stream));
     if (ix->part.enabled) {
-        CU(cudaMemsetAsync(ix->part.view.cursor, 0, (ix->part.view.P + 1) * sizeof(unsigned long long), c->compute_stream));
+        CU(cudaMemsetAsync(ix->part.view.cursor, 0, ix->part.view.P * sizeof(unsigned long long), c->compute_stream));
         ix->part.pending = 0;
     }
     ix->counting = true;

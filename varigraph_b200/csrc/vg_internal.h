@@ -30,12 +30,10 @@ struct InsertReport {               // lives in device memory
 // updates hit L2 instead of paying one random DRAM access each.
 struct PartView {
     uint64_t* keybuf;               // P partitions x cap hashes (key >> 8)
-    uint64_t* overflow;             // keys whose partition was full (probed directly afterwards)
-    unsigned long long* cursor;     // P fill counts, then the overflow count at [P]
+    unsigned long long* cursor;     // P fill counts
     uint32_t P;
     uint32_t shift;                 // partition = bucket >> shift
-    uint64_t cap;                   // capacity of one partition
-    uint64_t ovf_cap;
+    uint64_t cap;                   // capacity of one partition; keys beyond it are probed directly
     uint32_t* ctr;                  // 2 x (4 << shift) u32 side counters: hits of the slice being probed
 };
 constexpr uint32_t kMaxPartitions = 256;

@@ -268,14 +268,33 @@ constexpr int kTileKeys = kCtaThreads * kSegBytes;  // at most one key per byte 
 
 struct ScatterSmem {
     uint64_t key[kTileKeys];
-    uint16_t pid[kTileKeys];
     uint32_t hist[kMaxPartitions];
     uint32_t off[kMaxPartitions];
     uint32_t fit[kMaxPartitions];
     unsigned long long base[kMaxPartitions];
-    uint32_t total;
     uint8_t lut[256];
 };
+
+// Rare path of the scatter: the key's partition buffer is full (a very skewed round, e.g. thousands
+// of identical reads).  Probe it right here, one key at a time, so no key is ever dropped and no
+// worst-case overflow buffer has to exist.  Kept out of line: it must not cost the hot path registers.
+__device__ __noinline__ void probe_one_direct(IndexView ix, uint64_t key, CountStats* stats) {
+    uint32_t b = bucket_of(key, ix.nbuckets);
+    for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
+        uint64_t v[4];
+        ld_bucket(ix.slots + 4ull * b, v);
+        bool saw_empty;
+        uint64_t seen = 0;
+        const int hs = match_slot(v, key, saw_empty, seen);
+        if (hs >= 0) {
+            slot_sat_add(ix.slots + 4ull * b + hs, seen, 1u);
+            atomicAdd(&stats->hits, 1ull);
+            return;
+        }
+        if (saw_empty) return;
+        b = (b + 1 == ix.nbuckets) ? 0 : b + 1;
+    }
+}
 
 template <bool kOdd, bool kK28>
 __global__ void __launch_bounds__(kCtaThreads, 3)
@@ -336,7 +355,6 @@ scatter_kernel(IndexView ix, PartView pv, Chunk c, int64_t first_tile, int64_t n
                 const uint32_t idx = lane * (kMaxPartitions / 32) + i;
                 if (idx < P) sm.off[idx] = excl + loc[i];
             }
-            if (lane == 31) sm.total = incl;
         }
         for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
             const uint32_t cnt = sm.hist[i];
@@ -355,23 +373,18 @@ scatter_kernel(IndexView ix, PartView pv, Chunk c, int64_t first_tile, int64_t n
         for (int j = 0; j < 16; ++j) {
             if ((emit >> j) & 1u) {
                 const uint32_t p = where[j] >> 12;
-                const uint32_t dst = sm.off[p] + (where[j] & 0xfffu);
-                sm.key[dst] = keys[j];
-                sm.pid[dst] = (uint16_t)p;
+                sm.key[sm.off[p] + (where[j] & 0xfffu)] = keys[j];
             }
         }
         __syncthreads();
-        // phase 4: coalesced copy-out, partition runs are contiguous on both sides
-        const uint32_t total = sm.total;
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            const uint32_t p = sm.pid[i];
-            const uint32_t r = i - sm.off[p];
-            const uint64_t key = sm.key[i];
-            if (r < sm.fit[p]) {
-                pv.keybuf[(uint64_t)p * pv.cap + sm.base[p] + r] = key;
-            } else {  // partition full: an adversarial or very skewed round; still counted exactly
-                const unsigned long long o = atomicAdd(&pv.cursor[P], 1ull);
-                if (o < pv.ovf_cap) pv.overflow[o] = key;
+        // phase 4: coalesced copy-out, one partition run per warp at a time (contiguous on both sides)
+        for (uint32_t p = warp; p < P; p += kCtaThreads / 32) {
+            const uint32_t cnt = sm.hist[p], fit = sm.fit[p], src = sm.off[p];
+            uint64_t* dst = pv.keybuf + (uint64_t)p * pv.cap + sm.base[p];
+            for (uint32_t i = lane; i < cnt; i += 32) {
+                const uint64_t key = sm.key[src + i];
+                if (i < fit) dst[i] = key;
+                else probe_one_direct(ix, key, stats);  // partition full: still counted, exactly
             }
         }
         __syncthreads();
@@ -547,41 +560,6 @@ probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsign
     if (threadIdx.x == 0 && blk_hit) atomicAdd(&stats->hits, blk_hit);
 }
 
-// The overflow list (keys whose partition buffer was full) is probed directly, CAS path.
-template <int kBatch>
-__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
-probe_list_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsigned long long* count_ptr, uint64_t cap,
-                  CountStats* stats) {
-    __shared__ unsigned long long blk_hit;
-    if (threadIdx.x == 0) blk_hit = 0;
-    __syncthreads();
-    const uint64_t n = min((uint64_t)*count_ptr, cap);
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp_gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    constexpr uint64_t kPerWarp = 32ull * kBatch;
-    uint32_t n_hit = 0;
-    for (uint64_t base = warp_gid * kPerWarp; base < n; base += nwarps * kPerWarp) {
-        uint64_t keys[kBatch];
-        uint32_t emit = 0;
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const uint64_t idx = base + (uint64_t)b * 32 + lane;
-            keys[b] = 0;
-            if (idx < n) {
-                keys[b] = ld_key_stream(list + idx);
-                emit |= 1u << b;
-            }
-        }
-        probe_and_count<false, kBatch>(ix, keys, emit, n_hit);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n_hit += __shfl_xor_sync(kFullMask, n_hit, d);
-    if (lane == 0 && n_hit) atomicAdd(&blk_hit, (unsigned long long)n_hit);
-    __syncthreads();
-    if (threadIdx.x == 0 && blk_hit) atomicAdd(&stats->hits, blk_hit);
-}
-
 // ---------------------------------------------------------------------------
 // extraction: counts in the key order given at index creation
 // ---------------------------------------------------------------------------
@@ -733,8 +711,8 @@ static inline unsigned grid_1d(uint64_t n, unsigned block, unsigned cap) {
 int count_variant() {
     static int v = [] {
         const char* e = getenv("VG_COUNT_BATCH");
-        int x = e ? atoi(e) : 8;
-        return x == 4 ? 4 : 8;
+        int x = e ? atoi(e) : 4;
+        return x == 8 ? 8 : 4;
     }();
     return v;
 }
@@ -846,10 +824,9 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
             probe_slice_kernel<8><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
         }
     }
-    probe_list_kernel<4><<<(unsigned)(nsm * 3), kCtaThreads, 0, s>>>(ix, pv.overflow, pv.cursor + pv.P, pv.ovf_cap, d_stats);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return cudaMemsetAsync(pv.cursor, 0, (pv.P + 1) * sizeof(unsigned long long), s);
+    return cudaMemsetAsync(pv.cursor, 0, pv.P * sizeof(unsigned long long), s);
 }
 
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,

@@ -1,0 +1,46 @@
+// construct_index_b200.hpp -- drop-in for include/construct_index.cuh + src/construct_index.cu.
+// Only make_mbf differs from the CPU class: the counting Bloom filter is filled on the device
+// (src/construct_index.cu:39-106) and copied back, after which the reference's own index()
+// (src/construct_index.cpp:592-700) runs unmodified against mbf -- index_kernel is, as in the
+// reference, the host code path (src/construct_index.cu:116-300 logs "on CPU").
+#pragma once
+#include "construct_index.hpp"  // reference header
+#include "counting_bloom_filter_b200.hpp"
+
+class ConstructIndexKernel : public ConstructIndex {
+public:
+    BloomFilterKernel* mbfD = nullptr;  // owned through the base class pointer `mbf`
+    int buffer_ = 100;
+    int gpu_ = 0;
+
+    ConstructIndexKernel(
+        const string& refFileName, const string& vcfFileName, const string& inputGraphFileName,
+        const string& outputGraphFileName, const bool& fastMode, const bool& useUniqueKmers,
+        const uint32_t& kmerLen, const uint32_t& vcfPloidy, const bool& debug, const uint32_t& threads,
+        const int buffer, const int gpu = 0
+    ) : ConstructIndex(refFileName, vcfFileName, inputGraphFileName, outputGraphFileName, fastMode, useUniqueKmers,
+                       kmerLen, vcfPloidy, debug, threads), buffer_(buffer), gpu_(gpu) {}
+
+    void make_mbf_kernel() {
+        cerr << "[" << __func__ << "::" << getTime() << "] " << "Initiating computation of k-mer frequencies in the reference genome on GPU ...\n";
+        uint64_t bfSize = mGenomeSize - mKmerLen + 1;
+        double errorRate = 0.01;
+        mbfD = new BloomFilterKernel(bfSize, errorRate, gpu_, buffer_);
+        mbf = mbfD;  // ConstructIndex::index() / clear_mbf() use and free it through the base pointer
+        cerr << "[" << __func__ << "::" << getTime() << "] " << "Making Counting Bloom Filter with a false positive rate of " << errorRate << " ...\n";
+        for (const auto& [chromosome, sequence] : mFastaSeqMap) {
+            mbfD->add_sequence_kernel(sequence, mKmerLen);
+            cerr << "[" << __func__ << "::" << getTime() << "] " << "Chromosome '" << chromosome << "' processed successfully ...\n";
+        }
+        mbfD->copyFilterDToHost();
+        cerr << "[" << __func__ << "::" << getTime() << "] " << "Counting Bloom Filter constructed successfully ..." << endl << endl;
+        cerr << "           - " << "Counting Bloom Filter size: " << mbf->get_size() << endl;
+        cerr << "           - " << "Hash functions count: " << mbf->get_num() << endl;
+        cerr << fixed << setprecision(2);
+        cerr << "           - " << "Counting Bloom Filter usage rate: " << mbf->get_cap() << endl << endl << endl;
+        cerr << defaultfloat << setprecision(6);
+        malloc_trim(0);
+    }
+
+    void index_kernel() { index(); }
+};
