@@ -342,6 +342,7 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; varigraph_b200 has no CPU path (use --impl reference)")
     import torch.distributed as dist
     from varigraph_b200 import capi
+    from varigraph_b200 import dist as vdist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -372,12 +373,11 @@ def main() -> None:
         if kev:
             kev[0].record(stream)
         ix.submit_device(lines_dev.data_ptr(), nbytes)
+        ix.flush()
         if kev:
             kev[1].record(stream)
         ix.extract_device(out32.data_ptr(), 4)
-        if world > 1:
-            dist.all_reduce(out32)
-        out32.clamp_(max=255)
+        return vdist.reduce_counts(out32)  # N > 1: the one NCCL all-reduce of the path; clamp to 255
 
     def barrier():
         if world > 1:
@@ -412,7 +412,7 @@ def main() -> None:
     total_positions = float(tp.item())
     value = total_positions / (ms_per_step * 1e-3)
     clk = clocks.stop(t_mark0, t_mark1)
-    device_counts = out32.to(torch.uint8).cpu().numpy()
+    device_counts = device_step().cpu().numpy()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------
     def e2e_step():
@@ -420,8 +420,7 @@ def main() -> None:
         ix.submit_ptr(lines_host.data_ptr(), nbytes)
         if world > 1:
             ix.extract_device(out32.data_ptr(), 4, stream.cuda_stream)  # syncs the context streams first
-            dist.all_reduce(out32)
-            counts_host.copy_(out32.clamp_(max=255).to(torch.uint8), non_blocking=True)
+            counts_host.copy_(vdist.reduce_counts(out32), non_blocking=True)
             torch.cuda.synchronize()
             capi.lib.vg_count_end(ix._h, None, None, None)
         else:
@@ -458,8 +457,8 @@ def main() -> None:
             sys.stderr.write(f"random-sector probe failed: {ex}\n")
     probes_per_s = positions / (kernel_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": ("vg::scatter_kernel + vg::probe_list_kernel (one count pass)" if ix.partitions
-                           else "vg::count_kernel"),
+                "traffic": None, "peak_source": peak_src, "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
+                           else "vg::count_kernel (K1+K2+K3 fused)"),
                 "kernel_ms": kernel_ms, "bytes_per_position": b_alg, "hit_fraction": h,
                 "random_sector_peak_gbs": rnd_gbs,
                 "frac_of_random_sector_peak": (probes_per_s * (1 + h) / rnd_sec) if rnd_sec else None}

@@ -84,6 +84,10 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
  * processed concurrently).  *read_bases accumulates mReadBase (src/fastq_kmer.cpp:105). */
 int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
 
+/* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
+ * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */
+int vg_count_flush(vg_index* ix);
+
 /* Waits for the sample's kernels, then writes c in the key order given at create.
  * c_out (n bytes, host), positions, hits may each be NULL. */
 int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hits);

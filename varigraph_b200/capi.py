@@ -50,6 +50,7 @@ def _load() -> ctypes.CDLL:
         "vg_count_submit": (c_int, [c_void_p, c_void_p, c_uint64]),
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
         "vg_count_files": (c_int, [c_void_p, P(c_char_p), c_int, c_int, P(c_uint64)]),
+        "vg_count_flush": (c_int, [c_void_p]),
         "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
         "vg_count_extract_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
         "vg_count_stats": (c_int, [c_void_p, P(c_uint64), P(c_uint64)]),
@@ -168,6 +169,9 @@ class Index:
 
     def submit_device(self, dev_ptr: int, nbytes: int, stream: int = 0) -> None:
         _chk(lib.vg_count_submit_device(self._h, c_void_p(dev_ptr), nbytes, c_void_p(stream)))
+
+    def flush(self) -> None:
+        _chk(lib.vg_count_flush(self._h))
 
     def count_files(self, paths, threads: int = 4) -> int:
         arr = (c_char_p * len(paths))(*[os.fsencode(p) for p in paths])

@@ -191,15 +191,19 @@ int vg_ctx_create(int device, int buffer_mb, vg_ctx** out) {
     return VG_OK;
 }
 
-static int ctx_ensure_ring(vg_ctx* c, int nslots) {
+// Device buffers of the staging ring; the pinned twins are only allocated for callers that hand
+// over pageable memory (a pinned source is DMA-ed from where it lies).
+static int ctx_ensure_ring(vg_ctx* c, int nslots, bool need_pinned) {
     while ((int)c->ring.size() < nslots) {
         vg::StageSlot s;
         CU(cudaMalloc((void**)&s.d_buf, c->chunk_bytes + 256));
-        CU(cudaHostAlloc((void**)&s.h_pin, c->chunk_bytes + 256, cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         c->ring.push_back(s);
     }
+    if (need_pinned)
+        for (auto& s : c->ring)
+            if (!s.h_pin) CU(cudaHostAlloc((void**)&s.h_pin, c->chunk_bytes + 256, cudaHostAllocDefault));
     return VG_OK;
 }
 
@@ -209,7 +213,7 @@ int vg_ctx_destroy(vg_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& s : c->ring) {
         cudaFree(s.d_buf);
-        cudaFreeHost(s.h_pin);
+        if (s.h_pin) cudaFreeHost(s.h_pin);
         cudaEventDestroy(s.copied);
         cudaEventDestroy(s.done);
     }
@@ -408,11 +412,13 @@ int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
     if (!ix->counting) return fail(VG_E_STATE, "vg_count_submit before vg_count_begin");
     vg_ctx* c = ix->ctx;
     DeviceGuard g(c->device);
-    int rc = ctx_ensure_ring(c, 3);
-    if (rc) return rc;
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, host_bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    // A deep ring lets the copy engine run ahead while a probe sweep occupies the compute stream.
+    const int want = pinned ? (int)std::min<uint64_t>(12, std::max<uint64_t>(3, (768ull << 20) / c->chunk_bytes)) : 3;
+    int rc = ctx_ensure_ring(c, std::max<int>(want, (int)c->ring.size()), !pinned);
+    if (rc) return rc;
     uint64_t off = 0;
     while (off < nbytes) {
         uint64_t len = std::min<uint64_t>(c->chunk_bytes, nbytes - off);
@@ -438,6 +444,12 @@ int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
         off += len;
     }
     return VG_OK;
+}
+
+int vg_count_flush(vg_index* ix) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    DeviceGuard g(ix->ctx->device);
+    return part_flush(ix, ix->ctx->compute_stream);
 }
 
 int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits) {

@@ -233,11 +233,14 @@ int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int thre
     while ((int)ctx->ring.size() < nslots) {
         vg::StageSlot s;
         cudaError_t e = cudaMalloc((void**)&s.d_buf, ctx->chunk_bytes + 256);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_pin, ctx->chunk_bytes + 256, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
         if (e != cudaSuccess) return vg::fail(VG_E_NOMEM, "staging ring: %s", cudaGetErrorString(e));
         ctx->ring.push_back(s);
+    }
+    for (auto& s : ctx->ring) {  // the feeder's workers parse straight into the pinned twins
+        if (!s.h_pin && cudaHostAlloc((void**)&s.h_pin, ctx->chunk_bytes + 256, cudaHostAllocDefault) != cudaSuccess)
+            return vg::fail(VG_E_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(cudaGetLastError()));
     }
     for (auto& sl : ctx->ring) {
         if (sl.busy) {
