@@ -226,6 +226,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(partitioned: bool):
+    """DRAM bytes of one count pass from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t["partitioned_pass_bytes" if partitioned else "direct_pass_bytes"]
+    except Exception:
+        return None
+
+
 def dist_info():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -457,7 +467,7 @@ def main() -> None:
             sys.stderr.write(f"random-sector probe failed: {ex}\n")
     probes_per_s = positions / (kernel_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
+                "traffic": ncu_traffic(ix.partitions > 0), "peak_source": peak_src, "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
                            else "vg::count_kernel (K1+K2+K3 fused)"),
                 "kernel_ms": kernel_ms, "bytes_per_position": b_alg, "hit_fraction": h,
                 "random_sector_peak_gbs": rnd_gbs,

@@ -147,6 +147,12 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
     int rc = count_device_chunk(ix, sl.d_buf, len, c->compute_stream);
     if (rc) return rc;
     CU(cudaEventRecord(sl.done, c->compute_stream));
+    // Staged input arrives at PCIe speed, slower than the kernels: sweep every 256 M k-mers so the
+    // sweeps hide under the copies and only a short one is left after the last piece.
+    if (ix->part.enabled && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, 256ull << 20)) {
+        rc = part_flush(ix, c->compute_stream);
+        if (rc) return rc;
+    }
     sl.busy = true;
     return VG_OK;
 }

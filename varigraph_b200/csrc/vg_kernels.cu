@@ -781,13 +781,10 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_
     using KernelT = void (*)(IndexView, PartView, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true, false>
                               : (ix.k == 28 ? (KernelT)scatter_kernel<false, true> : (KernelT)scatter_kernel<false, false>);
-    static bool attr_set[3] = {false, false, false};
-    const int which = (ix.k & 1) ? 0 : (ix.k == 28 ? 1 : 2);
     const size_t smem = sizeof(ScatterSmem);
-    if (!attr_set[which]) {
+    {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set[which] = true;
     }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem) != cudaSuccess || occ < 1) occ = 1;
