@@ -97,6 +97,43 @@ static int part_setup(vg_index* ix) {
         return VG_OK;
     }
     ps.enabled = true;
+    // Presence pre-filter: 4 bits per key (measured best on B200: 30 MB for the chr20 index beats both
+    // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
+    // the streaming traffic; larger indexes go without.  VG_PREFILTER=0 disables it.
+    const char* pe = getenv("VG_PREFILTER");
+    if (!(pe && atoi(pe) == 0) && ix->n > 0) {
+        uint64_t bytes = 0;
+        if (ix->n / 2 <= (64ull << 20)) bytes = ix->n / 2;
+        if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
+        if (bytes >= 64) {
+            const uint32_t nwords = (uint32_t)std::min<uint64_t>(bytes / 4, 0x7fffffffull);
+            if (cudaMalloc((void**)&ps.d_filter, (size_t)nwords * 4) == cudaSuccess) {
+                CU(cudaMemsetAsync(ps.d_filter, 0, (size_t)nwords * 4, c->compute_stream));
+                CU(vg::launch_prefilter_build(ps.d_filter, nwords, ix->d_key56, ix->n, c->compute_stream));
+                CU(cudaStreamSynchronize(c->compute_stream));
+                ps.filter.words = ps.d_filter;
+                ps.filter.nwords = nwords;
+                // pin it in L2 for the kernels of this context's stream
+                cudaDeviceProp prop;
+                if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                    const size_t want = std::min<size_t>((size_t)nwords * 4, (size_t)prop.persistingL2CacheMaxSize);
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                    cudaStreamAttrValue av{};
+                    av.accessPolicyWindow.base_ptr = ps.d_filter;
+                    av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)nwords * 4, (size_t)prop.accessPolicyMaxWindowSize);
+                    av.accessPolicyWindow.hitRatio = 1.0f;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(c->compute_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                    cudaGetLastError();
+                    c->l2_window = av.accessPolicyWindow;
+                    c->has_l2_window = true;
+                }
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     return VG_OK;
 }
 
@@ -129,7 +166,7 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
             room = (int64_t)(ps.round_keys / tile_bytes);
         }
         const int64_t nt = std::min<int64_t>(T - t, room);
-        CU(vg::launch_scatter(ix->view, ps.view, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s));
+        CU(vg::launch_scatter(ix->view, ps.view, ps.filter, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s));
         ix->launches += 1;
         ps.pending += (uint64_t)nt * tile_bytes;
         t += nt;
@@ -236,6 +273,12 @@ int vg_ctx_set_stream(vg_ctx* c, void* cuda_stream) {
     DeviceGuard g(c->device);
     CU(cudaStreamSynchronize(c->compute_stream));
     c->compute_stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_compute_stream;
+    if (c->has_l2_window) {  // the caller's stream inherits the pre-filter's L2 persisting window
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow = c->l2_window;
+        cudaStreamSetAttribute(c->compute_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     return VG_OK;
 }
 
@@ -368,6 +411,7 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->part.view.keybuf);
     cudaFree(ix->part.view.cursor);
     cudaFree(ix->part.view.ctr);
+    cudaFree(ix->part.d_filter);
     delete ix;
     return VG_OK;
 }

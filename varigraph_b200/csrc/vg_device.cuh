@@ -123,6 +123,13 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets)
     return __umulhi((uint32_t)(x >> 32), nbuckets);
 }
 
+// ---- presence pre-filter (word-blocked Bloom, 2 bits per key in one 32-bit word) -------------
+__device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& mask) {
+    const uint64_t h = key56 * 0xD6E8FEB86659FD93ULL;
+    word = __umulhi((uint32_t)(h >> 32), nwords);
+    mask = (1u << ((uint32_t)h & 31u)) | (1u << (((uint32_t)h >> 5) & 31u));
+}
+
 // ---- the view of a staged chunk --------------------------------------------
 // `al` is the 16-byte aligned-down base; live bytes are [lo, hi) relative to it.
 // Everything outside behaves like '\n'.

@@ -41,6 +41,8 @@ struct vg_ctx {
     cudaStream_t own_compute_stream = nullptr;
     std::vector<vg::StageSlot> ring;
     int next_slot = 0;
+    bool has_l2_window = false;          // L2 persisting window over the presence pre-filter
+    cudaAccessPolicyWindow l2_window{};
 };
 
 // Host-side state of the partitioned probing path of one index.
@@ -49,6 +51,8 @@ struct PartState {
     vg::PartView view{};
     uint64_t round_keys = 0;   // keys a round may accumulate before it must be probed
     uint64_t pending = 0;      // upper bound of keys scattered since the last probe pass
+    vg::PrefilterView filter{nullptr, 0};
+    uint32_t* d_filter = nullptr;
 };
 
 struct vg_index {

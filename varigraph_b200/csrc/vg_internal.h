@@ -14,6 +14,16 @@ struct IndexView {
     int has_special;
 };
 
+// Presence pre-filter: a word-blocked Bloom filter over the index keys (both bits of a key sit in
+// one 32-bit word, so a query is one 4-byte load).  Small enough to stay L2-resident (an L2
+// persisting access-policy window pins it), it lets the scatter drop most k-mers that are not in
+// the index before they cost a key write and a probe.  No false negatives, so results are unchanged
+// (the reference has no such filter on the read path: SURVEY F1).
+struct PrefilterView {
+    const uint32_t* words;          // nullptr: disabled
+    uint32_t nwords;
+};
+
 struct CountStats {                 // lives in device memory
     unsigned long long positions;   // emitted k-mer positions (what kmer_sketch_fastq tests against the map)
     unsigned long long hits;        // positions whose k-mer is in the index
@@ -56,8 +66,10 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
                          int ctas_per_sm, int nsm, cudaStream_t s);
 // Scatter the k-mers ending in tiles [first_tile, first_tile + ntiles) of the chunk (d_bases, nbytes)
 // into the partition buffers; launch_probe_partitions then probes every partition and resets them.
-cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_t* d_bases, uint64_t nbytes,
-                           int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm, cudaStream_t s);
+cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
+                           uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
+                           cudaStream_t s);
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, cudaStream_t s);
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);

@@ -296,9 +296,17 @@ __device__ __noinline__ void probe_one_direct(IndexView ix, uint64_t key, CountS
     }
 }
 
+__global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w, m;
+    prefilter_slot(key56[i], nwords, w, m);
+    atomicOr(words + w, m);
+}
+
 template <bool kOdd, bool kK28>
 __global__ void __launch_bounds__(kCtaThreads, 3)
-scatter_kernel(IndexView ix, PartView pv, Chunk c, int64_t first_tile, int64_t ntiles, CountStats* stats) {
+scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t first_tile, int64_t ntiles, CountStats* stats) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
     __shared__ unsigned long long blk_pos;
@@ -314,8 +322,48 @@ scatter_kernel(IndexView ix, PartView pv, Chunk c, int64_t first_tile, int64_t n
         // phase 1: encode; rank every emitted key inside its partition (order within a tile is free)
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         uint64_t keys[16];
-        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, sm.lut, keys) : encode_keys_any(c, off, kp, sm.lut, keys);
-        n_pos += __popc(emit);
+        uint32_t emit;
+        if (pf.words) {
+            // Presence pre-filter (L2-resident, never a false negative).  The filter words of the first
+            // eight k-mers are in flight while the next eight are rolled and hashed.
+            uint32_t fw[16];
+            auto fetch8 = [&](int g, uint32_t e8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t w, m;
+                    prefilter_slot(keys[g + j], pf.nwords, w, m);
+                    fw[g + j] = ((e8 >> j) & 1u) ? __ldg(pf.words + w) : 0u;
+                }
+            };
+            if (kOdd) {
+                OddEncoder enc;
+                enc.init(c, off, kp, sm.lut);
+                uint64_t h[8];
+                const uint32_t e0 = enc.next<8>(kp, h);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) keys[j] = h[j];
+                fetch8(0, e0);
+                const uint32_t e1 = enc.next<8>(kp, h);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) keys[8 + j] = h[j];
+                fetch8(8, e1);
+                emit = e0 | (e1 << 8);
+            } else {
+                emit = encode_keys_any(c, off, kp, sm.lut, keys);
+                fetch8(0, emit & 0xffu);
+                fetch8(8, emit >> 8);
+            }
+            n_pos += __popc(emit);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                uint32_t w, m;
+                prefilter_slot(keys[j], pf.nwords, w, m);
+                if ((fw[j] & m) != m) emit &= ~(1u << j);
+            }
+        } else {
+            emit = kOdd ? encode_keys_odd(c, off, kp, sm.lut, keys) : encode_keys_any(c, off, kp, sm.lut, keys);
+            n_pos += __popc(emit);
+        }
         uint32_t where[16];  // partition << 12 | rank
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -774,11 +822,18 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
 
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes) { return tiles_for(make_chunk(d_bases, nbytes)); }
 
-cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_t* d_bases, uint64_t nbytes,
-                           int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm, cudaStream_t s) {
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    prefilter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(words, nwords, d_key56, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
+                           uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
+                           cudaStream_t s) {
     if (ntiles <= 0) return cudaSuccess;
     Chunk c = make_chunk(d_bases, nbytes);
-    using KernelT = void (*)(IndexView, PartView, Chunk, int64_t, int64_t, CountStats*);
+    using KernelT = void (*)(IndexView, PartView, PrefilterView, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true, false>
                               : (ix.k == 28 ? (KernelT)scatter_kernel<false, true> : (KernelT)scatter_kernel<false, false>);
     const size_t smem = sizeof(ScatterSmem);
@@ -790,7 +845,7 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const uint8_
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem) != cudaSuccess || occ < 1) occ = 1;
     int64_t grid = (int64_t)nsm * occ;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, kCtaThreads, smem, s>>>(ix, pv, c, first_tile, ntiles, d_stats);
+    kern<<<(unsigned)grid, kCtaThreads, smem, s>>>(ix, pv, pf, c, first_tile, ntiles, d_stats);
     return cudaGetLastError();
 }
 
