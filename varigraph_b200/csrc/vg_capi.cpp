@@ -68,7 +68,11 @@ static int part_setup(vg_index* ix) {
     if (const char* e = getenv("VG_SLICE_BYTES")) slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
     uint32_t shift = 0;
     while ((32ull << (shift + 1)) <= slice_bytes) ++shift;  // buckets per slice = 2^shift
-    const uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
+    uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
+    if (P > 256 && !getenv("VG_SLICE_BYTES")) {  // big tables: 64 MB slices still fit L2, half the partitions
+        ++shift;
+        P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
+    }
     if (force != 1 && table_bytes < (96ull << 20)) return VG_OK;  // the table itself lives in L2
     if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
     uint64_t round_keys = 1024ull << 20, slack = 65536;

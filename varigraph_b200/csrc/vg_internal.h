@@ -46,7 +46,7 @@ struct PartView {
     uint64_t cap;                   // capacity of one partition; keys beyond it are probed directly
     uint32_t* ctr;                  // 2 x (4 << shift) u32 side counters: hits of the slice being probed
 };
-constexpr uint32_t kMaxPartitions = 256;
+constexpr uint32_t kMaxPartitions = 1024;
 
 struct CbfView {
     uint8_t* cells;                 // m saturating u8 counters

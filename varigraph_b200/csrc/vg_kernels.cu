@@ -384,11 +384,10 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t fir
         __syncthreads();
         // phase 2: offsets inside the tile (warp 0) and space in the global partition buffers
         if (warp == 0) {
-            uint32_t loc[kMaxPartitions / 32], sum = 0;
-#pragma unroll
-            for (int i = 0; i < (int)(kMaxPartitions / 32); ++i) {
-                const uint32_t idx = lane * (kMaxPartitions / 32) + i;
-                loc[i] = sum;
+            const uint32_t per = (P + 31) / 32;  // consecutive slices per lane
+            uint32_t sum = 0;
+            for (uint32_t i = 0; i < per; ++i) {
+                const uint32_t idx = lane * per + i;
                 sum += idx < P ? sm.hist[idx] : 0u;
             }
             uint32_t incl = sum;
@@ -397,11 +396,13 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t fir
                 uint32_t y = __shfl_up_sync(kFullMask, incl, d);
                 if (lane >= (uint32_t)d) incl += y;
             }
-            const uint32_t excl = incl - sum;
-#pragma unroll
-            for (int i = 0; i < (int)(kMaxPartitions / 32); ++i) {
-                const uint32_t idx = lane * (kMaxPartitions / 32) + i;
-                if (idx < P) sm.off[idx] = excl + loc[i];
+            uint32_t run = incl - sum;
+            for (uint32_t i = 0; i < per; ++i) {
+                const uint32_t idx = lane * per + i;
+                if (idx < P) {
+                    sm.off[idx] = run;
+                    run += sm.hist[idx];
+                }
             }
         }
         for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
