@@ -52,6 +52,19 @@ __device__ __forceinline__ uint64_t hash64(uint64_t x, uint64_t m) {
     return x;
 }
 
+// Same function for 2k >= 32 (k >= 16): the mask's low word is all ones, so only high words are masked.
+__device__ __forceinline__ uint64_t hash64_wide(uint64_t x, uint32_t mask_hi) {
+    const uint64_t m = ((uint64_t)mask_hi << 32) | 0xffffffffu;
+    x = (x * 0x1FFFFFULL - 1ULL) & m;
+    x ^= x >> 24;
+    x = (x * 265ULL) & m;
+    x ^= x >> 14;
+    x = (x * 21ULL) & m;
+    x ^= x >> 28;
+    x = (x * 0x80000001ULL) & m;
+    return x;
+}
+
 // Reverse complement of the k bases held in the low 2k bits of f (oldest base highest).
 __device__ __forceinline__ uint64_t revcomp2k(uint64_t f, uint32_t k) {
     uint64_t y = __brevll(~f);
@@ -124,11 +137,13 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets)
 }
 
 // ---- presence pre-filter (word-blocked Bloom, 2 bits per key in one 32-bit word) -------------
-__device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& mask) {
+// word: which 32-bit word; bits: the key's two bit positions, packed as lo5 | hi5 << 5.
+__device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& bits) {
     const uint64_t h = key56 * 0xD6E8FEB86659FD93ULL;
     word = __umulhi((uint32_t)(h >> 32), nwords);
-    mask = (1u << ((uint32_t)h & 31u)) | (1u << (((uint32_t)h >> 5) & 31u));
+    bits = (uint32_t)h & 1023u;
 }
+__device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) { return (1u << (bits & 31u)) | (1u << (bits >> 5)); }
 
 // ---- the view of a staged chunk --------------------------------------------
 // `al` is the 16-byte aligned-down base; live bytes are [lo, hi) relative to it.
@@ -219,6 +234,21 @@ struct OddEncoder {
     __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N]) {
         const uint32_t top = 2 * (kp.k - 1);
         uint32_t emit = 0;
+        if (kp.k >= 17) {  // uniform: 2(k-1) >= 32, so the incoming complement only touches the high word
+            const uint32_t mask_hi = (uint32_t)(kp.mask >> 32), tsh = top - 32;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const uint32_t cb = p0 >> 30;
+                p0 <<= 2;
+                fwd = ((fwd << 2) | cb) & kp.mask;
+                const uint32_t rhi = (uint32_t)(rev >> 32), rlo = (uint32_t)rev;
+                rev = ((uint64_t)((rhi >> 2) | ((3u ^ cb) << tsh)) << 32) | __funnelshift_r(rlo, rhi, 2);
+                keys[j] = hash64_wide(fwd < rev ? fwd : rev, mask_hi);
+                emit |= ((all_k >> 15) & 1u) << j;
+                all_k <<= 1;
+            }
+            return emit;
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             uint64_t cb = p0 >> 30;

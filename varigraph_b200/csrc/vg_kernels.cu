@@ -299,9 +299,9 @@ __device__ __noinline__ void probe_one_direct(IndexView ix, uint64_t key, CountS
 __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t w, m;
-    prefilter_slot(key56[i], nwords, w, m);
-    atomicOr(words + w, m);
+    uint32_t w, bits;
+    prefilter_slot(key56[i], nwords, w, bits);
+    atomicOr(words + w, prefilter_mask(bits));
 }
 
 template <bool kOdd, bool kK28>
@@ -326,12 +326,12 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t fir
         if (pf.words) {
             // Presence pre-filter (L2-resident, never a false negative).  The filter words of the first
             // eight k-mers are in flight while the next eight are rolled and hashed.
-            uint32_t fw[16];
+            uint32_t fw[16], fb[16];  // filter word; the key's two bit positions (5 + 5 bits)
             auto fetch8 = [&](int g, uint32_t e8) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    uint32_t w, m;
-                    prefilter_slot(keys[g + j], pf.nwords, w, m);
+                    uint32_t w;
+                    prefilter_slot(keys[g + j], pf.nwords, w, fb[g + j]);
                     fw[g + j] = ((e8 >> j) & 1u) ? __ldg(pf.words + w) : 0u;
                 }
             };
@@ -356,8 +356,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t fir
             n_pos += __popc(emit);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                uint32_t w, m;
-                prefilter_slot(keys[j], pf.nwords, w, m);
+                const uint32_t m = prefilter_mask(fb[j]);
                 if ((fw[j] & m) != m) emit &= ~(1u << j);
             }
         } else {
