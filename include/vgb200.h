@@ -97,6 +97,14 @@ int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hi
 int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* cuda_stream);
 int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits);
 
+/* Count consumers on the device: hist[v] = number of index entries whose count is v,
+ * over all entries or over the subset marked by vg_index_set_flags (flags: n bytes in key order,
+ * non-zero = counted; NULL clears the subset).  With flags = "f <= 1 and homozygous in some sample"
+ * this is the histogram Varigraph::get_hom_kmer builds by walking the host map
+ * (src/varigraph.cpp:253-296).  Call after the sample's reads are submitted; implies a flush. */
+int vg_index_set_flags(vg_index* ix, const uint8_t* flags);
+int vg_count_histogram(vg_index* ix, uint64_t* hist256);
+
 /* Test / tooling hook: out[p] = key of the k-mer ENDING at byte p of the chunk, or ~0 when
  * the reference encoder emits nothing there (src/kmer.cpp:126-146).  Device buffers. */
 int vg_encode_positions_device(vg_ctx* ctx, const void* dev_bases, uint64_t nbytes, uint32_t k,

@@ -481,9 +481,12 @@ def test_genotype_vcf_identical_to_reference(tmp_path):
                     "-t", "4"] + extra, cwd=str(d))
         with gzip.open(d / "S0.varigraph.vcf.gz", "rb") as f:
             out[name] = f.read()
+        out[name + "_hist"] = [l.split("] ", 1)[-1] for l in log.splitlines() if "[kmer_histogram::" in l]
         if name == "gpu":
             assert "Collecting kmers from read on GPU" in log
     assert out["gpu"] == out["cpu"]
+    # the hom-k-mer coverage histogram (device histogram vs the reference's walk over the host map)
+    assert out["gpu_hist"] == out["cpu_hist"] and len(out["cpu_hist"]) > 0
     assert out["gpu"] == t["vcf"]  # and equal to the committed golden VCF
 
 
@@ -508,3 +511,23 @@ def test_construct_on_gpu_then_identical_genotypes(tmp_path):
         with gzip.open(d / "S0.varigraph.vcf.gz", "rb") as f:
             out[name] = f.read()
     assert out["gpu"] == out["cpu"] and out["gpu"].count(b"\n") > 50
+
+
+def test_count_histogram_matches_numpy(ctx, vglib):
+    """N1: the device histogram of c (all entries / a flagged subset) equals numpy's on the host vector."""
+    t = helpers.tiny()
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    ix.begin()
+    ix.submit(t["lines"])
+    h_all = ix.histogram()
+    flags = (np.arange(t["keys"].size) % 3 == 0).astype(np.uint8)
+    ix.set_flags(flags)
+    h_sub = ix.histogram()
+    ix.set_flags(None)
+    h_again = ix.histogram()
+    counts, _, _ = ix.end()
+    assert np.array_equal(counts, t["counts"])
+    assert np.array_equal(h_all, np.bincount(counts, minlength=256).astype(np.uint64))
+    assert np.array_equal(h_sub, np.bincount(counts[flags > 0], minlength=256).astype(np.uint64))
+    assert np.array_equal(h_again, h_all)
+    ix.close()

@@ -51,6 +51,8 @@ def _load() -> ctypes.CDLL:
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
         "vg_count_files": (c_int, [c_void_p, P(c_char_p), c_int, c_int, P(c_uint64)]),
         "vg_count_flush": (c_int, [c_void_p]),
+        "vg_index_set_flags": (c_int, [c_void_p, c_void_p]),
+        "vg_count_histogram": (c_int, [c_void_p, c_void_p]),
         "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
         "vg_count_extract_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
         "vg_count_stats": (c_int, [c_void_p, P(c_uint64), P(c_uint64)]),
@@ -172,6 +174,19 @@ class Index:
 
     def flush(self) -> None:
         _chk(lib.vg_count_flush(self._h))
+
+    def set_flags(self, flags) -> None:
+        if flags is None:
+            _chk(lib.vg_index_set_flags(self._h, None))
+            return
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert f.size == self.n
+        _chk(lib.vg_index_set_flags(self._h, _ptr(f)))
+
+    def histogram(self) -> np.ndarray:
+        out = np.zeros(256, dtype=np.uint64)
+        _chk(lib.vg_count_histogram(self._h, _ptr(out)))
+        return out
 
     def count_files(self, paths, threads: int = 4) -> int:
         arr = (c_char_p * len(paths))(*[os.fsencode(p) for p in paths])

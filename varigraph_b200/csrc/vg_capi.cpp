@@ -411,6 +411,8 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->view.slots);
     cudaFree(ix->d_key56);
     cudaFree(ix->d_counts);
+    cudaFree(ix->d_flags);
+    cudaFree(ix->d_hist);
     cudaFree(ix->d_misc);
     cudaFree(ix->part.view.keybuf);
     cudaFree(ix->part.view.cursor);
@@ -539,6 +541,39 @@ int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* c
         CU(cudaStreamSynchronize(c->compute_stream));
     }
     CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, dev_out, elem_bytes, s));
+    return VG_OK;
+}
+
+int vg_index_set_flags(vg_index* ix, const uint8_t* flags) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    if (!flags) {
+        CU(cudaStreamSynchronize(c->compute_stream));
+        cudaFree(ix->d_flags);
+        ix->d_flags = nullptr;
+        return VG_OK;
+    }
+    if (!ix->d_flags) CU(cudaMalloc((void**)&ix->d_flags, std::max<uint64_t>(ix->n, 4)));
+    CU(cudaMemcpyAsync(ix->d_flags, flags, ix->n, cudaMemcpyHostToDevice, c->compute_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    return VG_OK;
+}
+
+int vg_count_histogram(vg_index* ix, uint64_t* hist256) {
+    if (!ix || !hist256) return fail(VG_E_INVALID, "vg_count_histogram: NULL argument");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->copy_stream));
+    int rc = part_flush(ix, c->compute_stream);
+    if (rc) return rc;
+    if (!ix->d_hist) CU(cudaMalloc((void**)&ix->d_hist, 256 * sizeof(unsigned long long)));
+    CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, ix->d_counts, 1, c->compute_stream));
+    CU(vg::launch_histogram(ix->d_counts, ix->d_flags, ix->n, ix->d_hist, c->compute_stream));
+    unsigned long long h[256];
+    CU(cudaMemcpyAsync(h, ix->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->compute_stream));
+    CU(cudaStreamSynchronize(c->compute_stream));
+    for (int i = 0; i < 256; ++i) hist256[i] = h[i];
     return VG_OK;
 }
 

@@ -62,6 +62,8 @@ struct vg_index {
     vg::IndexView view{};
     uint64_t* d_key56 = nullptr;   // key order given at create, hash only (key >> 8)
     uint8_t* d_counts = nullptr;   // scratch for vg_count_end
+    uint8_t* d_flags = nullptr;    // optional per-entry subset for vg_count_histogram
+    unsigned long long* d_hist = nullptr;
     vg::DeviceMisc* d_misc = nullptr;
     uint64_t duplicates = 0;
     uint64_t launches = 0;

@@ -75,6 +75,8 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
                            int out_elem_bytes, cudaStream_t s);
+cudaError_t launch_histogram(const uint8_t* d_counts, const uint8_t* d_flags, uint64_t n, unsigned long long* d_hist,
+                             cudaStream_t s);
 cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes, uint64_t* d_out,
                              cudaStream_t s);
 

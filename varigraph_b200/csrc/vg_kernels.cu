@@ -637,6 +637,22 @@ __global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56,
 }
 
 // ---------------------------------------------------------------------------
+// count consumers: 256-bin histogram of c over a (static, per-graph) subset of the index entries --
+// the device half of Varigraph::get_hom_kmer (src/varigraph.cpp:253-296), SURVEY 8f N1.
+// ---------------------------------------------------------------------------
+__global__ void histogram_kernel(const uint8_t* __restrict__ counts, const uint8_t* __restrict__ flags, uint64_t n,
+                                 unsigned long long* hist) {
+    __shared__ unsigned int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (!flags || flags[i]) atomicAdd(&sh[counts[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// ---------------------------------------------------------------------------
 // per-position keys (test hook + synthetic index construction for bench.py)
 // out[p] = (hash << 8 | k) for the k-mer ENDING at byte p, or ~0.
 // ---------------------------------------------------------------------------
@@ -888,6 +904,14 @@ cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_
     if (out_elem_bytes == 1) extract_kernel<uint8_t><<<g, 256, 0, s>>>(ix, d_key56, n, (uint8_t*)d_out);
     else if (out_elem_bytes == 4) extract_kernel<uint32_t><<<g, 256, 0, s>>>(ix, d_key56, n, (uint32_t*)d_out);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_histogram(const uint8_t* d_counts, const uint8_t* d_flags, uint64_t n, unsigned long long* d_hist,
+                             cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess || n == 0) return e;
+    histogram_kernel<<<grid_1d(n, 256, 148 * 8), 256, 0, s>>>(d_counts, d_flags, n, d_hist);
     return cudaGetLastError();
 }
 

@@ -44,6 +44,13 @@ public:
         for (auto& th : pool) th.join();
     }
     size_t size() const { return cptr_.size(); }
+    bool has_flags = false;  // vg_index_set_flags done for this graph (see VarigraphKernel)
+    // the map entries in the order the device index knows them
+    template <typename Fn>
+    void for_each_entry(std::unordered_map<uint64_t, kmerCovFreBitVec>& map, Fn fn) {
+        size_t i = 0;
+        for (auto& kv : map) fn(i++, kv.second);
+    }
     ~DeviceGraphIndex() { release(); }
 
 private:
@@ -70,6 +77,7 @@ private:
         map_ = &map;
         size_ = map.size();
         k_ = k;
+        has_flags = false;
     }
     const void* map_ = nullptr;
     size_t size_ = 0;
