@@ -54,8 +54,9 @@ struct DeviceGuard {
 };
 
 // ---- partitioned probing: set-up, scatter, flush ---------------------------------------------
-// Used when the slot table is much larger than L2 (direct probing then pays one random DRAM
-// access per k-mer) and the partition count stays within what one CTA tile can scatter well.
+// Used for every table of 8 MB or more whose slice count stays within what one CTA tile can scatter
+// well (<= 1024): direct probing of a table much larger than L2 pays one random DRAM access per
+// k-mer, and even an L2-resident table is probed faster through the sweep than with per-hit CAS.
 // VG_PARTITION=0 forces direct probing, =1 forces partitioning; VG_SLICE_BYTES / VG_ROUND_KEYS /
 // VG_PART_SLACK tune it (the tests use them to drive tiny tables through every branch).
 static int part_setup(vg_index* ix) {
@@ -64,16 +65,24 @@ static int part_setup(vg_index* ix) {
     const int force = env ? atoi(env) : -1;
     if (force == 0) return VG_OK;
     const uint64_t table_bytes = 32ull * ix->view.nbuckets;
+    // Slices of 32 MB (L2-resident with room to spare); 64 MB for very large tables to keep the slice
+    // count down; smaller ones for small tables so that at least three slices exist -- measured on
+    // B200, the scatter + sweep pipeline (pre-filter, fire-and-forget side counters) also beats direct
+    // probing with CAS when the whole table fits L2 (68 vs 52 G k-mers/s on a 96 MB table).
     uint64_t slice_bytes = 32ull << 20;
-    if (const char* e = getenv("VG_SLICE_BYTES")) slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
+    if (const char* e = getenv("VG_SLICE_BYTES")) {
+        slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
+    } else {
+        while (slice_bytes > (1ull << 20) && table_bytes / slice_bytes < 3) slice_bytes >>= 1;
+    }
     uint32_t shift = 0;
     while ((32ull << (shift + 1)) <= slice_bytes) ++shift;  // buckets per slice = 2^shift
     uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
-    if (P > 256 && !getenv("VG_SLICE_BYTES")) {  // big tables: 64 MB slices still fit L2, half the partitions
+    if (P > 256 && !getenv("VG_SLICE_BYTES")) {
         ++shift;
         P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
     }
-    if (force != 1 && table_bytes < (96ull << 20)) return VG_OK;  // the table itself lives in L2
+    if (force != 1 && table_bytes < (8ull << 20)) return VG_OK;   // tiny table: direct probing
     if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
     uint64_t round_keys = 1024ull << 20, slack = 65536;
     if (const char* e = getenv("VG_ROUND_KEYS")) round_keys = strtoull(e, nullptr, 10) >= 4096 ? strtoull(e, nullptr, 10) : round_keys;
