@@ -22,23 +22,16 @@ public:
                        kmerLen, vcfPloidy, debug, threads), buffer_(buffer), gpu_(gpu) {}
 
     void make_mbf_kernel() {
-        cerr << "[" << __func__ << "::" << getTime() << "] " << "Initiating computation of k-mer frequencies in the reference genome on GPU ...\n";
-        uint64_t bfSize = mGenomeSize - mKmerLen + 1;
-        double errorRate = 0.01;
-        mbfD = new BloomFilterKernel(bfSize, errorRate, gpu_, buffer_);
+        const uint64_t n = mGenomeSize - mKmerLen + 1;  // as ConstructIndex::make_mbf sizes it (p = 0.01)
+        mbfD = new BloomFilterKernel(n, 0.01, gpu_, buffer_);
         mbf = mbfD;  // ConstructIndex::index() / clear_mbf() use and free it through the base pointer
-        cerr << "[" << __func__ << "::" << getTime() << "] " << "Making Counting Bloom Filter with a false positive rate of " << errorRate << " ...\n";
-        for (const auto& [chromosome, sequence] : mFastaSeqMap) {
-            mbfD->add_sequence_kernel(sequence, mKmerLen);
-            cerr << "[" << __func__ << "::" << getTime() << "] " << "Chromosome '" << chromosome << "' processed successfully ...\n";
-        }
+        cerr << "[" << __func__ << "::" << getTime() << "] " << "Counting reference k-mers into the Bloom filter on GPU "
+             << gpu_ << " (" << mbf->get_size() << " cells, " << mbf->get_num() << " hashes) ...\n";
+        uint64_t added = 0;
+        for (const auto& [chromosome, sequence] : mFastaSeqMap) added += mbfD->add_sequence_kernel(sequence, mKmerLen);
         mbfD->copyFilterDToHost();
-        cerr << "[" << __func__ << "::" << getTime() << "] " << "Counting Bloom Filter constructed successfully ..." << endl << endl;
-        cerr << "           - " << "Counting Bloom Filter size: " << mbf->get_size() << endl;
-        cerr << "           - " << "Hash functions count: " << mbf->get_num() << endl;
-        cerr << fixed << setprecision(2);
-        cerr << "           - " << "Counting Bloom Filter usage rate: " << mbf->get_cap() << endl << endl << endl;
-        cerr << defaultfloat << setprecision(6);
+        cerr << "[" << __func__ << "::" << getTime() << "] " << added << " k-mers added; filter usage rate "
+             << fixed << setprecision(2) << mbf->get_cap() << defaultfloat << setprecision(6) << "\n\n";
         malloc_trim(0);
     }
 

@@ -42,10 +42,8 @@ public:
         ci->index_kernel();
         ci->save_index();
         ci->clear_mbf();
-        cerr << endl;
-        cerr << "           - " << "Total number of bases in the Genome Graph: " << ci->mGraphBaseNum << endl;
-        cerr << "           - " << "Total number of k-mers present in the Genome Graph: " << ci->mGraphKmerHashHapStrMap.size() << endl;
-        cerr << "           - " << "Total number of haplotypes present in the Genome Graph: " << ci->mHapMap.size() << endl << endl << endl;
+        cerr << "[" << __func__ << "::" << getTime() << "] " << "graph: " << ci->mGraphBaseNum << " bases, "
+             << ci->mGraphKmerHashHapStrMap.size() << " k-mers, " << ci->mHapMap.size() << " haplotypes\n\n";
     }
 
     // src/varigraph.cu:62-86
@@ -104,11 +102,8 @@ public:
         FastqKmerKernelClass.build_fastq_index_kernel();
         ReadDepth_ = FastqKmerKernelClass.mReadBase / (float)ConstructIndexClassPtr_->mGenomeSize;
         cal_ave_cov_kmer_kernel();
-        cerr << endl;
-        cerr << fixed << setprecision(2);
-        cerr << "           - " << "Size of the sequenced data: " << FastqKmerKernelClass.mReadBase / 1e9 << " Gb" << endl;
-        cerr << "           - " << "Depth of the sequenced data: " << ReadDepth_ << endl;
-        cerr << "           - " << "Coverage of haplotype k-mers: " << hapKmerCoverage_ << endl << endl << endl;
-        cerr << defaultfloat << setprecision(6);
+        cerr << "[" << __func__ << "::" << getTime() << "] " << fixed << setprecision(2) << "sequenced "
+             << FastqKmerKernelClass.mReadBase / 1e9 << " Gb, depth " << ReadDepth_ << ", haplotype k-mer coverage "
+             << hapKmerCoverage_ << defaultfloat << setprecision(6) << "\n\n";
     }
 };
