@@ -197,9 +197,15 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
     int rc = count_device_chunk(ix, sl.d_buf, len, c->compute_stream);
     if (rc) return rc;
     CU(cudaEventRecord(sl.done, c->compute_stream));
-    // Staged input arrives at PCIe speed, slower than the kernels: sweep every 256 M k-mers so the
-    // sweeps hide under the copies and only a short one is left after the last piece.
-    if (ix->part.enabled && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, 256ull << 20)) {
+    // Staged input arrives at PCIe speed, slower than the kernels: sweep every 384 M k-mers (tunable:
+    // VG_STAGED_ROUND_KEYS) so the sweeps hide under the copies and only a short one is left after
+    // the last piece.
+    static const uint64_t staged_round = [] {
+        const char* e = getenv("VG_STAGED_ROUND_KEYS");
+        const uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
+        return v >= 4096 ? v : (384ull << 20);  // measured flat between 256 M and 1 G, worse below
+    }();
+    if (ix->part.enabled && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, staged_round)) {
         rc = part_flush(ix, c->compute_stream);
         if (rc) return rc;
     }
