@@ -264,15 +264,14 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
 // ---------------------------------------------------------------------------
 // partitioned probing: scatter by table slice, then probe slice by slice out of L2
 // ---------------------------------------------------------------------------
-constexpr int kTileKeys = kCtaThreads * kSegBytes;  // at most one key per byte of a CTA tile
-
-struct ScatterSmem {
-    uint64_t key[kTileKeys];
-    uint32_t hist[kMaxPartitions];
-    uint32_t off[kMaxPartitions];
-    uint32_t fit[kMaxPartitions];
-    unsigned long long base[kMaxPartitions];
-    uint8_t lut[256];
+// Shared memory of the scatter (dynamic, sized by the launcher): nbuf buffers of
+//   hist[P]        k-mers of the tile per table slice
+//   bins[P * cap]  the tile's k-mers, one fixed-capacity bin per slice
+// plus the nt4 LUT.  With two buffers a CTA needs one barrier per tile: the copy-out of tile t
+// overlaps the encoding of tile t+1 by its faster warps.
+struct ScatterCfg {
+    uint32_t bin_cap;  // keys per slice bin; the rare overflow goes to global memory key by key
+    uint32_t nbuf;     // 1 or 2
 };
 
 // Rare path of the scatter: the key's partition buffer is full (a very skewed round, e.g. thousands
@@ -304,138 +303,123 @@ __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const u
     atomicOr(words + w, prefilter_mask(bits));
 }
 
+// A key that finds its tile bin full: reserve one place in the slice's key list right away.
+__device__ __noinline__ void scatter_one_global(IndexView ix, PartView pv, uint32_t p, uint64_t key, CountStats* stats) {
+    const unsigned long long pos = atomicAdd(&pv.cursor[p], 1ull);
+    if (pos < pv.cap) pv.keybuf[(uint64_t)p * pv.cap + pos] = key;
+    else probe_one_direct(ix, key, stats);
+}
+
+// K1 of the partitioned path.  Per 4 KiB CTA tile, eight positions per lane at a time: encode + hash,
+// drop what the presence pre-filter rules out, and append each survivor to its table slice's bin in
+// shared memory (rank = shared-memory atomic).  After ONE barrier the warps copy the bins out:
+// one global reservation per slice and tile (all slices of a warp reserved at once, a lane each),
+// then coalesced 8-byte stores -- a tile's run for a slice is contiguous in the slice's key list.
 template <bool kOdd, bool kK28>
-__global__ void __launch_bounds__(kCtaThreads, 3)
-scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, Chunk c, int64_t first_tile, int64_t ntiles, CountStats* stats) {
+__global__ void __launch_bounds__(kCtaThreads, 4)
+scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
+               CountStats* stats) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
+    const uint32_t P = pv.P, cap = cfg.bin_cap;
+    uint64_t* bins0 = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* hist0 = reinterpret_cast<uint32_t*>(bins0 + (size_t)cfg.nbuf * P * cap);
+    uint8_t* lut = reinterpret_cast<uint8_t*>(hist0 + (size_t)cfg.nbuf * P);
     __shared__ unsigned long long blk_pos;
-    lut_init(sm.lut);
+    lut_init(lut);
     if (threadIdx.x == 0) blk_pos = 0;
+    for (uint32_t i = threadIdx.x; i < cfg.nbuf * P; i += blockDim.x) hist0[i] = 0;
+    __syncthreads();
     KmerParams kp{ix.k, ix.mask};
-    const uint32_t P = pv.P;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t n_pos = 0;
+    uint32_t n_pos = 0, buf = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sm.hist[i] = 0;
-        __syncthreads();
-        // phase 1: encode; rank every emitted key inside its partition (order within a tile is free)
+        uint32_t* hist = hist0 + (size_t)buf * P;
+        uint64_t* bins = bins0 + (size_t)buf * P * cap;
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
-        uint64_t keys[16];
-        uint32_t emit;
-        if (pf.words) {
-            // Presence pre-filter (L2-resident, never a false negative).  The filter words of the first
-            // eight k-mers are in flight while the next eight are rolled and hashed.
-            uint32_t fw[16], fb[16];  // filter word; the key's two bit positions (5 + 5 bits)
-            auto fetch8 = [&](int g, uint32_t e8) {
+        // ---- encode, filter, bin -----------------------------------------------------------------
+        auto bin8 = [&](const uint64_t (&keys)[8], uint32_t emit) {
+            if (pf.words) {  // L2-resident presence pre-filter: never a false negative
+                uint32_t fw[8], fb[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     uint32_t w;
-                    prefilter_slot(keys[g + j], pf.nwords, w, fb[g + j]);
-                    fw[g + j] = ((e8 >> j) & 1u) ? __ldg(pf.words + w) : 0u;
+                    prefilter_slot(keys[j], pf.nwords, w, fb[j]);
+                    fw[j] = ((emit >> j) & 1u) ? __ldg(pf.words + w) : 0u;
                 }
-            };
-            if (kOdd) {
-                OddEncoder enc;
-                enc.init(c, off, kp, sm.lut);
-                uint64_t h[8];
-                const uint32_t e0 = enc.next<8>(kp, h);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) keys[j] = h[j];
-                fetch8(0, e0);
-                const uint32_t e1 = enc.next<8>(kp, h);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) keys[8 + j] = h[j];
-                fetch8(8, e1);
-                emit = e0 | (e1 << 8);
-            } else {
-                emit = encode_keys_any(c, off, kp, sm.lut, keys);
-                fetch8(0, emit & 0xffu);
-                fetch8(8, emit >> 8);
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t m = prefilter_mask(fb[j]);
+                    if ((fw[j] & m) != m) emit &= ~(1u << j);
+                }
             }
-            n_pos += __popc(emit);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t m = prefilter_mask(fb[j]);
-                if ((fw[j] & m) != m) emit &= ~(1u << j);
-            }
-        } else {
-            emit = kOdd ? encode_keys_odd(c, off, kp, sm.lut, keys) : encode_keys_any(c, off, kp, sm.lut, keys);
-            n_pos += __popc(emit);
-        }
-        uint32_t where[16];  // partition << 12 | rank
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            where[j] = 0;
-            if ((emit >> j) & 1u) {
-                if (kK28 && keys[j] == kKey56Max) {  // the hash no slot can hold: counted beside the table
-                    emit &= ~(1u << j);
-                    if (ix.has_special) {
-                        atomicAdd(ix.special, 1ull);
-                        atomicAdd(&stats->hits, 1ull);
+            for (int j = 0; j < 8; ++j) {
+                if ((emit >> j) & 1u) {
+                    if (kK28 && keys[j] == kKey56Max) {  // the hash no slot can hold: counted beside the table
+                        if (ix.has_special) {
+                            atomicAdd(ix.special, 1ull);
+                            atomicAdd(&stats->hits, 1ull);
+                        }
+                        continue;
                     }
-                    continue;
-                }
-                const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
-                where[j] = (p << 12) | atomicAdd(&sm.hist[p], 1u);
-            }
-        }
-        __syncthreads();
-        // phase 2: offsets inside the tile (warp 0) and space in the global partition buffers
-        if (warp == 0) {
-            const uint32_t per = (P + 31) / 32;  // consecutive slices per lane
-            uint32_t sum = 0;
-            for (uint32_t i = 0; i < per; ++i) {
-                const uint32_t idx = lane * per + i;
-                sum += idx < P ? sm.hist[idx] : 0u;
-            }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(kFullMask, incl, d);
-                if (lane >= (uint32_t)d) incl += y;
-            }
-            uint32_t run = incl - sum;
-            for (uint32_t i = 0; i < per; ++i) {
-                const uint32_t idx = lane * per + i;
-                if (idx < P) {
-                    sm.off[idx] = run;
-                    run += sm.hist[idx];
+                    const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
+                    const uint32_t r = atomicAdd(&hist[p], 1u);
+                    if (r < cap) bins[(size_t)p * cap + r] = keys[j];
+                    else scatter_one_global(ix, pv, p, keys[j], stats);
                 }
             }
-        }
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-            const uint32_t cnt = sm.hist[i];
-            unsigned long long b = 0;
-            uint32_t fit = 0;
-            if (cnt) {
-                b = atomicAdd(&pv.cursor[i], (unsigned long long)cnt);
-                fit = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)cnt, pv.cap - b);
-            }
-            sm.base[i] = b;
-            sm.fit[i] = fit;
-        }
-        __syncthreads();
-        // phase 3: tile-local sort by partition in shared memory
+        };
+        if (kOdd) {
+            OddEncoder enc;
+            enc.init(c, off, kp, lut);
+            uint64_t keys[8];
+            uint32_t emit = enc.next<8>(kp, keys);
+            n_pos += __popc(emit);
+            bin8(keys, emit);
+            emit = enc.next<8>(kp, keys);
+            n_pos += __popc(emit);
+            bin8(keys, emit);
+        } else {
+            uint64_t k16[16], keys[8];
+            const uint32_t emit = encode_keys_any(c, off, kp, lut, k16);
+            n_pos += __popc(emit);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if ((emit >> j) & 1u) {
-                const uint32_t p = where[j] >> 12;
-                sm.key[sm.off[p] + (where[j] & 0xfffu)] = keys[j];
-            }
+            for (int j = 0; j < 8; ++j) keys[j] = k16[j];
+            bin8(keys, emit & 0xffu);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) keys[j] = k16[8 + j];
+            bin8(keys, emit >> 8);
         }
         __syncthreads();
-        // phase 4: coalesced copy-out, one partition run per warp at a time (contiguous on both sides)
-        for (uint32_t p = warp; p < P; p += kCtaThreads / 32) {
-            const uint32_t cnt = sm.hist[p], fit = sm.fit[p], src = sm.off[p];
-            uint64_t* dst = pv.keybuf + (uint64_t)p * pv.cap + sm.base[p];
-            for (uint32_t i = lane; i < cnt; i += 32) {
-                const uint64_t key = sm.key[src + i];
-                if (i < fit) dst[i] = key;
-                else probe_one_direct(ix, key, stats);  // partition full: still counted, exactly
+        // ---- copy-out: slices warp, warp + 8, ...; lane l reserves for the l-th of them ----------
+        for (uint32_t p0 = warp; p0 < P; p0 += 32 * (kCtaThreads / 32)) {
+            const uint32_t mine = p0 + lane * (kCtaThreads / 32);
+            uint32_t cnt = 0;
+            unsigned long long base = 0;
+            if (mine < P) {
+                cnt = min(hist[mine], cap);
+                hist[mine] = 0;  // re-armed for the tile that reuses this buffer
+                if (cnt) base = atomicAdd(&pv.cursor[mine], (unsigned long long)cnt);
+            }
+#pragma unroll 1
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t p = p0 + l * (kCtaThreads / 32);
+                if (p >= P) break;
+                const uint32_t n = __shfl_sync(kFullMask, cnt, l);
+                if (n == 0) continue;
+                const unsigned long long b = __shfl_sync(kFullMask, base, l);
+                const uint32_t fit = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
+                uint64_t* dst = pv.keybuf + (uint64_t)p * pv.cap + b;
+                const uint64_t* src = bins + (size_t)p * cap;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint64_t key = src[i];
+                    if (i < fit) dst[i] = key;
+                    else probe_one_direct(ix, key, stats);  // slice list full: still counted, exactly
+                }
             }
         }
-        __syncthreads();
+        if (cfg.nbuf == 2) buf ^= 1;
+        else __syncthreads();
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_pos += __shfl_xor_sync(kFullMask, n_pos, d);
@@ -849,10 +833,23 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
                            cudaStream_t s) {
     if (ntiles <= 0) return cudaSuccess;
     Chunk c = make_chunk(d_bases, nbytes);
-    using KernelT = void (*)(IndexView, PartView, PrefilterView, Chunk, int64_t, int64_t, CountStats*);
+    using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true, false>
                               : (ix.k == 28 ? (KernelT)scatter_kernel<false, true> : (KernelT)scatter_kernel<false, false>);
-    const size_t smem = sizeof(ScatterSmem);
+    // Bin capacity: ~2.2x the expected k-mers per slice and tile (the pre-filter passes roughly half),
+    // within a shared-memory budget that still lets four CTAs share an SM; two buffers when they fit.
+    static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 2.2; }();
+    static const int want_nbuf = [] { const char* e = getenv("VG_SCATTER_NBUF"); return e ? atoi(e) : 0; }();
+    static const size_t budget = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52) * 1024; }();
+    const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
+    uint32_t cap = (uint32_t)(expect * capx) + 8;
+    ScatterCfg cfg{cap, 2};
+    auto bytes = [&](uint32_t cp, uint32_t nb) { return (size_t)nb * pv.P * ((size_t)cp * 8 + 4) + 256; };
+    // measured on B200: one buffer (two barriers per tile, more CTAs per SM) beats two
+    if (want_nbuf != 2 || bytes(cap, 2) > budget) cfg.nbuf = 1;
+    while (cap > 4 && bytes(cap, cfg.nbuf) > budget) --cap;
+    cfg.bin_cap = cap;
+    const size_t smem = bytes(cap, cfg.nbuf);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -861,7 +858,7 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem) != cudaSuccess || occ < 1) occ = 1;
     int64_t grid = (int64_t)nsm * occ;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, kCtaThreads, smem, s>>>(ix, pv, pf, c, first_tile, ntiles, d_stats);
+    kern<<<(unsigned)grid, kCtaThreads, smem, s>>>(ix, pv, pf, cfg, c, first_tile, ntiles, d_stats);
     return cudaGetLastError();
 }
 
