@@ -303,6 +303,15 @@ __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const u
     atomicOr(words + w, prefilter_mask(bits));
 }
 
+__device__ __forceinline__ void st_shared_u64(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_shared_u64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
 // A key that finds its tile bin full: reserve one place in the slice's key list right away.
 __device__ __noinline__ void scatter_one_global(IndexView ix, PartView pv, uint32_t p, uint64_t key, CountStats* stats) {
     const unsigned long long pos = atomicAdd(&pv.cursor[p], 1ull);
@@ -335,6 +344,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         uint32_t* hist = hist0 + (size_t)buf * P;
         uint64_t* bins = bins0 + (size_t)buf * P * cap;
+        const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);  // 32-bit shared-memory address
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         // ---- encode, filter, bin -----------------------------------------------------------------
         auto bin8 = [&](const uint64_t (&keys)[8], uint32_t emit) {
@@ -352,8 +362,11 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                     if ((fw[j] & m) != m) emit &= ~(1u << j);
                 }
             }
+            uint32_t over = 0;   // keys whose bin is full (rare): handled after the hot loop
+            uint32_t ps[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+                ps[j] = 0;
                 if ((emit >> j) & 1u) {
                     if (kK28 && keys[j] == kKey56Max) {  // the hash no slot can hold: counted beside the table
                         if (ix.has_special) {
@@ -364,9 +377,15 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                     }
                     const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
                     const uint32_t r = atomicAdd(&hist[p], 1u);
-                    if (r < cap) bins[(size_t)p * cap + r] = keys[j];
-                    else scatter_one_global(ix, pv, p, keys[j], stats);
+                    ps[j] = p;
+                    if (r < cap) st_shared_u64(bins_s + (p * cap + r) * 8u, keys[j]);
+                    else over |= 1u << j;
                 }
+            }
+            if (over) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if ((over >> j) & 1u) scatter_one_global(ix, pv, ps[j], keys[j], stats);
             }
         };
         if (kOdd) {
@@ -410,12 +429,10 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                 const unsigned long long b = __shfl_sync(kFullMask, base, l);
                 const uint32_t fit = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
                 uint64_t* dst = pv.keybuf + (uint64_t)p * pv.cap + b;
-                const uint64_t* src = bins + (size_t)p * cap;
-                for (uint32_t i = lane; i < n; i += 32) {
-                    const uint64_t key = src[i];
-                    if (i < fit) dst[i] = key;
-                    else probe_one_direct(ix, key, stats);  // slice list full: still counted, exactly
-                }
+                const uint32_t src_s = bins_s + p * cap * 8u;
+                for (uint32_t i = lane; i < fit; i += 32) dst[i] = ld_shared_u64(src_s + i * 8u);
+                if (fit < n)  // slice list full (a very skewed round): still counted, exactly
+                    for (uint32_t i = fit + lane; i < n; i += 32) probe_one_direct(ix, ld_shared_u64(src_s + i * 8u), stats);
             }
         }
         if (cfg.nbuf == 2) buf ^= 1;
