@@ -319,7 +319,10 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--buffer-mb", type=int, default=64)
     ap.add_argument("--load-factor", type=float, default=0.0)
+    ap.add_argument("--kmer", type=int, default=27, help="k (BASELINE configs use the default 27)")
     a = ap.parse_args()
+    global K
+    K = a.kmer
     rank, world, local = dist_info()
     steps, warmup = a.steps, max(a.warmup, 3 if a.impl == "b200" else a.warmup)
     L = a.genome_mb * 1_000_000
