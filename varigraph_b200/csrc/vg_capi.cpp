@@ -365,7 +365,6 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     ix->view.k = k;
     ix->view.mask = (1ULL << (2 * k)) - 1;
     ix->view.nbuckets = (uint32_t)nb64;
-    ix->view.has_special = 0;
     auto bail = [&](int code) {
         vg_index_destroy(ix);
         return code;
@@ -383,7 +382,6 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     CUB(cudaMalloc((void**)&ix->d_counts, std::max<uint64_t>(n, 4)));
     CUB(cudaMalloc((void**)&ix->d_misc, sizeof(vg::DeviceMisc)));
     CUB(cudaMemset(ix->d_misc, 0, sizeof(vg::DeviceMisc)));
-    ix->view.special = &ix->d_misc->special;
     cudaStream_t s = c->compute_stream;
     CUB(vg::launch_table_fill_empty(ix->view.slots, nslots, s));
 
@@ -400,12 +398,12 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
             uint64_t h = key >> 8;
             if (h > ix->view.mask)
                 return bail(fail(VG_E_INVALID, "keys[%llu]: hash exceeds 2k bits", (unsigned long long)(off + i)));
-            if (h == ((1ULL << 56) - 1)) ix->view.has_special = 1;
             tmp[(size_t)i] = h;
         }
         CUB(cudaMemcpyAsync(ix->d_key56 + off, tmp.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         CUB(cudaStreamSynchronize(s));
     }
+    CUB(vg::launch_unhash(ix->d_key56, n, ix->view.mask, s));
     CUB(vg::launch_insert(ix->view, ix->d_key56, n, &ix->d_misc->report, s));
     vg::DeviceMisc misc;
     CUB(cudaMemcpyAsync(&misc, ix->d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));

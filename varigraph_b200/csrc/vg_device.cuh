@@ -65,6 +65,30 @@ __device__ __forceinline__ uint64_t hash64_wide(uint64_t x, uint32_t mask_hi) {
     return x;
 }
 
+// hash64 is a bijection on [0, 2^2k): the inverse lets the device index be keyed by the canonical
+// k-mer itself, so the per-position hash (26 instructions) is paid once per index key at build time
+// instead of once per read position.  Matching canonical k-mers == matching their hashes.
+__host__ __device__ constexpr uint64_t inv_odd64(uint64_t a) {  // a^-1 mod 2^64 by Newton's iteration
+    uint64_t x = a;
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+__device__ __forceinline__ uint64_t unxorshift(uint64_t y, int s) {
+    uint64_t x = y;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x = y ^ (x >> s);  // enough for 56-bit values and s >= 14
+    return x;
+}
+__device__ __forceinline__ uint64_t hash64_inv(uint64_t y, uint64_t m) {
+    uint64_t x = (y * inv_odd64(0x80000001ULL)) & m;
+    x = unxorshift(x, 28);
+    x = (x * inv_odd64(21ULL)) & m;
+    x = unxorshift(x, 14);
+    x = (x * inv_odd64(265ULL)) & m;
+    x = unxorshift(x, 24);
+    return ((x + 1ULL) * inv_odd64(0x1FFFFFULL)) & m;
+}
+
 // Reverse complement of the k bases held in the low 2k bits of f (oldest base highest).
 __device__ __forceinline__ uint64_t revcomp2k(uint64_t f, uint32_t k) {
     uint64_t y = __brevll(~f);
@@ -131,8 +155,10 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
     return r;
 }
 
+// Home bucket of a key (a canonical k-mer, i.e. structured input: fold the high half down before the
+// Fibonacci multiply, take the product's high word, range-reduce without a division).
 __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets) {
-    uint64_t x = key56 * 0x9E3779B97F4A7C15ULL;
+    uint64_t x = (key56 ^ (key56 >> 29)) * 0x9E3779B97F4A7C15ULL;
     return __umulhi((uint32_t)(x >> 32), nbuckets);
 }
 
@@ -228,9 +254,10 @@ struct OddEncoder {
         rev = revcomp2k(fwd, kp.k);
     }
 
-    // Consumes the next N own positions: keys[j] = hash64(canonical k-mer ending there); returns the
-    // N-bit emit mask (bit j: the reference encoder emits; keys[j] is meaningless where it does not).
-    template <int N>
+    // Consumes the next N own positions: keys[j] = the canonical k-mer ending there (kHashed: its
+    // hash64, i.e. the reference's key >> 8); returns the N-bit emit mask (bit j: the reference encoder
+    // emits; keys[j] is meaningless where it does not).
+    template <int N, bool kHashed = true>
     __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N]) {
         const uint32_t top = 2 * (kp.k - 1);
         uint32_t emit = 0;
@@ -243,7 +270,8 @@ struct OddEncoder {
                 fwd = ((fwd << 2) | cb) & kp.mask;
                 const uint32_t rhi = (uint32_t)(rev >> 32), rlo = (uint32_t)rev;
                 rev = ((uint64_t)((rhi >> 2) | ((3u ^ cb) << tsh)) << 32) | __funnelshift_r(rlo, rhi, 2);
-                keys[j] = hash64_wide(fwd < rev ? fwd : rev, mask_hi);
+                const uint64_t canon = fwd < rev ? fwd : rev;
+                keys[j] = kHashed ? hash64_wide(canon, mask_hi) : canon;
                 emit |= ((all_k >> 15) & 1u) << j;
                 all_k <<= 1;
             }
@@ -255,7 +283,8 @@ struct OddEncoder {
             p0 <<= 2;
             fwd = ((fwd << 2) | cb) & kp.mask;
             rev = (rev >> 2) | ((3ULL ^ cb) << top);
-            keys[j] = hash64(fwd < rev ? fwd : rev, kp.mask);
+            const uint64_t canon = fwd < rev ? fwd : rev;
+            keys[j] = kHashed ? hash64(canon, kp.mask) : canon;
             emit |= ((all_k >> 15) & 1u) << j;
             all_k <<= 1;
         }
@@ -283,6 +312,7 @@ struct RollState {
     uint32_t run;  // saturates at k: only run >= k is ever observed
 };
 
+template <bool kHashed = true>
 __device__ __forceinline__ bool roll_push(RollState& s, uint32_t e, const KmerParams& kp, uint64_t& key) {
     if (!(e & 4u)) {
         s.run = 0;
@@ -294,7 +324,8 @@ __device__ __forceinline__ bool roll_push(RollState& s, uint32_t e, const KmerPa
     if (s.fwd == s.rev) return false;
     if (s.run < kp.k) s.run += 1;
     if (s.run < kp.k) return false;
-    key = hash64(s.fwd < s.rev ? s.fwd : s.rev, kp.mask);
+    const uint64_t canon = s.fwd < s.rev ? s.fwd : s.rev;
+    key = kHashed ? hash64(canon, kp.mask) : canon;
     return true;
 }
 
@@ -303,6 +334,7 @@ __device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, con
     return lut[c.al[pos]];
 }
 
+template <bool kHashed = true>
 __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
                                            const uint8_t* lut, uint64_t (&keys)[16]) {
 #pragma unroll
@@ -357,7 +389,7 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
             continue;
         }
         uint64_t key;
-        if (roll_push(st, e, kp, key)) {
+        if (roll_push<kHashed>(st, e, kp, key)) {
             keys[j] = key;
             emit |= 1u << j;
         }

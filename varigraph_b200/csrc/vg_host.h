@@ -21,7 +21,6 @@ struct StageSlot {
 struct DeviceMisc {  // small device-resident scalars of one index
     CountStats stats;
     InsertReport report;
-    unsigned long long special;
 };
 
 constexpr int kCtaThreadsHost = 256;                // == kCtaThreads in vg_device.cuh
@@ -60,7 +59,7 @@ struct vg_index {
     PartState part;
     uint64_t n = 0;
     vg::IndexView view{};
-    uint64_t* d_key56 = nullptr;   // key order given at create, hash only (key >> 8)
+    uint64_t* d_key56 = nullptr;   // key order given at create: the canonical k-mer of each key
     uint8_t* d_counts = nullptr;   // scratch for vg_count_end
     uint8_t* d_flags = nullptr;    // optional per-entry subset for vg_count_histogram
     unsigned long long* d_hist = nullptr;

@@ -6,12 +6,10 @@
 namespace vg {
 
 struct IndexView {
-    uint64_t* slots;                // nbuckets * 4 slots of [hash:56 | count:8]; empty = ~0
+    uint64_t* slots;                // nbuckets * 4 slots of [canonical k-mer:56 | count:8]; empty = ~0
     uint32_t nbuckets;
     uint32_t k;
     uint64_t mask;                  // 2^(2k) - 1
-    unsigned long long* special;    // counter for the one key a slot cannot hold (k == 28 only)
-    int has_special;
 };
 
 // Presence pre-filter: a word-blocked Bloom filter over the index keys (both bits of a key sit in
@@ -59,6 +57,8 @@ struct CbfView {
 int sm_count(int device);
 
 cudaError_t launch_table_fill_empty(uint64_t* slots, uint64_t nslots, cudaStream_t s);
+// in place: hash (the reference's key >> 8) -> canonical k-mer (hash64 is invertible)
+cudaError_t launch_unhash(uint64_t* d_key56, uint64_t n, uint64_t mask, cudaStream_t s);
 cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
                           cudaStream_t s);
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);

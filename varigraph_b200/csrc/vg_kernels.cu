@@ -26,13 +26,18 @@ __global__ void fill_empty_kernel(uint64_t* slots, uint64_t nslots) {
     for (; i < nslots; i += stride) slots[i] = kSlotEmpty;
 }
 
+__global__ void unhash_kernel(uint64_t* key56, uint64_t n, uint64_t mask) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key56[i] = hash64_inv(key56[i], mask);
+}
+
 // One thread per key.  Claims the first empty slot in probe order with a 64-bit CAS; because
 // slots are never freed, "an empty slot ends the search" holds for every later lookup.
 __global__ void insert_kernel(IndexView ix, const uint64_t* __restrict__ key56, uint64_t n, InsertReport* rep) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t key = key56[i];
-    if (key == kKey56Max) return;  // lives in ix.special
+    if (key == kKey56Max) return;  // not a canonical k-mer (min(fwd, rev) is never all ones): cannot be hit
     uint64_t want = key << 8;
     uint32_t b = bucket_of(key, ix.nbuckets);
     for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
@@ -110,25 +115,13 @@ __device__ __forceinline__ T pick(const T (&a)[N], uint32_t i) {  // a[i] withou
 //    after all of them are in flight, so the round trips overlap instead of serialising.
 // st[b]: bit 31 hit, bits 16-23 count seen, bits 8-9 slot in bucket; later bit 30 CAS issued and
 // bits 0-7 the amount to add.
-template <bool kK28, int kBatch>
+template <int kBatch>
 __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint64_t (&keys)[kBatch], uint32_t emit,
                                                 uint32_t& n_hit) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t bk[kBatch], st[kBatch];
     uint64_t prev[kBatch];
-    uint32_t havem = emit & ((1u << kBatch) - 1);
-    if (kK28) {
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            if (((havem >> b) & 1u) && keys[b] == kKey56Max) {  // the hash no slot can hold
-                havem &= ~(1u << b);
-                if (ix.has_special) {
-                    atomicAdd(ix.special, 1ull);
-                    n_hit += 1;
-                }
-            }
-        }
-    }
+    const uint32_t havem = emit & ((1u << kBatch) - 1);
     uint32_t pend = 0;  // positions whose search continues in the next bucket
     {
         uint64_t v[kBatch][4];
@@ -209,7 +202,7 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
     }
 }
 
-template <bool kOdd, bool kK28, int kBatch>
+template <bool kOdd, int kBatch>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
 count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
     __shared__ uint8_t lut[256];
@@ -228,20 +221,20 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
 #pragma unroll 1
             for (int part = 0; part < 16 / kBatch; ++part) {
                 uint64_t keys[kBatch];
-                uint32_t emit = enc.next<kBatch>(kp, keys);
+                uint32_t emit = enc.next<kBatch, false>(kp, keys);
                 n_pos += __popc(emit);
-                probe_and_count<kK28, kBatch>(ix, keys, emit, n_hit);
+                probe_and_count<kBatch>(ix, keys, emit, n_hit);
             }
         } else {
             uint64_t k16[16];
-            uint32_t emit = encode_keys_any(c, off, kp, lut, k16);
+            uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16);
             n_pos += __popc(emit);
 #pragma unroll
             for (int part = 0; part < 16 / kBatch; ++part) {
                 uint64_t keys[kBatch];
 #pragma unroll
                 for (int j = 0; j < kBatch; ++j) keys[j] = k16[part * kBatch + j];
-                probe_and_count<kK28, kBatch>(ix, keys, (emit >> (part * kBatch)) & ((1u << kBatch) - 1), n_hit);
+                probe_and_count<kBatch>(ix, keys, (emit >> (part * kBatch)) & ((1u << kBatch) - 1), n_hit);
             }
         }
     }
@@ -324,7 +317,7 @@ __device__ __noinline__ void scatter_one_global(IndexView ix, PartView pv, uint3
 // shared memory (rank = shared-memory atomic).  After ONE barrier the warps copy the bins out:
 // one global reservation per slice and tile (all slices of a warp reserved at once, a lane each),
 // then coalesced 8-byte stores -- a tile's run for a slice is contiguous in the slice's key list.
-template <bool kOdd, bool kK28>
+template <bool kOdd>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
@@ -368,13 +361,6 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             for (int j = 0; j < 8; ++j) {
                 ps[j] = 0;
                 if ((emit >> j) & 1u) {
-                    if (kK28 && keys[j] == kKey56Max) {  // the hash no slot can hold: counted beside the table
-                        if (ix.has_special) {
-                            atomicAdd(ix.special, 1ull);
-                            atomicAdd(&stats->hits, 1ull);
-                        }
-                        continue;
-                    }
                     const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
                     const uint32_t r = atomicAdd(&hist[p], 1u);
                     ps[j] = p;
@@ -392,15 +378,15 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             OddEncoder enc;
             enc.init(c, off, kp, lut);
             uint64_t keys[8];
-            uint32_t emit = enc.next<8>(kp, keys);
+            uint32_t emit = enc.next<8, false>(kp, keys);
             n_pos += __popc(emit);
             bin8(keys, emit);
-            emit = enc.next<8>(kp, keys);
+            emit = enc.next<8, false>(kp, keys);
             n_pos += __popc(emit);
             bin8(keys, emit);
         } else {
             uint64_t k16[16], keys[8];
-            const uint32_t emit = encode_keys_any(c, off, kp, lut, k16);
+            const uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16);
             n_pos += __popc(emit);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[j];
@@ -619,8 +605,7 @@ __global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56,
     uint64_t key = key56[i];
     uint32_t c = 0;
     if (key == kKey56Max) {
-        unsigned long long s = *ix.special;
-        c = s > 255ull ? 255u : (uint32_t)s;
+        c = 0;  // not a canonical k-mer: no read position can produce it
     } else {
         uint32_t b = bucket_of(key, ix.nbuckets);
         for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
@@ -793,6 +778,12 @@ cudaError_t launch_table_fill_empty(uint64_t* slots, uint64_t nslots, cudaStream
     return cudaGetLastError();
 }
 
+cudaError_t launch_unhash(uint64_t* d_key56, uint64_t n, uint64_t mask, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    unhash_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_key56, n, mask);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
                           cudaStream_t s) {
     if (n == 0) return cudaSuccess;
@@ -804,9 +795,7 @@ cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s) {
     uint64_t nslots = 4ull * ix.nbuckets;
     clear_counts_kernel<<<grid_1d(nslots, 256, 148 * 16), 256, 0, s>>>(ix.slots, nslots);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return cudaMemsetAsync(ix.special, 0, sizeof(unsigned long long), s);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
@@ -816,8 +805,8 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
     int64_t ntiles = tiles_for(c);
     // persistent grid: exactly the CTAs that are resident at once, each striding over the tiles
     using KernelT = void (*)(IndexView, Chunk, int64_t, CountStats*);
-    KernelT kern = (ix.k & 1) ? (count_variant() == 4 ? (KernelT)count_kernel<true, false, 4> : (KernelT)count_kernel<true, false, 8>)
-                   : (ix.k == 28 ? (KernelT)count_kernel<false, true, 4> : (KernelT)count_kernel<false, false, 4>);
+    KernelT kern = (ix.k & 1) ? (count_variant() == 4 ? (KernelT)count_kernel<true, 4> : (KernelT)count_kernel<true, 8>)
+                              : (KernelT)count_kernel<false, 4>;
     int occ = 0;
     if (ctas_per_sm <= 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1) occ = 2;
@@ -826,14 +815,7 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
     }
     int64_t grid = (int64_t)nsm * occ;
     if (grid > ntiles) grid = ntiles;
-    if (ix.k & 1) {
-        if (count_variant() == 4) count_kernel<true, false, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
-        else count_kernel<true, false, 8><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
-    } else if (ix.k == 28) {
-        count_kernel<false, true, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
-    } else {
-        count_kernel<false, false, 4><<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
-    }
+    kern<<<(unsigned)grid, kCtaThreads, 0, s>>>(ix, c, ntiles, d_stats);
     return cudaGetLastError();
 }
 
@@ -851,8 +833,7 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     if (ntiles <= 0) return cudaSuccess;
     Chunk c = make_chunk(d_bases, nbytes);
     using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
-    KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true, false>
-                              : (ix.k == 28 ? (KernelT)scatter_kernel<false, true> : (KernelT)scatter_kernel<false, false>);
+    KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true> : (KernelT)scatter_kernel<false>;
     // Bin capacity: ~2.2x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // within a shared-memory budget that still lets four CTAs share an SM; two buffers when they fit.
     static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 2.2; }();
