@@ -10,6 +10,7 @@
 // Replaces (does not port) src/kmer.cu:39-69, src/fastq_kmer.cu:99-162 (sort + reduce_by_key +
 // host map probes) and src/counting_bloom_filter.cu:5-104 of the reference; results follow the
 // reference CPU path src/kmer.cpp:110-149 + src/fastq_kmer.cpp:126-141.
+#include <algorithm>
 #include <cstdlib>
 
 #include "vg_device.cuh"
@@ -257,14 +258,16 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
 // ---------------------------------------------------------------------------
 // partitioned probing: scatter by table slice, then probe slice by slice out of L2
 // ---------------------------------------------------------------------------
-// Shared memory of the scatter (dynamic, sized by the launcher): nbuf buffers of
-//   hist[P]        k-mers of the tile per table slice
-//   bins[P * cap]  the tile's k-mers, one fixed-capacity bin per slice
-// plus the nt4 LUT.  With two buffers a CTA needs one barrier per tile: the copy-out of tile t
-// overlaps the encoding of tile t+1 by its faster warps.
+// Shared memory of the scatter (dynamic, sized by the launcher):
+//   bins[P * stride]     the tile's k-mers, one fixed-capacity bin per table slice; the stride is odd
+//                        (in 8-byte words) so that equal ranks of different bins fall into different banks
+//   base[P]              where the tile's run starts in each slice's key list (after reservation)
+//   hist[P], cnt[P], fit[P]   k-mers per slice: seen / in the bin / fitting the slice's key list
+// plus the nt4 LUT.
 struct ScatterCfg {
-    uint32_t bin_cap;  // keys per slice bin; the rare overflow goes to global memory key by key
-    uint32_t nbuf;     // 1 or 2
+    uint32_t cap;     // keys per bin; the rare overflow goes to global memory key by key
+    uint32_t stride;  // cap | 1
+    uint32_t magic;   // 2^32 / cap + 1: slot / cap == __umulhi(slot, magic) for slot < 2^32 / cap
 };
 
 // Rare path of the scatter: the key's partition buffer is full (a very skewed round, e.g. thousands
@@ -314,30 +317,32 @@ __device__ __noinline__ void scatter_one_global(IndexView ix, PartView pv, uint3
 
 // K1 of the partitioned path.  Per 4 KiB CTA tile, eight positions per lane at a time: encode + hash,
 // drop what the presence pre-filter rules out, and append each survivor to its table slice's bin in
-// shared memory (rank = shared-memory atomic).  After ONE barrier the warps copy the bins out:
-// one global reservation per slice and tile (all slices of a warp reserved at once, a lane each),
-// then coalesced 8-byte stores -- a tile's run for a slice is contiguous in the slice's key list.
+// shared memory (rank = shared-memory atomic).  After a barrier the bins are copied out: one global
+// reservation per slice and tile (a thread per slice), a second barrier, then a thread per bin slot
+// -- a tile's run for a slice is contiguous in the slice's key list, so the 8-byte stores coalesce
+// run by run whatever the number of slices (a warp per bin wastes lanes once bins get short).
 template <bool kOdd>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const uint32_t P = pv.P, cap = cfg.bin_cap;
-    uint64_t* bins0 = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* hist0 = reinterpret_cast<uint32_t*>(bins0 + (size_t)cfg.nbuf * P * cap);
-    uint8_t* lut = reinterpret_cast<uint8_t*>(hist0 + (size_t)cfg.nbuf * P);
+    const uint32_t P = pv.P, cap = cfg.cap;
+    uint64_t* bins = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned long long* base_s = reinterpret_cast<unsigned long long*>(bins + (size_t)P * cfg.stride);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(base_s + P);
+    uint32_t* cnt_s = hist + P;
+    uint32_t* fit_s = cnt_s + P;
+    uint8_t* lut = reinterpret_cast<uint8_t*>(fit_s + P);
     __shared__ unsigned long long blk_pos;
     lut_init(lut);
     if (threadIdx.x == 0) blk_pos = 0;
-    for (uint32_t i = threadIdx.x; i < cfg.nbuf * P; i += blockDim.x) hist0[i] = 0;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     KmerParams kp{ix.k, ix.mask};
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t n_pos = 0, buf = 0;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);  // 32-bit shared-memory address
+    uint32_t n_pos = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        uint32_t* hist = hist0 + (size_t)buf * P;
-        uint64_t* bins = bins0 + (size_t)buf * P * cap;
-        const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);  // 32-bit shared-memory address
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         // ---- encode, filter, bin -----------------------------------------------------------------
         auto bin8 = [&](const uint64_t (&keys)[8], uint32_t emit) {
@@ -364,7 +369,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                     const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
                     const uint32_t r = atomicAdd(&hist[p], 1u);
                     ps[j] = p;
-                    if (r < cap) st_shared_u64(bins_s + (p * cap + r) * 8u, keys[j]);
+                    if (r < cap) st_shared_u64(bins_s + ((p * cfg.stride + r) << 3), keys[j]);
                     else over |= 1u << j;
                 }
             }
@@ -396,33 +401,28 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             bin8(keys, emit >> 8);
         }
         __syncthreads();
-        // ---- copy-out: slices warp, warp + 8, ...; lane l reserves for the l-th of them ----------
-        for (uint32_t p0 = warp; p0 < P; p0 += 32 * (kCtaThreads / 32)) {
-            const uint32_t mine = p0 + lane * (kCtaThreads / 32);
-            uint32_t cnt = 0;
-            unsigned long long base = 0;
-            if (mine < P) {
-                cnt = min(hist[mine], cap);
-                hist[mine] = 0;  // re-armed for the tile that reuses this buffer
-                if (cnt) base = atomicAdd(&pv.cursor[mine], (unsigned long long)cnt);
-            }
-#pragma unroll 1
-            for (uint32_t l = 0; l < 32; ++l) {
-                const uint32_t p = p0 + l * (kCtaThreads / 32);
-                if (p >= P) break;
-                const uint32_t n = __shfl_sync(kFullMask, cnt, l);
-                if (n == 0) continue;
-                const unsigned long long b = __shfl_sync(kFullMask, base, l);
-                const uint32_t fit = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
-                uint64_t* dst = pv.keybuf + (uint64_t)p * pv.cap + b;
-                const uint32_t src_s = bins_s + p * cap * 8u;
-                for (uint32_t i = lane; i < fit; i += 32) dst[i] = ld_shared_u64(src_s + i * 8u);
-                if (fit < n)  // slice list full (a very skewed round): still counted, exactly
-                    for (uint32_t i = fit + lane; i < n; i += 32) probe_one_direct(ix, ld_shared_u64(src_s + i * 8u), stats);
+        // ---- copy-out: reserve (one global atomic per slice and tile, all slices at once) ... ----------
+        for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) {
+            const uint32_t n = min(hist[p], cap);
+            hist[p] = 0;  // re-armed for the next tile
+            unsigned long long b = 0;
+            if (n) b = atomicAdd(&pv.cursor[p], (unsigned long long)n);
+            cnt_s[p] = n;
+            fit_s[p] = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
+            base_s[p] = (unsigned long long)p * pv.cap + b;
+        }
+        __syncthreads();
+        // ---- ... then one bin slot per thread and step; a bin's keys are contiguous on both sides ----
+        const uint32_t nslots = P * cap;
+        for (uint32_t q = threadIdx.x; q < nslots; q += blockDim.x) {
+            const uint32_t p = __umulhi(q, cfg.magic), i = q - p * cap;
+            if (i < cnt_s[p]) {
+                const uint64_t key = ld_shared_u64(bins_s + ((p * cfg.stride + i) << 3));
+                if (i < fit_s[p]) pv.keybuf[base_s[p] + i] = key;
+                else probe_one_direct(ix, key, stats);  // slice list full (a very skewed round): still exact
             }
         }
-        if (cfg.nbuf == 2) buf ^= 1;
-        else __syncthreads();
+        __syncthreads();
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_pos += __shfl_xor_sync(kFullMask, n_pos, d);
@@ -835,19 +835,22 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true> : (KernelT)scatter_kernel<false>;
     // Bin capacity: ~2.2x the expected k-mers per slice and tile (the pre-filter passes roughly half),
-    // within a shared-memory budget that still lets four CTAs share an SM; two buffers when they fit.
+    // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
+    // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
+    // path, so this only tunes speed.
     static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 2.2; }();
-    static const int want_nbuf = [] { const char* e = getenv("VG_SCATTER_NBUF"); return e ? atoi(e) : 0; }();
     static const size_t budget = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52) * 1024; }();
     const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
-    uint32_t cap = (uint32_t)(expect * capx) + 8;
-    ScatterCfg cfg{cap, 2};
-    auto bytes = [&](uint32_t cp, uint32_t nb) { return (size_t)nb * pv.P * ((size_t)cp * 8 + 4) + 256; };
-    // measured on B200: one buffer (two barriers per tile, more CTAs per SM) beats two
-    if (want_nbuf != 2 || bytes(cap, 2) > budget) cfg.nbuf = 1;
-    while (cap > 4 && bytes(cap, cfg.nbuf) > budget) --cap;
-    cfg.bin_cap = cap;
-    const size_t smem = bytes(cap, cfg.nbuf);
+    const uint32_t want = (uint32_t)(expect * capx) + 8;
+    auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 256; };
+    uint32_t cap = want;
+    while (cap > 4 && bytes(cap) > budget) --cap;
+    if (cap < want && cap < 24) {  // many slices: two CTAs per SM with deeper bins
+        cap = want;
+        while (cap > 4 && bytes(cap) > 2 * budget) --cap;
+    }
+    ScatterCfg cfg{cap, cap | 1u, (uint32_t)((1ull << 32) / cap) + 1u};
+    const size_t smem = bytes(cap);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
