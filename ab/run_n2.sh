@@ -1,6 +1,13 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-nvidia-smi topo -m 2>&1 | head -8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 2> gpurun_out/n2_err.log | tee gpurun_out/bench_n2.json | cut -c1-900
-tail -5 gpurun_out/n2_err.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 "$@" 2> gpurun_out/n2_err.log | tee -a gpurun_out/bench_n2.jsonl | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value %.4g e2e %.4g ms %.2f pass_ms %.2f | %s | eq=%s launches=%s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['config']['parallelism'],d['e2e']['counts_equal_device_path'],d['gpu_launches']))"; tail -3 gpurun_out/n2_err.log | cut -c1-300; }
+rm -f gpurun_out/bench_n2.jsonl
+echo "== p2p"; run
+echo "== nccl"; run --reduce nccl
+echo "== sharded"; run --index sharded
+echo "== sharded 256"; run --index sharded --round-mb 256

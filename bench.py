@@ -18,8 +18,12 @@ read k-mer of the sample against the index, produce the count vector.
   --impl reference   times that reference CPU path alone, same config/metric/unit
 
 N > 1 (torchrun): reads are sharded over ranks (each rank counts its own 30x sample: weak scaling),
-the index is replicated, and one NCCL all-reduce of the u32 count vector per sample (then clamp to
-255: exact) is the only exchange.
+the index is replicated, and the only exchange is one reduce of the count vectors per sample:
+min(255, sum over ranks), exact.  By default every rank reads its peers' u8 vectors over
+NVLink (vg_count_allreduce: CUDA IPC peer memory, a device-side barrier, no NCCL in the data path);
+--reduce nccl uses an NCCL all-reduce of u32 instead (also the fallback if peer mapping fails).
+--index sharded cuts the index itself over the ranks (the index > HBM layout): the scatter kernel
+stores every k-mer straight into the owning GPU's key list over NVLink, rounds of --round-mb.
 """
 from __future__ import annotations
 
@@ -320,6 +324,10 @@ def main() -> None:
     ap.add_argument("--buffer-mb", type=int, default=64)
     ap.add_argument("--load-factor", type=float, default=0.0)
     ap.add_argument("--kmer", type=int, default=27, help="k (BASELINE configs use the default 27)")
+    ap.add_argument("--index", default="replicated", choices=["replicated", "sharded"],
+                    help="N > 1: a replica of the index per GPU (default) or one index cut over the GPUs")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N > 1, replicated: how counts are combined")
+    ap.add_argument("--round-mb", type=int, default=512, help="sharded index: bases per rank and round")
     a = ap.parse_args()
     global K
     K = a.kmer
@@ -377,20 +385,60 @@ def main() -> None:
     stream = torch.cuda.Stream(device=dev)  # explicit: the legacy default stream's handle is 0 (= "unset")
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ix = capi.Index(ctx, keys_np, K, a.load_factor)
+    # ---- N > 1: map the peers' memory (handles travel through torch.distributed, data never does) ----
+    sharded = world > 1 and a.index == "sharded"
+    comm, reduce_how = None, ("nccl" if world > 1 else None)
+    if world > 1 and (sharded or a.reduce == "p2p"):
+        def exchange(mine: bytes):
+            got = [None] * world
+            dist.all_gather_object(got, mine)
+            return got
+        round_bytes = a.round_mb << 20
+        table_est = int(nkeys / world / (4 * (a.load_factor or 0.3)) * 32 * 1.1) + (64 << 20)
+        arena = (nkeys + (1 << 20)) + ((table_est + round_bytes * 10 + (128 << 20)) if sharded else 0)
+        ok = torch.ones(1, device=dev)
+        try:
+            comm = capi.Comm(ctx, rank, world, arena, exchange)
+        except capi.VgError as ex:
+            sys.stderr.write(f"rank {rank}: peer mapping failed ({ex})\n")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            if sharded:
+                raise SystemExit("bench.py: --index sharded needs CUDA IPC peer mappings")
+            comm = None
+        else:
+            reduce_how = "p2p"
+    ix = capi.Index(ctx, keys_np, K, a.load_factor, comm=comm if sharded else None,
+                    round_bytes=(a.round_mb << 20) if sharded else 0)
     out32 = torch.empty(max(nkeys, 1), dtype=torch.int32, device=dev)
+    out8 = torch.empty(max(nkeys, 1) + 32, dtype=torch.uint8, device=dev)
     counts_host = torch.empty(max(nkeys, 1), dtype=torch.uint8, pin_memory=True)
+    # sharded index: the sample goes in rounds of at most --round-mb, cut at read boundaries
+    rec = READ_LEN + 1
+    per_round = max(1, ((a.round_mb << 20) - (1 << 20)) // rec) * rec
+    round_cuts = [(o, min(per_round, nbytes - o)) for o in range(0, nbytes, per_round)] if sharded else []
 
-    def device_step(kev=None):
+    def device_step(kev=None, want=False):
         ix.begin()
         if kev:
             kev[0].record(stream)
+        if sharded:
+            for o, ln in round_cuts:
+                ix.submit_device(lines_dev.data_ptr() + o, ln)
+                ix.flush()
+            if kev:
+                kev[1].record(stream)
+            return ix.end(want_counts=want)[0]  # collective: counts of all keys on every rank (device; host if asked)
         ix.submit_device(lines_dev.data_ptr(), nbytes)
         ix.flush()
         if kev:
             kev[1].record(stream)
+        if comm is not None:  # every rank sums its peers' u8 vectors over NVLink
+            comm.allreduce_counts(ix, want_host=False, dev_out=out8.data_ptr())
+            return out8[:max(nkeys, 1)]
         ix.extract_device(out32.data_ptr(), 4)
-        return vdist.reduce_counts(out32)  # N > 1: the one NCCL all-reduce of the path; clamp to 255
+        return vdist.reduce_counts(out32)  # N > 1 with --reduce nccl: all-reduce of u32, clamp to 255
 
     def barrier():
         if world > 1:
@@ -414,6 +462,8 @@ def main() -> None:
     barrier()
     t_mark1 = clocks.mark()
     launches_timed = ix.launches - launches0 + steps  # + the extract kernel of each step
+    if comm is not None:
+        launches_timed += comm.launches * steps // (steps + warmup)
     total_ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([k0.elapsed_time(k1) for k0, k1 in kevs]))
     tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -425,13 +475,23 @@ def main() -> None:
     total_positions = float(tp.item())
     value = total_positions / (ms_per_step * 1e-3)
     clk = clocks.stop(t_mark0, t_mark1)
-    device_counts = device_step().cpu().numpy()
+    dc = device_step(want=True)
+    device_counts = dc if isinstance(dc, np.ndarray) else dc.cpu().numpy()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------
     def e2e_step():
         ix.begin()
+        if sharded:
+            for o, ln in round_cuts:
+                ix.submit_ptr(lines_host.data_ptr() + o, ln)
+                ix.flush()
+            capi._chk(capi.lib.vg_count_end(ix._h, counts_host.data_ptr(), None, None))
+            return
         ix.submit_ptr(lines_host.data_ptr(), nbytes)
-        if world > 1:
+        if comm is not None:
+            capi._chk(capi.lib.vg_count_allreduce(comm._h, ix._h, counts_host.data_ptr(), None))
+            capi._chk(capi.lib.vg_count_end(ix._h, None, None, None))
+        elif world > 1:
             ix.extract_device(out32.data_ptr(), 4, stream.cuda_stream)  # syncs the context streams first
             counts_host.copy_(vdist.reduce_counts(out32), non_blocking=True)
             torch.cuda.synchronize()
@@ -496,14 +556,21 @@ def main() -> None:
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "index_kmers": nkeys, "index_table_bytes": ix.table_bytes, "table_partitions": ix.partitions,
                            "reads_per_gpu": nbytes // (READ_LEN + 1), "positions_per_gpu": positions,
-                           "parallelism": f"reads sharded x{world}, index replicated" if world > 1 else "1 GPU",
+                           "parallelism": (f"reads sharded x{world}, index "
+                                           + (f"sharded x{world} (k-mer all-to-all fused into the scatter over NVLink, "
+                                              f"{len(round_cuts)} rounds)" if sharded else f"replicated, counts reduced by {reduce_how}")
+                                           if world > 1 else "1 GPU"),
                            "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
                         "d2h_bytes_per_step": int(nkeys + 16), "counts_equal_device_path": e2e_counts_ok},
                 "gpu_launches": int(launches_timed) + steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "parity": parity}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()  # nobody unmaps a peer's arena while it is still in use
     ix.close()
+    if comm is not None:
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

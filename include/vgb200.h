@@ -32,6 +32,7 @@ extern "C" {
 typedef struct vg_ctx vg_ctx;     /* one CUDA device: streams, staging rings */
 typedef struct vg_index vg_index; /* device-resident graph k-mer index + read-coverage counters */
 typedef struct vg_cbf vg_cbf;     /* device-resident counting Bloom filter */
+typedef struct vg_comm vg_comm;   /* one rank of a group of GPUs that map each other's memory (NVLink) */
 
 const char* vg_last_error(void);
 int vg_version(void);
@@ -126,6 +127,51 @@ int vg_cbf_add_sequence(vg_cbf* cbf, const char* host_seq, uint64_t len, uint32_
 int vg_cbf_download(vg_cbf* cbf, uint8_t* host_filter);
 /* BloomFilter::count / find for a batch (src/counting_bloom_filter.cpp:40-67); either out may be NULL. */
 int vg_cbf_query(vg_cbf* cbf, const uint64_t* host_keys, uint64_t n, uint8_t* count_out, uint8_t* find_out);
+
+/* ---- several GPUs (one process per GPU) ---------------------------------------------------
+ * The reference counts on one device (main.cu:221, src/fastq_kmer.cu); BASELINE.json's north star
+ * shards the reads over the GPUs of a box.  Peers reach each other's memory directly over NVLink
+ * (CUDA IPC mappings): no host and no NCCL in the data path.  The caller only carries the 64-byte
+ * handles between the processes (MPI, torch.distributed, a file ...):
+ *     vg_comm_create -> vg_comm_handle -> [all-gather the handles] -> vg_comm_connect.
+ * arena_bytes: device memory this rank exposes to its peers (count vectors; for a sharded index also
+ * its part of the table and the key lists it receives).  Calls marked COLLECTIVE must be made by every
+ * rank, in the same order; a rank whose peer does not arrive within VG_BARRIER_TIMEOUT_MS (20 s)
+ * gives up and the next host-visible result call returns VG_E_STATE. */
+#define VG_COMM_HANDLE_BYTES 64
+int vg_comm_create(vg_ctx* ctx, int rank, int world, uint64_t arena_bytes, vg_comm** out);
+int vg_comm_handle(const vg_comm* comm, void* handle_out /* VG_COMM_HANDLE_BYTES */);
+int vg_comm_connect(vg_comm* comm, const void* handles /* world x VG_COMM_HANDLE_BYTES, rank order */);
+int vg_comm_destroy(vg_comm* comm);
+int vg_comm_rank(const vg_comm* comm);
+int vg_comm_world(const vg_comm* comm);
+uint64_t vg_comm_launches(const vg_comm* comm);  /* barrier / combine kernels launched so far */
+int vg_comm_barrier(vg_comm* comm); /* COLLECTIVE; device-side, enqueued on the context stream */
+int vg_comm_check(vg_comm* comm);   /* waits for the context stream; VG_E_STATE if a barrier timed out */
+
+/* Replicated index, reads sharded over the ranks (the default layout): COLLECTIVE end of a sample.
+ * c = min(255, sum over ranks of the per-rank counts) -- exact, counts being saturating sums -- with
+ * every rank reading its peers' u8 count vectors over NVLink.  Implies vg_count_flush.  The n counts
+ * land in dev_out (device, may be NULL) and / or c_out (host, may be NULL); with c_out the call
+ * returns when they are there, otherwise it is asynchronous on the context stream. */
+int vg_count_allreduce(vg_comm* comm, vg_index* ix, uint8_t* c_out, void* dev_out);
+
+/* Sharded index (the index does not fit one GPU): ONE open-addressing table cut into `world` runs of
+ * buckets, one per rank.  COLLECTIVE; every rank passes the same keys in the same order and keeps those
+ * whose home bucket it owns.  Each rank then submits ITS reads with vg_count_submit / _submit_device /
+ * _files as usual: the scatter kernel stores every k-mer straight into the key list of the GPU that owns
+ * its table slice (the all-to-all of k-mers is the kernel's own copy-out), and each GPU probes its
+ * slices.  Differences from a plain index:
+ *   - a round holds at most round_bytes of submitted bases per rank (0 = 256 MB); vg_count_room() says
+ *     how much still fits, a submit beyond it fails with VG_E_STATE;
+ *   - vg_count_begin, vg_count_flush (end of a round) and vg_count_end (last round + result) are COLLECTIVE;
+ *   - vg_count_end gives every rank the counts of all n keys (c_out), its own positions, and the hits
+ *     found in its part of the table; sums over ranks equal the single-GPU figures;
+ *   - vg_count_extract_device / vg_count_histogram are not available. */
+int vg_index_create_sharded(vg_comm* comm, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
+                            uint64_t round_bytes, vg_index** out);
+uint64_t vg_index_own_keys(const vg_index* ix);  /* keys in this rank's part of the table */
+uint64_t vg_count_room(const vg_index* ix);      /* bytes of bases the current round still takes; ~0 if unlimited */
 
 /* Diagnostic: measured throughput of uniform random 32-byte sector gathers over a table of
  * table_bytes (>> L2) with the same load shape as the index probe: the denominator of the

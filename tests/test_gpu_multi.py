@@ -1,0 +1,96 @@
+"""GPU suite, multi-GPU part: vg_comm (peer memory over CUDA IPC), the count all-reduce of the replicated
+layout and the sharded index with its fused k-mer all-to-all -- against the oracle, bit-exact.
+World size 2 runs as two processes; on a 1-GPU box both ranks share the device."""
+import socket
+
+import numpy as np
+import pytest
+
+from tests import helpers, multi_worker
+from varigraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+NOKMER = helpers.NOKMER
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _workload(oracle, k=27, seed=3, genome=150_000, index_from=60_000, nreads=5000):
+    g = synth.make_genome(genome, seed=seed)
+    lines = synth.random_reads_lines(nreads, 150, g, seed=seed + 1)
+    pos = oracle.positions(g[:index_from], k)
+    keys = np.unique(pos[pos != NOKMER])
+    return keys, lines, g
+
+
+def _read_of(g, at):
+    return np.concatenate([g[at: at + 150], np.frombuffer(b"\n", dtype=np.uint8)])
+
+
+# ---- a group of one: the sharded code path without any peer -------------------------------------
+@pytest.mark.parametrize("k", [27, 16])
+def test_sharded_group_of_one_matches_oracle(ctx, vglib, oracle, monkeypatch, k):
+    monkeypatch.setenv("VG_SLICE_BYTES", "16384")
+    monkeypatch.setenv("VG_PART_SLACK", "64")
+    keys, lines, _ = _workload(oracle, k=k, seed=k)
+    comm = vglib.Comm(ctx, 0, 1, 64 << 20)
+    ix = vglib.Index(ctx, keys, k, comm=comm, round_bytes=128 * 1024)
+    assert ix.own_keys == keys.size and ix.partitions >= 3
+    for _ in range(2):
+        ix.begin()
+        rounds = multi_worker.submit_in_rounds(ix, lines, None)
+        counts, positions, hits = ix.end()
+    assert rounds >= 5
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    assert (positions, hits) == (wpos, whits)
+    assert np.array_equal(counts, want)
+    with pytest.raises(vglib.VgError) as ei:   # a round takes round_bytes and no more
+        ix.begin()
+        ix.submit(lines)
+    assert ei.value.code == vglib.VG_E_STATE
+    ix.close()
+    comm.close()
+
+
+def _run_two_ranks(tmp_path, scenario, keys, lines, k, env=None, round_bytes=0, arena=96 << 20):
+    import torch.multiprocessing as mp
+    path = str(tmp_path / scenario)
+    np.savez(path + ".in.npz", keys=keys, lines=lines, k=k, arena=arena, round_bytes=round_bytes)
+    mp.spawn(multi_worker.worker, args=(2, _free_port(), scenario, path, env or {}), nprocs=2, join=True)
+    return [np.load(f"{path}.out{r}.npz") for r in range(2)]
+
+
+def test_two_ranks_replicated_allreduce_over_peer_memory(tmp_path, oracle):
+    """Reads sharded over two ranks, index replicated, counts summed by reading the peer's vector."""
+    keys, lines, g = _workload(oracle)
+    hot = np.tile(_read_of(g, 1000), 300)  # one read 300 times: saturates only once both ranks are combined
+    lines = np.concatenate([hot[: 150 * 151], lines, hot[150 * 151:]])
+    r0, r1 = _run_two_ranks(tmp_path, "replicated", keys, lines, 27)
+    want, wpos, whits = oracle.count_lines(keys, lines, 27)
+    assert np.array_equal(r0["counts"], want) and np.array_equal(r1["counts"], want)
+    assert int(r0["pos"]) + int(r1["pos"]) == wpos and int(r0["hits"]) + int(r1["hits"]) == whits
+    assert want.max() == 255
+
+
+@pytest.mark.parametrize("skewed", [False, True])
+def test_two_ranks_sharded_index_matches_oracle(tmp_path, oracle, skewed):
+    """The index cut over two ranks; every rank scatters its reads' k-mers into the owner's key lists."""
+    keys, lines, g = _workload(oracle, seed=11)
+    env = {"VG_SLICE_BYTES": "16384", "VG_PART_SLACK": "64"}
+    if skewed:  # identical reads overflow the owner's key list: those keys are probed in the peer's table
+        env["VG_PART_SLACK"] = "0"
+        lines = np.concatenate([np.tile(_read_of(g, 2000), 700), lines[: 151 * 800], np.tile(_read_of(g, 7000), 254)])
+    r0, r1 = _run_two_ranks(tmp_path, "sharded", keys, lines, 27, env=env, round_bytes=96 * 1024)
+    want, wpos, whits = oracle.count_lines(keys, lines, 27)
+    assert np.array_equal(r0["counts"], want) and np.array_equal(r1["counts"], want)
+    assert int(r0["pos"]) + int(r1["pos"]) == wpos and int(r0["hits"]) + int(r1["hits"]) == whits
+    assert int(r0["own"]) + int(r1["own"]) == keys.size and min(int(r0["own"]), int(r1["own"])) > keys.size // 3
+    assert int(r0["rounds"]) == int(r1["rounds"]) >= 2
+    if skewed:
+        assert want.max() == 255

@@ -63,6 +63,19 @@ def _load() -> ctypes.CDLL:
         "vg_cbf_add_sequence": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, P(c_uint64)]),
         "vg_cbf_download": (c_int, [c_void_p, c_void_p]),
         "vg_cbf_query": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
+        "vg_comm_create": (c_int, [c_void_p, c_int, c_int, c_uint64, P(c_void_p)]),
+        "vg_comm_handle": (c_int, [c_void_p, c_void_p]),
+        "vg_comm_connect": (c_int, [c_void_p, c_void_p]),
+        "vg_comm_destroy": (c_int, [c_void_p]),
+        "vg_comm_rank": (c_int, [c_void_p]),
+        "vg_comm_world": (c_int, [c_void_p]),
+        "vg_comm_launches": (c_uint64, [c_void_p]),
+        "vg_comm_barrier": (c_int, [c_void_p]),
+        "vg_comm_check": (c_int, [c_void_p]),
+        "vg_count_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+        "vg_index_create_sharded": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, c_uint64, P(c_void_p)]),
+        "vg_index_own_keys": (c_uint64, [c_void_p]),
+        "vg_count_room": (c_uint64, [c_void_p]),
         "vg_host_alloc": (c_int, [P(c_void_p), c_uint64]),
         "vg_host_free": (c_int, [c_void_p]),
     }
@@ -135,17 +148,80 @@ class Context:
             pass
 
 
-class Index:
-    """Device twin of mGraphKmerHashHapStrMap plus the read-coverage counters (vg_index)."""
+HANDLE_BYTES = 64
 
-    def __init__(self, ctx: Context, keys: np.ndarray, k: int, load_factor: float = 0.0):
-        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+
+class Comm:
+    """One rank of a group of GPUs that map each other's memory over NVLink (vg_comm).
+    `exchange(my_handle: bytes) -> [bytes] * world` carries the handles between the processes
+    (torch.distributed.all_gather_object in the tests and bench.py)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, arena_bytes: int, exchange=None):
         h = c_void_p()
-        _chk(lib.vg_index_create(ctx._h, _ptr(keys), keys.size, k, load_factor, byref(h)))
+        _chk(lib.vg_comm_create(ctx._h, rank, world, arena_bytes, byref(h)))
         self._h = h
         self.ctx = ctx
+        self.rank, self.world = rank, world
+        if world > 1:
+            mine = ctypes.create_string_buffer(HANDLE_BYTES)
+            _chk(lib.vg_comm_handle(self._h, mine))
+            everyone = exchange(mine.raw)
+            assert len(everyone) == world and all(len(x) == HANDLE_BYTES for x in everyone)
+            _chk(lib.vg_comm_connect(self._h, ctypes.create_string_buffer(b"".join(everyone), world * HANDLE_BYTES)))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.vg_comm_launches(self._h))
+
+    def barrier(self) -> None:
+        _chk(lib.vg_comm_barrier(self._h))
+
+    def check(self) -> None:
+        _chk(lib.vg_comm_check(self._h))
+
+    def allreduce_counts(self, index: "Index", want_host: bool = True, dev_out: int = 0):
+        """COLLECTIVE: min(255, sum over ranks) of a replicated index's counts -> u8[n] (host) or None."""
+        out = np.empty(index.n, dtype=np.uint8) if want_host else None
+        _chk(lib.vg_count_allreduce(self._h, index._h, _ptr(out) if want_host else None, c_void_p(dev_out)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            lib.vg_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    """Device twin of mGraphKmerHashHapStrMap plus the read-coverage counters (vg_index).
+    With `comm` the index is sharded over the group's GPUs (vg_index_create_sharded): flush() and
+    end() are then collective and a round takes at most `round_bytes` of bases (see room())."""
+
+    def __init__(self, ctx: Context, keys: np.ndarray, k: int, load_factor: float = 0.0, comm: "Comm" = None,
+                 round_bytes: int = 0):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        h = c_void_p()
+        if comm is None:
+            _chk(lib.vg_index_create(ctx._h, _ptr(keys), keys.size, k, load_factor, byref(h)))
+        else:
+            _chk(lib.vg_index_create_sharded(comm._h, _ptr(keys), keys.size, k, load_factor, round_bytes, byref(h)))
+        self._h = h
+        self.ctx = ctx
+        self.comm = comm
         self.n = int(keys.size)
         self.k = k
+
+    @property
+    def own_keys(self) -> int:
+        return int(lib.vg_index_own_keys(self._h))
+
+    def room(self) -> int:
+        return int(lib.vg_count_room(self._h))
 
     @property
     def table_bytes(self) -> int:

@@ -33,25 +33,8 @@ int fail(int code, const char* fmt, ...) {
 
 using vg::fail;
 
-#define CU(expr)                                                                              \
-    do {                                                                                      \
-        cudaError_t e__ = (expr);                                                             \
-        if (e__ != cudaSuccess)                                                               \
-            return fail(e__ == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "%s: %s", #expr, \
-                        cudaGetErrorString(e__));                                             \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+#define CU VG_CU
+using vg::DeviceGuard;
 
 // ---- partitioned probing: set-up, scatter, flush ---------------------------------------------
 // Used for every table of 8 MB or more whose slice count stays within what one CTA tile can scatter
@@ -59,6 +42,24 @@ struct DeviceGuard {
 // k-mer, and even an L2-resident table is probed faster through the sweep than with per-hit CAS.
 // VG_PARTITION=0 forces direct probing, =1 forces partitioning; VG_SLICE_BYTES / VG_ROUND_KEYS /
 // VG_PART_SLACK tune it (the tests use them to drive tiny tables through every branch).
+void vg::pin_in_l2(vg_ctx* c, void* ptr, size_t bytes) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = ptr;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(c->compute_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+        c->l2_window = av.accessPolicyWindow;
+        c->has_l2_window = true;
+    }
+}
+
 static int part_setup(vg_index* ix) {
     vg_ctx* c = ix->ctx;
     const char* env = getenv("VG_PARTITION");
@@ -95,6 +96,9 @@ static int part_setup(vg_index* ix) {
     ps.view.P = (uint32_t)P;
     ps.view.shift = shift;
     ps.view.cap = (round_keys / P) * 5 / 4 + slack;
+    ps.view.world = 1;
+    ps.view.rank = 0;
+    ps.view.P_local = (uint32_t)P;
     ps.round_keys = round_keys;
     cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long));
@@ -126,22 +130,7 @@ static int part_setup(vg_index* ix) {
                 CU(cudaStreamSynchronize(c->compute_stream));
                 ps.filter.words = ps.d_filter;
                 ps.filter.nwords = nwords;
-                // pin it in L2 for the kernels of this context's stream
-                cudaDeviceProp prop;
-                if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-                    const size_t want = std::min<size_t>((size_t)nwords * 4, (size_t)prop.persistingL2CacheMaxSize);
-                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-                    cudaStreamAttrValue av{};
-                    av.accessPolicyWindow.base_ptr = ps.d_filter;
-                    av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)nwords * 4, (size_t)prop.accessPolicyMaxWindowSize);
-                    av.accessPolicyWindow.hitRatio = 1.0f;
-                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                    cudaStreamSetAttribute(c->compute_stream, cudaStreamAttributeAccessPolicyWindow, &av);
-                    cudaGetLastError();
-                    c->l2_window = av.accessPolicyWindow;
-                    c->has_l2_window = true;
-                }
+                vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
             } else {
                 cudaGetLastError();
             }
@@ -152,6 +141,7 @@ static int part_setup(vg_index* ix) {
 
 static int part_flush(vg_index* ix, cudaStream_t s) {
     PartState& ps = ix->part;
+    if (ix->sharded) return VG_OK;  // a sharded round ends only in the collective calls (vg_count_flush / _end)
     if (!ps.enabled || ps.pending == 0) return VG_OK;
     CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
     ix->launches += ps.view.P + 1;
@@ -173,6 +163,9 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
     int64_t t = 0;
     while (t < T) {
         int64_t room = (int64_t)((ps.round_keys - ps.pending) / tile_bytes);
+        if (ix->sharded && room < T - t)
+            return fail(VG_E_STATE, "sharded index: the round is full (%llu of %llu bytes); call vg_count_flush on every rank",
+                        (unsigned long long)ps.pending, (unsigned long long)ps.round_keys);
         if (room < 64 && ps.pending) {
             int rc = part_flush(ix, s);
             if (rc) return rc;
@@ -205,7 +198,7 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
         const uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
         return v >= 4096 ? v : (384ull << 20);  // measured flat between 256 M and 1 G, worse below
     }();
-    if (ix->part.enabled && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, staged_round)) {
+    if (ix->part.enabled && !ix->sharded && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, staged_round)) {
         rc = part_flush(ix, c->compute_stream);
         if (rc) return rc;
     }
@@ -365,6 +358,8 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     ix->view.k = k;
     ix->view.mask = (1ULL << (2 * k)) - 1;
     ix->view.nbuckets = (uint32_t)nb64;
+    ix->view.nb_total = (uint32_t)nb64;
+    ix->view.b_base = 0;
     auto bail = [&](int code) {
         vg_index_destroy(ix);
         return code;
@@ -421,13 +416,17 @@ int vg_index_destroy(vg_index* ix) {
     if (!ix) return VG_OK;
     DeviceGuard g(ix->ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ix->view.slots);
+    if (!ix->sharded) {  // a sharded index keeps these in its group's arena
+        cudaFree(ix->view.slots);
+        cudaFree(ix->d_counts);
+        cudaFree(ix->part.view.keybuf);
+    }
     cudaFree(ix->d_key56);
-    cudaFree(ix->d_counts);
+    cudaFree(ix->d_idx);
+    cudaFree(ix->d_combined);
     cudaFree(ix->d_flags);
     cudaFree(ix->d_hist);
     cudaFree(ix->d_misc);
-    cudaFree(ix->part.view.keybuf);
     cudaFree(ix->part.view.cursor);
     cudaFree(ix->part.view.ctr);
     cudaFree(ix->part.d_filter);
@@ -452,6 +451,10 @@ int vg_count_begin(vg_index* ix) {
     if (ix->part.enabled) {
         CU(cudaMemsetAsync(ix->part.view.cursor, 0, ix->part.view.P * sizeof(unsigned long long), c->compute_stream));
         ix->part.pending = 0;
+    }
+    if (ix->sharded) {  // no peer may probe this table (a key whose list is full) before it is cleared
+        int rc = vg_comm_barrier(ix->comm);
+        if (rc) return rc;
     }
     ix->counting = true;
     return VG_OK;
@@ -518,7 +521,18 @@ int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
 int vg_count_flush(vg_index* ix) {
     if (!ix) return fail(VG_E_INVALID, "index is NULL");
     DeviceGuard g(ix->ctx->device);
+    if (ix->sharded) {
+        CU(cudaStreamSynchronize(ix->ctx->copy_stream));
+        return vg::sharded_flush(ix, ix->ctx->compute_stream);
+    }
     return part_flush(ix, ix->ctx->compute_stream);
+}
+
+uint64_t vg_count_room(const vg_index* ix) {
+    if (!ix || !ix->sharded) return ~0ull;
+    // every staged piece of a submit may end in a partly filled 4 KiB tile, which counts as a whole one
+    const uint64_t used = ix->part.pending + 4096 * (ix->part.round_keys / ix->ctx->chunk_bytes + 2);
+    return used >= ix->part.round_keys ? 0 : ix->part.round_keys - used;
 }
 
 int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits) {
@@ -553,7 +567,8 @@ int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* c
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->compute_stream));
     }
-    CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, dev_out, elem_bytes, s));
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: the counts of all keys come from vg_count_end");
+    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, dev_out, elem_bytes, s));
     return VG_OK;
 }
 
@@ -580,8 +595,9 @@ int vg_count_histogram(vg_index* ix, uint64_t* hist256) {
     CU(cudaStreamSynchronize(c->copy_stream));
     int rc = part_flush(ix, c->compute_stream);
     if (rc) return rc;
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: take the histogram of vg_count_end's counts");
     if (!ix->d_hist) CU(cudaMalloc((void**)&ix->d_hist, 256 * sizeof(unsigned long long)));
-    CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, ix->d_counts, 1, c->compute_stream));
+    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
     CU(vg::launch_histogram(ix->d_counts, ix->d_flags, ix->n, ix->d_hist, c->compute_stream));
     unsigned long long h[256];
     CU(cudaMemcpyAsync(h, ix->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->compute_stream));
@@ -595,11 +611,17 @@ int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hi
     if (!ix->counting) return fail(VG_E_STATE, "vg_count_end before vg_count_begin");
     vg_ctx* c = ix->ctx;
     DeviceGuard g(c->device);
+    if (ix->sharded) {  // collective: last round, then every rank gets the counts of all keys
+        CU(cudaStreamSynchronize(c->copy_stream));
+        int frc = vg::sharded_flush(ix, c->compute_stream);
+        if (frc == VG_OK) frc = vg::sharded_end(ix, c_out);
+        if (frc) return frc;
+    }
     int rc = vg_count_stats(ix, positions, hits);
     if (rc) return rc;
     for (auto& sl : c->ring) sl.busy = false;
-    if (c_out && ix->n) {
-        CU(vg::launch_extract(ix->view, ix->d_key56, ix->n, ix->d_counts, 1, c->compute_stream));
+    if (c_out && ix->n && !ix->sharded) {
+        CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
         CU(cudaMemcpyAsync(c_out, ix->d_counts, ix->n, cudaMemcpyDeviceToHost, c->compute_stream));
         CU(cudaStreamSynchronize(c->compute_stream));
     }

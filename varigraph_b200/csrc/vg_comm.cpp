@@ -1,0 +1,445 @@
+// vg_comm.cpp -- the multi-GPU half of include/vgb200.h: one process per GPU, peers reach each other's
+// memory directly over NVLink / NVSwitch (CUDA IPC mappings), no NCCL and no host in the data path.
+//
+//   vg_comm                  rank, world, a symmetric arena, a device-side barrier over peer flags
+//   vg_count_allreduce       replicated index, reads sharded: min(255, sum of the ranks' u8 counts),
+//                            each rank reading its peers' count vectors (1 byte per key on the wire)
+//   vg_index_create_sharded  the index is ONE open-addressing table cut into `world` runs of buckets,
+//                            one per GPU (index > HBM variant); the scatter kernel's copy-out
+//                            stores every k-mer into the key list of the GPU that owns its table slice,
+//                            so the all-to-all of k-mers is fused into the kernel that produces them.
+//
+// The reference has no multi-GPU path (src/fastq_kmer.cu runs one device, main.cu:221); this is the
+// BASELINE.json north-star's "hash-partitioned shard with an all-to-all of k-mers ... count arrays
+// reduced over NVLink".
+#include "../../include/vgb200.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "vg_host.h"
+#include "vg_internal.h"
+
+using vg::DeviceGuard;
+using vg::fail;
+#define CU VG_CU
+
+static_assert(sizeof(cudaIpcMemHandle_t) == VG_COMM_HANDLE_BYTES, "VG_COMM_HANDLE_BYTES must match cudaIpcMemHandle_t");
+
+namespace {
+
+constexpr size_t kArenaAlign = 256;
+constexpr size_t kFlagsBytes = 256;  // kMaxWorld x u64, at arena offset 0
+
+// Bump allocation out of the symmetric arena: every rank must make the same calls in the same order.
+void* arena_alloc(vg_comm* cm, size_t bytes, size_t* off_out) {
+    const size_t off = (cm->arena_used + kArenaAlign - 1) & ~(kArenaAlign - 1);
+    if (off + bytes > cm->arena_bytes) return nullptr;
+    cm->arena_used = off + bytes;
+    if (off_out) *off_out = off;
+    return cm->arena + off;
+}
+
+vg::PeerPtrs peers_at(const vg_comm* cm, size_t off) {
+    vg::PeerPtrs pp{};
+    for (int r = 0; r < cm->world; ++r) pp.p[r] = cm->peer_base[r] + off;
+    return pp;
+}
+
+int barrier_on(vg_comm* cm, cudaStream_t s) {
+    if (cm->world == 1) return VG_OK;
+    cm->epoch += 1;
+    CU(vg::launch_peer_barrier(peers_at(cm, 0), cm->world, cm->rank, cm->epoch, cm->timeout_ns, cm->d_timeout, s));
+    cm->launches += 1;
+    return VG_OK;
+}
+
+// After a stream synchronize: did any barrier give up on a peer?
+int check_peers(vg_comm* cm) {
+    if (cm->world == 1) return VG_OK;
+    unsigned int t = 0;
+    CU(cudaMemcpy(&t, cm->d_timeout, sizeof t, cudaMemcpyDeviceToHost));
+    if (t) return fail(VG_E_STATE, "rank %d: a peer did not reach a barrier within %.1f s; results are incomplete", cm->rank,
+                       cm->timeout_ns * 1e-9);
+    return VG_OK;
+}
+
+// extract-to-symmetric-buffer done on every rank -> out = min(255, sum over ranks), on stream s.
+int combine_from_peers(vg_comm* cm, size_t counts_off, uint64_t n, uint8_t* d_out, cudaStream_t s) {
+    int rc = barrier_on(cm, s);  // every rank's vector is complete
+    if (rc) return rc;
+    CU(vg::launch_combine_counts(peers_at(cm, counts_off), cm->world, n, d_out, cm->ctx->nsm, s));
+    cm->launches += 1;
+    return barrier_on(cm, s);    // nobody overwrites its vector while a peer still reads it
+}
+
+}  // namespace
+
+extern "C" {
+
+int vg_comm_create(vg_ctx* c, int rank, int world, uint64_t arena_bytes, vg_comm** out) {
+    if (!c || !out) return fail(VG_E_INVALID, "vg_comm_create: NULL argument");
+    *out = nullptr;
+    if (world < 1 || world > vg::kMaxWorld || rank < 0 || rank >= world)
+        return fail(VG_E_INVALID, "rank %d / world %d outside 0 <= rank < world <= %d", rank, world, vg::kMaxWorld);
+    if (arena_bytes < (1u << 20)) arena_bytes = 1u << 20;
+    DeviceGuard g(c->device);
+    vg_comm* cm = new vg_comm();
+    cm->ctx = c;
+    cm->rank = rank;
+    cm->world = world;
+    cm->arena_bytes = (size_t)arena_bytes;
+    if (const char* e = getenv("VG_BARRIER_TIMEOUT_MS")) {
+        const unsigned long long ms = strtoull(e, nullptr, 10);
+        if (ms) cm->timeout_ns = ms * 1000000ull;
+    }
+    cudaError_t e = cudaMalloc((void**)&cm->arena, cm->arena_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&cm->d_timeout, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(cm->arena, 0, kFlagsBytes);
+    if (e == cudaSuccess) e = cudaMemset(cm->d_timeout, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(cm->arena);
+        cudaFree(cm->d_timeout);
+        delete cm;
+        return fail(e == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "vg_comm_create (%llu-byte arena): %s",
+                    (unsigned long long)arena_bytes, cudaGetErrorString(e));
+    }
+    cm->arena_used = kFlagsBytes;
+    cm->peer_base[rank] = cm->arena;
+    cm->connected = world == 1;
+    *out = cm;
+    return VG_OK;
+}
+
+int vg_comm_handle(const vg_comm* cm, void* handle_out) {
+    if (!cm || !handle_out) return fail(VG_E_INVALID, "vg_comm_handle: NULL argument");
+    DeviceGuard g(cm->ctx->device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, cm->arena));
+    memcpy(handle_out, &h, sizeof h);
+    return VG_OK;
+}
+
+int vg_comm_connect(vg_comm* cm, const void* handles) {
+    if (!cm || !handles) return fail(VG_E_INVALID, "vg_comm_connect: NULL argument");
+    if (cm->connected) return cm->world == 1 ? VG_OK : fail(VG_E_STATE, "vg_comm_connect: already connected");
+    DeviceGuard g(cm->ctx->device);
+    for (int r = 0; r < cm->world; ++r) {
+        if (r == cm->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * VG_COMM_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (q != cm->rank && cm->peer_base[q]) {
+                    cudaIpcCloseMemHandle(cm->peer_base[q]);
+                    cm->peer_base[q] = nullptr;
+                }
+            return fail(VG_E_CUDA, "rank %d cannot map rank %d's arena (cudaIpcOpenMemHandle: %s)", cm->rank, r,
+                        cudaGetErrorString(e));
+        }
+        cm->peer_base[r] = (uint8_t*)p;
+    }
+    cm->connected = true;
+    return VG_OK;
+}
+
+int vg_comm_barrier(vg_comm* cm) {
+    if (!cm || !cm->connected) return fail(VG_E_STATE, "vg_comm_barrier: not connected");
+    DeviceGuard g(cm->ctx->device);
+    return barrier_on(cm, cm->ctx->compute_stream);
+}
+
+int vg_comm_rank(const vg_comm* cm) { return cm ? cm->rank : -1; }
+int vg_comm_world(const vg_comm* cm) { return cm ? cm->world : 0; }
+uint64_t vg_comm_launches(const vg_comm* cm) { return cm ? cm->launches : 0; }
+
+int vg_comm_destroy(vg_comm* cm) {
+    if (!cm) return VG_OK;
+    DeviceGuard g(cm->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < cm->world; ++r)
+        if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);
+    cudaFree(cm->arena);
+    cudaFree(cm->d_timeout);
+    cudaFree(cm->d_reduced);
+    cudaGetLastError();
+    delete cm;
+    return VG_OK;
+}
+
+// Replicated index, reads sharded over ranks: every rank extracts its u8 counts into the arena, then
+// sums all ranks' vectors with a clamp at 255 -- exact, counts being saturating sums:
+// min(255, sum_r min(255, c_r)) == min(255, total).  Collective; the result lands in dev_out (n bytes
+// on the device, may be NULL) and / or c_out (host, may be NULL).
+int vg_count_allreduce(vg_comm* cm, vg_index* ix, uint8_t* c_out, void* dev_out) {
+    if (!cm || !ix) return fail(VG_E_INVALID, "vg_count_allreduce: NULL argument");
+    if (!cm->connected) return fail(VG_E_STATE, "vg_count_allreduce: vg_comm_connect first");
+    if (ix->sharded) return fail(VG_E_STATE, "vg_count_allreduce is for replicated indexes; a sharded one combines in vg_count_end");
+    if (ix->ctx != cm->ctx) return fail(VG_E_INVALID, "index and comm live on different contexts");
+    vg_ctx* c = cm->ctx;
+    DeviceGuard g(c->device);
+    const uint64_t n = ix->n;
+    const size_t need = (size_t)((n + 15) & ~15ull) + 16;
+    if (cm->reduce_bytes < need) {
+        if (cm->reduce_bytes) return fail(VG_E_STATE, "vg_count_allreduce: one index size per comm (arena scratch is %zu bytes)", cm->reduce_bytes);
+        if (!arena_alloc(cm, need, &cm->reduce_off)) return fail(VG_E_NOMEM, "arena too small for a %zu-byte count vector", need);
+        cm->reduce_bytes = need;
+        CU(cudaMalloc((void**)&cm->d_reduced, need));
+    }
+    cudaStream_t s = c->compute_stream;
+    int rc = vg_count_flush(ix);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, n, cm->arena + cm->reduce_off, 1, s));
+    ix->launches += 1;
+    uint8_t* out = dev_out ? (uint8_t*)dev_out : cm->d_reduced;
+    rc = combine_from_peers(cm, cm->reduce_off, n, out, s);
+    if (rc) return rc;
+    if (c_out) {
+        CU(cudaMemcpyAsync(c_out, out, n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return check_peers(cm);
+    }
+    return VG_OK;
+}
+
+int vg_comm_check(vg_comm* cm) {
+    if (!cm) return fail(VG_E_INVALID, "comm is NULL");
+    DeviceGuard g(cm->ctx->device);
+    CU(cudaStreamSynchronize(cm->ctx->compute_stream));
+    return check_peers(cm);
+}
+
+// ---------------------------------------------------------------------------
+// sharded index
+// ---------------------------------------------------------------------------
+int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
+                            uint64_t round_bytes, vg_index** out) {
+    if (!cm || !out || (!keys && n)) return fail(VG_E_INVALID, "vg_index_create_sharded: NULL argument");
+    *out = nullptr;
+    if (!cm->connected) return fail(VG_E_STATE, "vg_index_create_sharded: vg_comm_connect first");
+    if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28 (reference asserts k<=28, src/kmer.cpp:124)", k);
+    if (load_factor <= 0) load_factor = 0.3;
+    if (load_factor > 0.9) return fail(VG_E_INVALID, "load_factor %.3f > 0.9", load_factor);
+    vg_ctx* c = cm->ctx;
+    DeviceGuard g(c->device);
+    const uint32_t W = (uint32_t)cm->world;
+
+    // ---- geometry: the same on every rank (depends on n, world and the tuning variables only) ----
+    uint64_t nb_min = (uint64_t)((double)n / W / (4.0 * load_factor)) + 1;
+    if (nb_min < 64) nb_min = 64;
+    uint64_t slice_bytes = 32ull << 20;
+    if (const char* e = getenv("VG_SLICE_BYTES")) slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
+    while (slice_bytes > 64 && nb_min * 32 / slice_bytes < 3) slice_bytes >>= 1;
+    uint32_t shift = 0;
+    while ((32ull << (shift + 1)) <= slice_bytes) ++shift;
+    uint64_t P_local = (nb_min + (1ull << shift) - 1) >> shift;
+    while (P_local * W > vg::kMaxPartitions) {
+        ++shift;
+        P_local = (nb_min + (1ull << shift) - 1) >> shift;
+    }
+    if (P_local < 3) P_local = 3;  // the sweep retires slice p-1 while slice p is probed: needs three
+    const uint64_t nb_local = P_local << shift, nb_total = nb_local * W;
+    if (nb_total >= 0xffffffffull) return fail(VG_E_INVALID, "index of %llu keys needs too many buckets", (unsigned long long)n);
+    if (round_bytes == 0) round_bytes = 256ull << 20;
+    round_bytes = (round_bytes + 4095) & ~4095ull;
+    uint64_t slack = 65536;
+    if (const char* e = getenv("VG_PART_SLACK")) slack = strtoull(e, nullptr, 10);
+    const uint64_t P = P_local * W;
+    const uint64_t cap = (round_bytes / P) * 5 / 4 + slack;
+
+    vg_index* ix = new vg_index();
+    ix->ctx = c;
+    ix->comm = cm;
+    ix->sharded = true;
+    ix->n = n;
+    ix->view.k = k;
+    ix->view.mask = (1ULL << (2 * k)) - 1;
+    ix->view.nbuckets = (uint32_t)nb_local;
+    ix->view.nb_total = (uint32_t)nb_total;
+    ix->view.b_base = (uint32_t)(nb_local * cm->rank);
+    auto bail = [&](int code) {
+        vg_index_destroy(ix);
+        return code;
+    };
+#define CUB(expr)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return bail(fail(e__ == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "%s: %s", #expr,     \
+                             cudaGetErrorString(e__)));                                                      \
+    } while (0)
+    // ---- symmetric objects (same order, same sizes on every rank) ----
+    size_t slots_off = 0, keybuf_off = 0, incount_off = 0;
+    const size_t counts_bytes = (size_t)((n + 15) & ~15ull) + 16;
+    PartState& ps = ix->part;
+    ix->view.slots = (uint64_t*)arena_alloc(cm, nb_local * 32, &slots_off);
+    ix->d_counts = (uint8_t*)arena_alloc(cm, counts_bytes, &ix->counts_off);
+    ps.view.keybuf = (uint64_t*)arena_alloc(cm, P * cap * sizeof(uint64_t), &keybuf_off);
+    ps.view.incount = (unsigned long long*)arena_alloc(cm, P * sizeof(unsigned long long), &incount_off);
+    if (!ix->view.slots || !ix->d_counts || !ps.view.keybuf || !ps.view.incount) {
+        ix->view.slots = nullptr;
+        return bail(fail(VG_E_NOMEM, "arena of %zu bytes too small: table %llu + counts %zu + key lists %llu bytes per rank",
+                         cm->arena_bytes, (unsigned long long)(nb_local * 32), counts_bytes, (unsigned long long)(P * cap * 8)));
+    }
+    ps.view.P = (uint32_t)P;
+    ps.view.shift = shift;
+    ps.view.cap = cap;
+    ps.view.world = W;
+    ps.view.rank = (uint32_t)cm->rank;
+    ps.view.P_local = (uint32_t)P_local;
+    for (uint32_t r = 0; r < W; ++r) {
+        ps.view.peer_keybuf[r] = (uint64_t*)(cm->peer_base[r] + keybuf_off);
+        ps.view.peer_slots[r] = (uint64_t*)(cm->peer_base[r] + slots_off);
+        ps.view.peer_incount[r] = (unsigned long long*)(cm->peer_base[r] + incount_off);
+    }
+    ps.round_keys = round_bytes;
+    cudaStream_t s = c->compute_stream;
+    CUB(cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long)));
+    CUB(cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift) * sizeof(uint32_t)));
+    CUB(cudaMalloc((void**)&ix->d_combined, counts_bytes));
+    CUB(cudaMalloc((void**)&ix->d_misc, sizeof(vg::DeviceMisc)));
+    CUB(cudaMemsetAsync(ix->d_misc, 0, sizeof(vg::DeviceMisc), s));
+    CUB(cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), s));
+    CUB(cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), s));
+    CUB(cudaMemsetAsync(ps.view.incount, 0, P * sizeof(unsigned long long), s));
+    CUB(vg::launch_table_fill_empty(ix->view.slots, 4ull * nb_local, s));
+
+    // ---- presence pre-filter over ALL keys (every rank filters its own reads before the exchange) ----
+    const char* pe = getenv("VG_PREFILTER");
+    uint32_t nwords = 0;
+    if (!(pe && atoi(pe) == 0) && n > 0) {
+        uint64_t bytes = n / 2 <= (64ull << 20) ? n / 2 : 0;
+        if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
+        if (bytes >= 64) {
+            nwords = (uint32_t)std::min<uint64_t>(bytes / 4, 0x7fffffffull);
+            CUB(cudaMalloc((void**)&ps.d_filter, (size_t)nwords * 4));
+            CUB(cudaMemsetAsync(ps.d_filter, 0, (size_t)nwords * 4, s));
+        }
+    }
+
+    // ---- keys: pass 0 counts this rank's own keys, pass 1 keeps them (with their caller positions) ----
+    const uint64_t piece = 1ull << 22;
+    std::vector<uint64_t> tmp((size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
+    uint64_t* d_piece = nullptr;
+    unsigned long long* d_n_own = nullptr;
+    CUB(cudaMalloc((void**)&d_piece, tmp.size() * sizeof(uint64_t)));
+    auto bail2 = [&](int code) {
+        cudaFree(d_piece);
+        cudaFree(d_n_own);
+        return bail(code);
+    };
+#define CUB2(expr)                                                                                           \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return bail2(fail(e__ == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "%s: %s", #expr,    \
+                              cudaGetErrorString(e__)));                                                     \
+    } while (0)
+    CUB2(cudaMalloc((void**)&d_n_own, sizeof(unsigned long long)));
+    for (int pass = 0; pass < 2; ++pass) {
+        CUB2(cudaMemsetAsync(d_n_own, 0, sizeof(unsigned long long), s));
+        for (uint64_t off = 0; off < n; off += piece) {
+            const uint64_t m = std::min<uint64_t>(piece, n - off);
+            for (uint64_t i = 0; i < m; ++i) {
+                const uint64_t key = keys[off + i];
+                if (pass == 0) {
+                    if ((key & 0xffu) != k)
+                        return bail2(fail(VG_E_INVALID, "keys[%llu]=0x%llx: low byte is not k=%u (src/kmer.cpp:138)",
+                                          (unsigned long long)(off + i), (unsigned long long)key, k));
+                    if ((key >> 8) > ix->view.mask)
+                        return bail2(fail(VG_E_INVALID, "keys[%llu]: hash exceeds 2k bits", (unsigned long long)(off + i)));
+                }
+                tmp[(size_t)i] = key >> 8;
+            }
+            CUB2(cudaMemcpyAsync(d_piece, tmp.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            CUB2(vg::launch_unhash(d_piece, m, ix->view.mask, s));
+            CUB2(vg::launch_select_owned(ix->view, d_piece, m, off, pass ? ix->d_key56 : nullptr, pass ? ix->d_idx : nullptr,
+                                         d_n_own, s));
+            if (pass == 1 && nwords) CUB2(vg::launch_prefilter_build(ps.d_filter, nwords, d_piece, m, s));
+            CUB2(cudaStreamSynchronize(s));  // tmp is reused
+        }
+        if (pass == 0) {
+            unsigned long long no = 0;
+            CUB2(cudaMemcpy(&no, d_n_own, sizeof no, cudaMemcpyDeviceToHost));
+            ix->n_own = no;
+            CUB2(cudaMalloc((void**)&ix->d_key56, std::max<uint64_t>(no, 1) * sizeof(uint64_t)));
+            CUB2(cudaMalloc((void**)&ix->d_idx, std::max<uint64_t>(no, 1) * sizeof(uint64_t)));
+        }
+    }
+    cudaFree(d_piece);
+    cudaFree(d_n_own);
+    d_piece = nullptr;
+    d_n_own = nullptr;
+    if (ix->n_own > 3.6 * nb_local)
+        return bail(fail(VG_E_NOMEM, "rank %d owns %llu keys for %llu slots", cm->rank, (unsigned long long)ix->n_own,
+                         (unsigned long long)(4 * nb_local)));
+    CUB(vg::launch_insert(ix->view, ix->d_key56, ix->n_own, &ix->d_misc->report, s));
+    vg::DeviceMisc misc;
+    CUB(cudaMemcpyAsync(&misc, ix->d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));
+    CUB(cudaStreamSynchronize(s));
+    if (misc.report.failed) return bail(fail(VG_E_NOMEM, "index build: %llu keys found no slot", misc.report.failed));
+    ix->duplicates = misc.report.duplicates;
+    if (nwords) {
+        ps.filter.words = ps.d_filter;
+        ps.filter.nwords = nwords;
+        vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
+    }
+    ps.enabled = true;
+#undef CUB
+#undef CUB2
+    // nobody scatters into (or probes) a peer's table before that peer has built it
+    int rc = barrier_on(cm, s);
+    if (rc) return bail(rc);
+    *out = ix;
+    return VG_OK;
+}
+
+uint64_t vg_index_own_keys(const vg_index* ix) { return ix ? (ix->sharded ? ix->n_own : ix->n) : 0; }
+
+}  // extern "C"
+
+// End of a round on a sharded index (collective): tell the owners how many keys they received, wait
+// for every rank's scatter, sweep this GPU's slices, wait again so that the next round's scatter
+// cannot overwrite lists a peer is still probing.
+int vg::sharded_flush(vg_index* ix, cudaStream_t s) {
+    vg_comm* cm = ix->comm;
+    PartState& ps = ix->part;
+    if (cm->world > 1) {
+        CU(vg::launch_publish_counts(ps.view, s));
+        int rc = barrier_on(cm, s);
+        if (rc) return rc;
+        CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+        ix->launches += (uint64_t)ps.view.P_local * cm->world + 2;
+        rc = barrier_on(cm, s);
+        if (rc) return rc;
+    } else {  // a group of one: the key lists and cursors are local
+        CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+        ix->launches += ps.view.P_local + 1;
+    }
+    ps.pending = 0;
+    return VG_OK;
+}
+
+// After the last round: counts of this GPU's own keys at their caller positions (zero elsewhere), then
+// the sum over ranks -- every key is owned by exactly one rank -- gives every rank all n counts.
+int vg::sharded_end(vg_index* ix, uint8_t* c_out) {
+    vg_comm* cm = ix->comm;
+    vg_ctx* c = ix->ctx;
+    cudaStream_t s = c->compute_stream;
+    const uint64_t n = ix->n;
+    CU(cudaMemsetAsync(ix->d_counts, 0, (size_t)((n + 15) & ~15ull), s));
+    CU(vg::launch_extract(ix->view, ix->d_key56, ix->d_idx, ix->n_own, ix->d_counts, 1, s));
+    ix->launches += 1;
+    int rc = combine_from_peers(cm, ix->counts_off, n, ix->d_combined, s);
+    if (rc) return rc;
+    if (c_out && n) CU(cudaMemcpyAsync(c_out, ix->d_combined, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return check_peers(cm);
+}

@@ -7,7 +7,27 @@
 
 #include "vg_internal.h"
 
+#define VG_CU(expr)                                                                                \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return vg::fail(e__ == cudaErrorMemoryAllocation ? -3 /* VG_E_NOMEM */ : -2 /* VG_E_CUDA */, "%s: %s", #expr, \
+                            cudaGetErrorString(e__));                                              \
+    } while (0)
+
 namespace vg {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // One pinned-host / device buffer pair of the staging ring.
 struct StageSlot {
@@ -29,6 +49,9 @@ constexpr uint64_t kTilePieceBytes = 64ull << 20;  // multiple of the 4 KiB CTA 
 int fail(int code, const char* fmt, ...);
 
 }  // namespace vg
+
+struct vg_index;
+struct vg_comm;
 
 struct vg_ctx {
     int device = 0;
@@ -54,12 +77,37 @@ struct PartState {
     uint32_t* d_filter = nullptr;
 };
 
+// One rank of a group of GPUs whose processes map each other's memory (CUDA IPC, NVLink).  Everything a
+// peer must reach lives in ONE device allocation per rank, the arena; all ranks carve it up with the same
+// sequence of sizes, so an object sits at the same offset everywhere and a peer's copy is
+// peer_base[r] + offset (a symmetric heap).
+struct vg_comm {
+    vg_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    uint8_t* peer_base[vg::kMaxWorld] = {};
+    bool connected = false;
+    unsigned long long epoch = 0;        // barriers enqueued so far (same on every rank)
+    unsigned int* d_timeout = nullptr;   // raised by a barrier that gave up on a peer
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    size_t reduce_off = 0, reduce_bytes = 0;  // symmetric scratch of vg_count_allreduce
+    uint8_t* d_reduced = nullptr;
+    uint64_t launches = 0;
+};
+
 struct vg_index {
     vg_ctx* ctx = nullptr;
     PartState part;
     uint64_t n = 0;
+    vg_comm* comm = nullptr;       // sharded index: the group it is spread over
+    bool sharded = false;
+    uint64_t n_own = 0;            // sharded: keys whose home bucket lies in this GPU's table
+    uint64_t* d_idx = nullptr;     // sharded: caller position of each own key
+    size_t counts_off = 0;         // sharded: arena offset of d_counts (peers read it in the combine)
+    uint8_t* d_combined = nullptr; // sharded: counts of all n keys after the combine
     vg::IndexView view{};
-    uint64_t* d_key56 = nullptr;   // key order given at create: the canonical k-mer of each key
+    uint64_t* d_key56 = nullptr;   // key order given at create: the canonical k-mer of each key (sharded: own keys)
     uint8_t* d_counts = nullptr;   // scratch for vg_count_end
     uint8_t* d_flags = nullptr;    // optional per-entry subset for vg_count_histogram
     unsigned long long* d_hist = nullptr;
@@ -79,6 +127,9 @@ struct vg_cbf {
 };
 
 namespace vg {
+void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
+int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier
+int sharded_end(vg_index* ix, uint8_t* c_out);        // vg_comm.cpp: extract own keys, combine over NVLink
 int enqueue_piece(vg_index* ix, int slot, const char* src, uint64_t len);
 int count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
 }  // namespace vg

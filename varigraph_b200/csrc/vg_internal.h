@@ -5,11 +5,20 @@
 
 namespace vg {
 
+constexpr int kMaxWorld = 16;     // ranks of a vg_comm (one GPU each)
+struct PeerPtrs {                 // the same symmetric-arena object on every rank, indexed by rank
+    void* p[kMaxWorld];
+};
+
 struct IndexView {
     uint64_t* slots;                // nbuckets * 4 slots of [canonical k-mer:56 | count:8]; empty = ~0
-    uint32_t nbuckets;
+    uint32_t nbuckets;              // buckets of THIS table
     uint32_t k;
     uint64_t mask;                  // 2^(2k) - 1
+    // A sharded index is one table of nb_total buckets cut into `world` equal runs, one per GPU: this
+    // table holds global buckets [b_base, b_base + nbuckets).  Unsharded: nb_total == nbuckets, b_base == 0.
+    uint32_t nb_total;
+    uint32_t b_base;
 };
 
 // Presence pre-filter: a word-blocked Bloom filter over the index keys (both bits of a key sit in
@@ -37,12 +46,21 @@ struct InsertReport {               // lives in device memory
 // is then streamed into L2 once and probed by all of its keys, so index probes and counter
 // updates hit L2 instead of paying one random DRAM access each.
 struct PartView {
-    uint64_t* keybuf;               // P partitions x cap hashes (key >> 8)
-    unsigned long long* cursor;     // P fill counts
-    uint32_t P;
-    uint32_t shift;                 // partition = bucket >> shift
-    uint64_t cap;                   // capacity of one partition; keys beyond it are probed directly
+    uint64_t* keybuf;               // this GPU's key lists: P_local slices x world sources x cap canonical k-mers
+    unsigned long long* cursor;     // P fill counts of the lists THIS GPU writes (global slice numbering)
+    uint32_t P;                     // slices of the whole (global) table = P_local * world
+    uint32_t shift;                 // slice = global bucket >> shift
+    uint64_t cap;                   // capacity of one key list; keys beyond it are probed directly
     uint32_t* ctr;                  // 2 x (4 << shift) u32 side counters: hits of the slice being probed
+    // Sharded index (world > 1): slice p belongs to GPU p / P_local, and the scatter stores its keys
+    // straight into that GPU's key list for source `rank` over NVLink (peer memory mapped with CUDA
+    // IPC) -- the all-to-all of k-mers is the scatter's own copy-out.  Unsharded: world == 1,
+    // P_local == P, peer_keybuf[0] == keybuf, peer_slots[0] == the table.
+    uint32_t world, rank, P_local;
+    unsigned long long* incount;    // world x P_local: how many keys each source put into each of MY lists
+    uint64_t* peer_keybuf[kMaxWorld];
+    uint64_t* peer_slots[kMaxWorld];           // for the rare direct probe of a key whose list is full
+    unsigned long long* peer_incount[kMaxWorld];
 };
 constexpr uint32_t kMaxPartitions = 1024;
 
@@ -61,6 +79,11 @@ cudaError_t launch_table_fill_empty(uint64_t* slots, uint64_t nslots, cudaStream
 cudaError_t launch_unhash(uint64_t* d_key56, uint64_t n, uint64_t mask, cudaStream_t s);
 cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
                           cudaStream_t s);
+// Sharded build: of the n canonical k-mers at d_key56 (caller positions first_idx + i), append those whose
+// home bucket lies in this table to d_own (+ their caller positions to d_own_idx) at *d_n_own.
+// d_own == nullptr only counts them.
+cudaError_t launch_select_owned(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint64_t first_idx,
+                                uint64_t* d_own, uint64_t* d_own_idx, unsigned long long* d_n_own, cudaStream_t s);
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
                          int ctas_per_sm, int nsm, cudaStream_t s);
@@ -73,8 +96,20 @@ cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint6
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
-cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
+// d_idx == nullptr: out[i] = count of d_key56[i]; else out[d_idx[i]] = ... (a sharded index's own keys)
+cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, const uint64_t* d_idx, uint64_t n, void* d_out,
                            int out_elem_bytes, cudaStream_t s);
+// ---- peer-memory collectives (vg_comm) ----
+// Device-side barrier: every rank stores `epoch` into slot `rank` of every peer's flag array, then waits
+// until all `world` slots of its own array have reached it.  Gives up after timeout_ns (a dead peer must
+// not hang the GPU) and raises *d_timeout.
+cudaError_t launch_peer_barrier(const PeerPtrs& peer_flags, int world, int rank, unsigned long long epoch,
+                                unsigned long long timeout_ns, unsigned int* d_timeout, cudaStream_t s);
+// Tell every owner how many keys this rank put into each of its lists (cursor -> peer incount), re-arm the cursors.
+cudaError_t launch_publish_counts(const PartView& pv, cudaStream_t s);
+// out[i] = min(255, sum over ranks of peer_counts[r][i]) for i in [0, n): the count reduce over NVLink.
+cudaError_t launch_combine_counts(const PeerPtrs& peer_counts, int world, uint64_t n, uint8_t* d_out, int nsm,
+                                  cudaStream_t s);
 cudaError_t launch_histogram(const uint8_t* d_counts, const uint8_t* d_flags, uint64_t n, unsigned long long* d_hist,
                              cudaStream_t s);
 cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes, uint64_t* d_out,

@@ -40,7 +40,7 @@ __global__ void insert_kernel(IndexView ix, const uint64_t* __restrict__ key56, 
     uint64_t key = key56[i];
     if (key == kKey56Max) return;  // not a canonical k-mer (min(fwd, rev) is never all ones): cannot be hit
     uint64_t want = key << 8;
-    uint32_t b = bucket_of(key, ix.nbuckets);
+    uint32_t b = bucket_of(key, ix.nb_total) - ix.b_base;  // a sharded build only passes this table's own keys
     for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
         uint64_t* base = ix.slots + 4ull * b;
 #pragma unroll
@@ -56,6 +56,21 @@ __global__ void insert_kernel(IndexView ix, const uint64_t* __restrict__ key56, 
         b = (b + 1 == ix.nbuckets) ? 0 : b + 1;
     }
     atomicAdd(&rep->failed, 1ull);
+}
+
+// Sharded build: keep the keys whose home bucket lies in this GPU's run of the global table.
+__global__ void select_owned_kernel(IndexView ix, const uint64_t* __restrict__ key56, uint64_t n, uint64_t first_idx,
+                                    uint64_t* own, uint64_t* own_idx, unsigned long long* n_own) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = key56[i];
+    if (key == kKey56Max) return;  // in nobody's table: its count is 0 everywhere
+    if (bucket_of(key, ix.nb_total) - ix.b_base >= ix.nbuckets) return;
+    const unsigned long long at = atomicAdd(n_own, 1ull);
+    if (own) {
+        own[at] = key;
+        own_idx[at] = first_idx + i;
+    }
 }
 
 __global__ void clear_counts_kernel(uint64_t* slots, uint64_t nslots) {
@@ -128,7 +143,7 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
         uint64_t v[kBatch][4];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            bk[b] = bucket_of(keys[b], ix.nbuckets);
+            bk[b] = bucket_of(keys[b], ix.nb_total) - ix.b_base;
             if ((havem >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
         }
 #pragma unroll
@@ -273,22 +288,50 @@ struct ScatterCfg {
 // Rare path of the scatter: the key's partition buffer is full (a very skewed round, e.g. thousands
 // of identical reads).  Probe it right here, one key at a time, so no key is ever dropped and no
 // worst-case overflow buffer has to exist.  Kept out of line: it must not cost the hot path registers.
-__device__ __noinline__ void probe_one_direct(IndexView ix, uint64_t key, CountStats* stats) {
-    uint32_t b = bucket_of(key, ix.nbuckets);
-    for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
+// `slots` / `b` are the table that owns the key and its home bucket there: for a sharded index that may be
+// a peer GPU's table (64-bit CAS works over NVLink; no sweep runs while keys are being scattered).
+__device__ __noinline__ void probe_one_direct(uint64_t* slots, uint32_t nbuckets, uint32_t b, uint64_t key,
+                                              CountStats* stats) {
+    for (uint32_t tries = 0; tries < nbuckets; ++tries) {
         uint64_t v[4];
-        ld_bucket(ix.slots + 4ull * b, v);
+        ld_bucket(slots + 4ull * b, v);
         bool saw_empty;
         uint64_t seen = 0;
         const int hs = match_slot(v, key, saw_empty, seen);
         if (hs >= 0) {
-            slot_sat_add(ix.slots + 4ull * b + hs, seen, 1u);
+            slot_sat_add(slots + 4ull * b + hs, seen, 1u);
             atomicAdd(&stats->hits, 1ull);
             return;
         }
         if (saw_empty) return;
-        b = (b + 1 == ix.nbuckets) ? 0 : b + 1;
+        b = (b + 1 == nbuckets) ? 0 : b + 1;
     }
+}
+// The table that owns `key` and the key's home bucket there.
+__device__ __forceinline__ void owner_table(const IndexView& ix, const PartView& pv, uint64_t key, uint64_t*& slots,
+                                            uint32_t& b) {
+    const uint32_t bg = bucket_of(key, ix.nb_total);
+    slots = ix.slots;
+    b = bg;
+    if (pv.world > 1) {
+        const uint32_t o = bg / ix.nbuckets;
+        slots = pv.peer_slots[o];
+        b = bg - o * ix.nbuckets;
+    }
+}
+__device__ __forceinline__ void probe_one_direct(const IndexView& ix, const PartView& pv, uint64_t key, CountStats* stats) {
+    uint64_t* slots;
+    uint32_t b;
+    owner_table(ix, pv, key, slots, b);
+    probe_one_direct(slots, ix.nbuckets, b, key, stats);
+}
+// Where slice p's keys from this GPU go: the slice owner's key list for source `rank`.
+__device__ __forceinline__ uint64_t* list_of(const PartView& pv, uint32_t p) {
+    if (pv.world > 1) {
+        const uint32_t o = p / pv.P_local, pl = p - o * pv.P_local;
+        return pv.peer_keybuf[o] + ((uint64_t)pl * pv.world + pv.rank) * pv.cap;
+    }
+    return pv.keybuf + (uint64_t)p * pv.cap;
 }
 
 __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n) {
@@ -309,10 +352,11 @@ __device__ __forceinline__ uint64_t ld_shared_u64(uint32_t addr) {
 }
 
 // A key that finds its tile bin full: reserve one place in the slice's key list right away.
-__device__ __noinline__ void scatter_one_global(IndexView ix, PartView pv, uint32_t p, uint64_t key, CountStats* stats) {
-    const unsigned long long pos = atomicAdd(&pv.cursor[p], 1ull);
-    if (pos < pv.cap) pv.keybuf[(uint64_t)p * pv.cap + pos] = key;
-    else probe_one_direct(ix, key, stats);
+__device__ __noinline__ void scatter_one_global(unsigned long long* cursor_p, uint64_t* list, uint64_t cap, uint64_t* slots,
+                                                uint32_t nbuckets, uint32_t b, uint64_t key, CountStats* stats) {
+    const unsigned long long pos = atomicAdd(cursor_p, 1ull);
+    if (pos < cap) list[pos] = key;
+    else probe_one_direct(slots, nbuckets, b, key, stats);
 }
 
 // K1 of the partitioned path.  Per 4 KiB CTA tile, eight positions per lane at a time: encode + hash,
@@ -366,7 +410,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             for (int j = 0; j < 8; ++j) {
                 ps[j] = 0;
                 if ((emit >> j) & 1u) {
-                    const uint32_t p = bucket_of(keys[j], ix.nbuckets) >> pv.shift;
+                    const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
                     const uint32_t r = atomicAdd(&hist[p], 1u);
                     ps[j] = p;
                     if (r < cap) st_shared_u64(bins_s + ((p * cfg.stride + r) << 3), keys[j]);
@@ -376,7 +420,12 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             if (over) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if ((over >> j) & 1u) scatter_one_global(ix, pv, ps[j], keys[j], stats);
+                    if ((over >> j) & 1u) {
+                        uint64_t* slots;
+                        uint32_t b;
+                        owner_table(ix, pv, keys[j], slots, b);
+                        scatter_one_global(&pv.cursor[ps[j]], list_of(pv, ps[j]), pv.cap, slots, ix.nbuckets, b, keys[j], stats);
+                    }
             }
         };
         if (kOdd) {
@@ -409,7 +458,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             if (n) b = atomicAdd(&pv.cursor[p], (unsigned long long)n);
             cnt_s[p] = n;
             fit_s[p] = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
-            base_s[p] = (unsigned long long)p * pv.cap + b;
+            base_s[p] = (unsigned long long)(list_of(pv, p) + b);
         }
         __syncthreads();
         // ---- ... then one bin slot per thread and step; a bin's keys are contiguous on both sides ----
@@ -418,8 +467,8 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             const uint32_t p = __umulhi(q, cfg.magic), i = q - p * cap;
             if (i < cnt_s[p]) {
                 const uint64_t key = ld_shared_u64(bins_s + ((p * cfg.stride + i) << 3));
-                if (i < fit_s[p]) pv.keybuf[base_s[p] + i] = key;
-                else probe_one_direct(ix, key, stats);  // slice list full (a very skewed round): still exact
+                if (i < fit_s[p]) reinterpret_cast<uint64_t*>(base_s[p])[i] = key;
+                else probe_one_direct(ix, pv, key, stats);  // slice list full (a very skewed round): still exact
             }
         }
         __syncthreads();
@@ -451,7 +500,7 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
         uint64_t v[kBatch][4];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            bk[b] = bucket_of(keys[b], ix.nbuckets);
+            bk[b] = bucket_of(keys[b], ix.nb_total) - ix.b_base;
             if ((emit >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
         }
 #pragma unroll
@@ -599,7 +648,8 @@ probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsign
 // extraction: counts in the key order given at index creation
 // ---------------------------------------------------------------------------
 template <typename OutT>
-__global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56, uint64_t n, OutT* out) {
+__global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56, const uint64_t* __restrict__ idx, uint64_t n,
+                               OutT* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t key = key56[i];
@@ -607,7 +657,7 @@ __global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56,
     if (key == kKey56Max) {
         c = 0;  // not a canonical k-mer: no read position can produce it
     } else {
-        uint32_t b = bucket_of(key, ix.nbuckets);
+        uint32_t b = bucket_of(key, ix.nb_total) - ix.b_base;
         for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
             uint64_t v[4];
             ld_bucket(ix.slots + 4ull * b, v);
@@ -619,7 +669,75 @@ __global__ void extract_kernel(IndexView ix, const uint64_t* __restrict__ key56,
             b = (b + 1 == ix.nbuckets) ? 0 : b + 1;
         }
     }
-    out[i] = (OutT)c;
+    out[idx ? idx[i] : i] = (OutT)c;
+}
+
+// ---------------------------------------------------------------------------
+// peer-memory collectives of vg_comm (one process per GPU; peers mapped with CUDA IPC over NVLink)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, unsigned long long epoch,
+                                    unsigned long long timeout_ns, unsigned int* timed_out) {
+    const int t = threadIdx.x;
+    if (t >= world) return;
+    __threadfence_system();
+    unsigned long long* theirs = (unsigned long long*)flags.p[t] + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = (const unsigned long long*)flags.p[rank] + t;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (global_ns() - t0 > timeout_ns) {  // a dead peer must not hang this GPU
+            atomicExch(timed_out, 1u);
+            break;
+        }
+        __nanosleep(256);
+    }
+}
+
+__global__ void publish_counts_kernel(PartView pv) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pv.P) return;
+    const uint32_t o = p / pv.P_local, pl = p - o * pv.P_local;
+    const unsigned long long n = pv.cursor[p];
+    pv.peer_incount[o][(size_t)pv.rank * pv.P_local + pl] = n < pv.cap ? n : pv.cap;
+    pv.cursor[p] = 0;  // re-armed for the next round
+}
+
+// out = min(255, sum over ranks) per byte, 16 bytes per thread and step: even and odd bytes are summed in
+// 16-bit lanes (world <= 16 ranks x 255 fits), clamped, and packed again.
+__global__ void combine_counts_kernel(PeerPtrs src, int world, uint64_t n, uint8_t* out) {
+    const uint64_t nvec = n / 16;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
+        for (int r = 0; r < world; ++r) {
+            const uint4 v = reinterpret_cast<const uint4*>(src.p[r])[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ev[j] += w[j] & 0x00ff00ffu;
+                od[j] += (w[j] >> 8) & 0x00ff00ffu;
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __vminu2(ev[j], 0x00ff00ffu) | (__vminu2(od[j], 0x00ff00ffu) << 8);
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
+        const uint64_t i = nvec * 16 + threadIdx.x;
+        uint32_t sum = 0;
+        for (int r = 0; r < world; ++r) sum += reinterpret_cast<const uint8_t*>(src.p[r])[i];
+        out[i] = (uint8_t)min(sum, 255u);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -792,6 +910,30 @@ cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t
     return cudaGetLastError();
 }
 
+cudaError_t launch_select_owned(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint64_t first_idx,
+                                uint64_t* d_own, uint64_t* d_own_idx, unsigned long long* d_n_own, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    select_owned_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix, d_key56, n, first_idx, d_own, d_own_idx, d_n_own);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_barrier(const PeerPtrs& flags, int world, int rank, unsigned long long epoch,
+                                unsigned long long timeout_ns, unsigned int* d_timeout, cudaStream_t s) {
+    peer_barrier_kernel<<<1, 32, 0, s>>>(flags, world, rank, epoch, timeout_ns, d_timeout);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_publish_counts(const PartView& pv, cudaStream_t s) {
+    publish_counts_kernel<<<(pv.P + 255) / 256, 256, 0, s>>>(pv);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_combine_counts(const PeerPtrs& counts, int world, uint64_t n, uint8_t* d_out, int nsm, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    combine_counts_kernel<<<grid_1d(n / 16 + 1, 256, (unsigned)nsm * 8), 256, 0, s>>>(counts, world, n, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s) {
     uint64_t nslots = 4ull * ix.nbuckets;
     clear_counts_kernel<<<grid_1d(nslots, 256, 148 * 16), 256, 0, s>>>(ix.slots, nslots);
@@ -867,40 +1009,47 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
                                     cudaStream_t s) {
     const bool b4 = count_variant() == 4;
     int occ = 0;
-    auto slice = [&](uint32_t p, uint32_t& b0, uint32_t& b1) {
+    auto slice = [&](uint32_t p, uint32_t& b0, uint32_t& b1) {  // local slice p of THIS table
         b0 = p << pv.shift;
         const uint64_t e = ((uint64_t)(p + 1)) << pv.shift;
         b1 = (uint32_t)(e > ix.nbuckets ? ix.nbuckets : e);
     };
     const size_t ctr_elems = (size_t)4 << pv.shift;
-    // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice
-    for (uint32_t p = 0; p <= pv.P; ++p) {
+    const bool sharded = pv.world > 1;
+    const uint32_t nsub = sharded ? pv.world : 1u;
+    // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice.
+    // A sharded index has one key list per source GPU and slice: one launch each, the first also retires.
+    for (uint32_t p = 0; p <= pv.P_local; ++p) {
         uint32_t b0 = 0, b1 = 0, r0 = 0, r1 = 0;
-        if (p < pv.P) slice(p, b0, b1);
+        if (p < pv.P_local) slice(p, b0, b1);
         if (p > 0) slice(p - 1, r0, r1);
         uint32_t* cur = pv.ctr + (size_t)(p & 1) * ctr_elems;
         uint32_t* prv = pv.ctr + (size_t)((p + 1) & 1) * ctr_elems;
-        const uint64_t* list = pv.keybuf + (uint64_t)(p < pv.P ? p : 0) * pv.cap;
-        const unsigned long long* cnt = pv.cursor + (p < pv.P ? p : 0);
-        if (b4) {
-            if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<4>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-            probe_slice_kernel<4><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
-        } else {
-            if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<8>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-            probe_slice_kernel<8><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+        const uint32_t q = p < pv.P_local ? p : 0;
+        for (uint32_t sub = 0; sub < (p < pv.P_local ? nsub : 1u); ++sub) {
+            const uint64_t* list = pv.keybuf + ((uint64_t)q * nsub + sub) * pv.cap;
+            const unsigned long long* cnt = sharded ? pv.incount + (size_t)sub * pv.P_local + q : pv.cursor + q;
+            if (sub) r0 = r1 = 0;
+            if (b4) {
+                if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<4>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
+                probe_slice_kernel<4><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+            } else {
+                if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<8>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
+                probe_slice_kernel<8><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+            }
         }
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || sharded) return e;  // sharded: publish_counts re-armed the cursors already
     return cudaMemsetAsync(pv.cursor, 0, pv.P * sizeof(unsigned long long), s);
 }
 
-cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, uint64_t n, void* d_out,
+cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, const uint64_t* d_idx, uint64_t n, void* d_out,
                            int out_elem_bytes, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     unsigned g = (unsigned)((n + 255) / 256);
-    if (out_elem_bytes == 1) extract_kernel<uint8_t><<<g, 256, 0, s>>>(ix, d_key56, n, (uint8_t*)d_out);
-    else if (out_elem_bytes == 4) extract_kernel<uint32_t><<<g, 256, 0, s>>>(ix, d_key56, n, (uint32_t*)d_out);
+    if (out_elem_bytes == 1) extract_kernel<uint8_t><<<g, 256, 0, s>>>(ix, d_key56, d_idx, n, (uint8_t*)d_out);
+    else if (out_elem_bytes == 4) extract_kernel<uint32_t><<<g, 256, 0, s>>>(ix, d_key56, d_idx, n, (uint32_t*)d_out);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
