@@ -157,17 +157,22 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
 
 // Home bucket of a key (a canonical k-mer, i.e. structured input: fold the high half down before the
 // Fibonacci multiply, take the product's high word, range-reduce without a division).
+__device__ __forceinline__ uint64_t key_mix(uint64_t key56) { return (key56 ^ (key56 >> 29)) * 0x9E3779B97F4A7C15ULL; }
 __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets) {
-    uint64_t x = (key56 ^ (key56 >> 29)) * 0x9E3779B97F4A7C15ULL;
-    return __umulhi((uint32_t)(x >> 32), nbuckets);
+    return __umulhi((uint32_t)(key_mix(key56) >> 32), nbuckets);
 }
 
 // ---- presence pre-filter (word-blocked Bloom, 2 bits per key in one 32-bit word) -------------
-// word: which 32-bit word; bits: the key's two bit positions, packed as lo5 | hi5 << 5.
+// word: which 32-bit word; bits: the key's two bit positions, packed as lo5 | hi5 << 5.  Both come from
+// the SAME product as the key's bucket (key_mix): the word from its high half (like the bucket -- that
+// correlation is harmless, keys still spread evenly over the words), the bits from the top of its low
+// half, so the scatter pays one 64-bit multiply per k-mer for the filter and the table slice together.
+__device__ __forceinline__ void prefilter_slot_mixed(uint64_t mixed, uint32_t nwords, uint32_t& word, uint32_t& bits) {
+    word = __umulhi((uint32_t)(mixed >> 32), nwords);
+    bits = (uint32_t)mixed >> 22;
+}
 __device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& bits) {
-    const uint64_t h = key56 * 0xD6E8FEB86659FD93ULL;
-    word = __umulhi((uint32_t)(h >> 32), nwords);
-    bits = (uint32_t)h & 1023u;
+    prefilter_slot_mixed(key_mix(key56), nwords, word, bits);
 }
 __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) { return (1u << (bits & 31u)) | (1u << (bits >> 5)); }
 

@@ -282,8 +282,11 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
 struct ScatterCfg {
     uint32_t cap;     // keys per bin; the rare overflow goes to global memory key by key
     uint32_t stride;  // cap | 1
-    uint32_t magic;   // 2^32 / cap + 1: slot / cap == __umulhi(slot, magic) for slot < 2^32 / cap
 };
+// c_magic[d] = 2^32 / d + 1, so that x / d == __umulhi(x, c_magic[d]) for x < 2^32 / d: the copy-out
+// walks bins x ranks with the tile's largest bin as the row length, whatever that turns out to be.
+constexpr uint32_t kMaxBinCap = 4095;
+__constant__ uint32_t c_magic[kMaxBinCap + 1];
 
 // Rare path of the scatter: the key's partition buffer is full (a very skewed round, e.g. thousands
 // of identical reads).  Probe it right here, one key at a time, so no key is ever dropped and no
@@ -378,8 +381,9 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     uint32_t* fit_s = cnt_s + P;
     uint8_t* lut = reinterpret_cast<uint8_t*>(fit_s + P);
     __shared__ unsigned long long blk_pos;
+    __shared__ uint32_t max_cnt;
     lut_init(lut);
-    if (threadIdx.x == 0) blk_pos = 0;
+    if (threadIdx.x == 0) blk_pos = 0, max_cnt = 0;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     KmerParams kp{ix.k, ix.mask};
@@ -390,29 +394,33 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         // ---- encode, filter, bin -----------------------------------------------------------------
         auto bin8 = [&](const uint64_t (&keys)[8], uint32_t emit) {
+            uint32_t ps[8];      // table slice of each key (with the pre-filter: | its filter bits << 10 at first)
             if (pf.words) {  // L2-resident presence pre-filter: never a false negative
-                uint32_t fw[8], fb[8];
+                uint32_t fw[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    uint32_t w;
-                    prefilter_slot(keys[j], pf.nwords, w, fb[j]);
+                    const uint64_t x = key_mix(keys[j]);  // one product serves the filter and the table slice
+                    uint32_t w, fb;
+                    prefilter_slot_mixed(x, pf.nwords, w, fb);
+                    ps[j] = (__umulhi((uint32_t)(x >> 32), ix.nb_total) >> pv.shift) | (fb << 10);
                     fw[j] = ((emit >> j) & 1u) ? __ldg(pf.words + w) : 0u;
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint32_t m = prefilter_mask(fb[j]);
+                    const uint32_t m = prefilter_mask(ps[j] >> 10);
                     if ((fw[j] & m) != m) emit &= ~(1u << j);
+                    ps[j] &= 1023u;
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ps[j] = bucket_of(keys[j], ix.nb_total) >> pv.shift;
             }
             uint32_t over = 0;   // keys whose bin is full (rare): handled after the hot loop
-            uint32_t ps[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                ps[j] = 0;
                 if ((emit >> j) & 1u) {
-                    const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
+                    const uint32_t p = ps[j];
                     const uint32_t r = atomicAdd(&hist[p], 1u);
-                    ps[j] = p;
                     if (r < cap) st_shared_u64(bins_s + ((p * cfg.stride + r) << 3), keys[j]);
                     else over |= 1u << j;
                 }
@@ -457,14 +465,15 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             unsigned long long b = 0;
             if (n) b = atomicAdd(&pv.cursor[p], (unsigned long long)n);
             cnt_s[p] = n;
+            if (n) atomicMax(&max_cnt, n);
             fit_s[p] = b >= pv.cap ? 0u : (uint32_t)min((unsigned long long)n, pv.cap - b);
             base_s[p] = (unsigned long long)(list_of(pv, p) + b);
         }
         __syncthreads();
         // ---- ... then one bin slot per thread and step; a bin's keys are contiguous on both sides ----
-        const uint32_t nslots = P * cap;
+        const uint32_t row = max_cnt, nslots = P * row, magic = c_magic[row];
         for (uint32_t q = threadIdx.x; q < nslots; q += blockDim.x) {
-            const uint32_t p = __umulhi(q, cfg.magic), i = q - p * cap;
+            const uint32_t p = __umulhi(q, magic), i = q - p * row;
             if (i < cnt_s[p]) {
                 const uint64_t key = ld_shared_u64(bins_s + ((p * cfg.stride + i) << 3));
                 if (i < fit_s[p]) reinterpret_cast<uint64_t*>(base_s[p])[i] = key;
@@ -472,6 +481,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) max_cnt = 0;  // read again only after the next tile's two barriers
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_pos += __shfl_xor_sync(kFullMask, n_pos, d);
@@ -976,22 +986,34 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     Chunk c = make_chunk(d_bases, nbytes);
     using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true> : (KernelT)scatter_kernel<false>;
-    // Bin capacity: ~2.2x the expected k-mers per slice and tile (the pre-filter passes roughly half),
+    // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
     // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
     // path, so this only tunes speed.
-    static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 2.2; }();
+    static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 1.8; }();
     static const size_t budget = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52) * 1024; }();
     const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
     const uint32_t want = (uint32_t)(expect * capx) + 8;
     auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 256; };
-    uint32_t cap = want;
+    static bool magic_on[64] = {};  // constant memory is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& magic_ready = magic_on[dev & 63];
+    if (!magic_ready) {
+        uint32_t m[kMaxBinCap + 1];
+        m[0] = 0;
+        for (uint32_t d = 1; d <= kMaxBinCap; ++d) m[d] = (uint32_t)((1ull << 32) / d) + 1u;
+        cudaError_t e = cudaMemcpyToSymbol(c_magic, m, sizeof m);
+        if (e != cudaSuccess) return e;
+        magic_ready = true;
+    }
+    uint32_t cap = want > kMaxBinCap ? kMaxBinCap : want;
     while (cap > 4 && bytes(cap) > budget) --cap;
     if (cap < want && cap < 24) {  // many slices: two CTAs per SM with deeper bins
-        cap = want;
+        cap = want > kMaxBinCap ? kMaxBinCap : want;
         while (cap > 4 && bytes(cap) > 2 * budget) --cap;
     }
-    ScatterCfg cfg{cap, cap | 1u, (uint32_t)((1ull << 32) / cap) + 1u};
+    ScatterCfg cfg{cap, cap | 1u};
     const size_t smem = bytes(cap);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
