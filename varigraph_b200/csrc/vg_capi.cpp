@@ -85,8 +85,14 @@ static int part_setup(vg_index* ix) {
     }
     if (force != 1 && table_bytes < (8ull << 20)) return VG_OK;   // tiny table: direct probing
     if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
+    // A round = the bases scattered before one sweep of the table: 1 G to start with (10 bytes of key list
+    // per base); part_grow doubles it when a sample turns out to be longer (VG_ROUND_KEYS pins it).
     uint64_t round_keys = 1024ull << 20, slack = 65536;
-    if (const char* e = getenv("VG_ROUND_KEYS")) round_keys = strtoull(e, nullptr, 10) >= 4096 ? strtoull(e, nullptr, 10) : round_keys;
+    ix->part.may_grow = true;
+    if (const char* e = getenv("VG_ROUND_KEYS")) {
+        round_keys = strtoull(e, nullptr, 10) >= 4096 ? strtoull(e, nullptr, 10) : round_keys;
+        ix->part.may_grow = false;
+    }
     if (const char* e = getenv("VG_PART_SLACK")) slack = strtoull(e, nullptr, 10);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -96,6 +102,7 @@ static int part_setup(vg_index* ix) {
     ps.view.P = (uint32_t)P;
     ps.view.shift = shift;
     ps.view.cap = (round_keys / P) * 5 / 4 + slack;
+    ps.slack = slack;
     ps.view.world = 1;
     ps.view.rank = 0;
     ps.view.P_local = (uint32_t)P;
@@ -149,6 +156,32 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     return VG_OK;
 }
 
+// A sample did not fit one round.  Every sweep costs a pass over the whole table plus ~2 P launches (about
+// 1.1 ms on the chr20 index), so the next rounds are made twice as long -- up to 4 G bases, and only while
+// the key lists stay within a quarter of the free HBM.  Called right after a sweep: the lists are empty.
+static void part_grow(vg_index* ix, cudaStream_t s) {
+    PartState& ps = ix->part;
+    if (!ps.may_grow || ix->sharded || ps.round_keys >= (4096ull << 20)) return;
+    const uint64_t P = ps.view.P, round2 = ps.round_keys * 2, cap2 = (round2 / P) * 5 / 4 + ps.slack;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (cap2 - ps.view.cap) * P * sizeof(uint64_t) > free_b / 4) {
+        cudaGetLastError();
+        ps.may_grow = false;
+        return;
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return;
+    uint64_t* bigger = nullptr;
+    if (cudaMalloc((void**)&bigger, P * cap2 * sizeof(uint64_t)) != cudaSuccess) {
+        cudaGetLastError();
+        ps.may_grow = false;
+        return;
+    }
+    cudaFree(ps.view.keybuf);
+    ps.view.keybuf = bigger;
+    ps.view.cap = cap2;
+    ps.round_keys = round2;
+}
+
 // Count every k-mer of a device-resident chunk on stream s (direct or partitioned).
 static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nbytes, cudaStream_t s) {
     vg_ctx* c = ix->ctx;
@@ -169,6 +202,7 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
         if (room < 64 && ps.pending) {
             int rc = part_flush(ix, s);
             if (rc) return rc;
+            part_grow(ix, s);
             room = (int64_t)(ps.round_keys / tile_bytes);
         }
         const int64_t nt = std::min<int64_t>(T - t, room);

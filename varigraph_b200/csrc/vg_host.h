@@ -73,6 +73,8 @@ struct PartState {
     vg::PartView view{};
     uint64_t round_keys = 0;   // keys a round may accumulate before it must be probed
     uint64_t pending = 0;      // upper bound of keys scattered since the last probe pass
+    uint64_t slack = 0;        // extra keys per list on top of 1.25 x the even share
+    bool may_grow = false;     // rounds double (up to 4 G bases) when a sample needs more than one
     vg::PrefilterView filter{nullptr, 0};
     uint32_t* d_filter = nullptr;
 };
