@@ -2,7 +2,7 @@
 """Turn ncu outputs (gpurun_out/*.ncu-rep, launch-list CSVs) into the small text summaries kept here.
 
   python profiles/summarize_ncu.py rep  <file.ncu-rep> <out.txt> "<title>"
-  python profiles/summarize_ncu.py list <launches.csv> <out.txt> "<title>"
+  python profiles/summarize_ncu.py list <launches.csv> <out.txt> "<title>" [last_n]   (only the last n launches)
 """
 import collections
 import csv
@@ -61,7 +61,7 @@ def rep(path, out, title):
                 f.write(f"  {n:7d} {100 * n / T:5.1f}%  {r[ix['Source']].strip()[:70]:70s} {best}\n")
 
 
-def launches(path, out, title):
+def launches(path, out, title, last_n=0):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr = rows[0]
     i_name, i_m, i_v, i_id = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
@@ -69,7 +69,7 @@ def launches(path, out, title):
     for r in rows[1:]:
         d.setdefault(r[i_id], {"name": r[i_name].split("(")[0][-48:]})[r[i_m]] = float(r[i_v].replace(",", ""))
     agg = collections.OrderedDict()
-    for v in d.values():
+    for v in list(d.values())[-last_n:]:
         a = agg.setdefault(v["name"], collections.Counter())
         a["n"] += 1
         for k, x in v.items():
@@ -88,4 +88,7 @@ def launches(path, out, title):
 
 if __name__ == "__main__":
     mode, path, out, title = sys.argv[1:5]
-    (rep if mode == "rep" else launches)(path, out, title)
+    if mode == "rep":
+        rep(path, out, title)
+    else:
+        launches(path, out, title, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
