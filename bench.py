@@ -366,7 +366,9 @@ def main() -> None:
     from varigraph_b200 import dist as vdist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        numa = vdist.bind_to_gpu_numa(local)  # before any pinned allocation: staging memory next to the GPU
         dist.init_process_group("nccl", device_id=dev)
 
     ref, alt, pos, vlen, keys = make_graph(dev, L, a.variants, seed=20261017)
@@ -560,7 +562,8 @@ def main() -> None:
                                            + (f"sharded x{world} (k-mer all-to-all fused into the scatter over NVLink, "
                                               f"{len(round_cuts)} rounds)" if sharded else f"replicated, counts reduced by {reduce_how}")
                                            if world > 1 else "1 GPU"),
-                           "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush"},
+                           "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush",
+                           "host_binding": numa},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
                         "d2h_bytes_per_step": int(nkeys + 16), "counts_equal_device_path": e2e_counts_ok},
                 "gpu_launches": int(launches_timed) + steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,

@@ -84,6 +84,11 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
  * FastqKmer::fastq_file_open for each path.  threads = inflate/parse workers (files are
  * processed concurrently).  *read_bases accumulates mReadBase (src/fastq_kmer.cpp:105). */
 int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
+/* Plain (not gzip) four-line FASTQ is shipped as raw text and parsed on the GPU, every record checked
+ * against kseq's rules; anything else -- and a file from its first irregular record on -- goes through
+ * the host kseq reader, so results never depend on the road taken.  This counts the raw blocks the
+ * device accepted so far (diagnostic; VG_RAW_FASTQ=0 disables the raw road). */
+uint64_t vg_index_fastq_blocks(const vg_index* ix);
 
 /* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
  * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */

@@ -94,3 +94,29 @@ def test_two_ranks_sharded_index_matches_oracle(tmp_path, oracle, skewed):
     assert int(r0["rounds"]) == int(r1["rounds"]) >= 2
     if skewed:
         assert want.max() == 255
+
+
+def test_independent_handles_in_threads(vglib, oracle):
+    """BASELINE config 5 (samples sharded over GPUs, no exchange) in miniature: distinct contexts and
+    indexes driven concurrently from different threads, each counting its own sample."""
+    import threading
+    keys, lines, g = _workload(oracle, seed=21, nreads=4000)
+    samples = [lines[: 151 * 2500], lines[151 * 1500:]]
+    got = [None, None]
+
+    def run(i):
+        c = vglib.Context(0, buffer_mb=1)
+        ix = vglib.Index(c, keys, 27)
+        for _ in range(3):
+            ix.begin()
+            ix.submit(samples[i])
+            got[i] = ix.end()
+        ix.close()
+        c.close()
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(2):
+        want, wpos, whits = oracle.count_lines(keys, samples[i], 27)
+        assert got[i] is not None and np.array_equal(got[i][0], want) and got[i][1:] == (wpos, whits)

@@ -339,6 +339,81 @@ def test_count_files_kseq_edge_cases(ctx, vglib, oracle, tmp_path):
     ix.close()
 
 
+def _fastq_text(rng, g, nreads, crlf=False):
+    eol = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(nreads):
+        n = rng.randint(1, 260)
+        at = rng.randint(0, g.size - n)
+        seq = g[at: at + n].tobytes()
+        if rng.random() < 0.02:
+            seq = seq[: n // 2] + b"N" + seq[n // 2 + 1:]
+        qual = bytes(rng.choice(b"@+>IJ#") for _ in range(len(seq)))   # quality lines may start with @ + >
+        out.append(b"@r%d some text" % i + eol + seq + eol + b"+" + eol + qual + eol)
+    return out
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_count_files_raw_fastq_parsed_on_device(ctx, vglib, oracle, tmp_path, monkeypatch, crlf):
+    """Plain four-line FASTQ goes to the GPU as raw text in many record-aligned blocks; same counts and
+    mReadBase as the kseq road and as the oracle's kseq restatement."""
+    t = helpers.tiny()
+    rng = random.Random(5 + crlf)
+    recs = _fastq_text(rng, t["genome"], 40_000, crlf)
+    data = b"".join(recs)
+    p = tmp_path / "big.fq"
+    p.write_bytes(data)
+    lines, nreads, bases, status = oracle.fastq_to_lines(data)
+    want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    before = ix.fastq_blocks
+    ix.begin()
+    rb = ix.count_files([str(p), str(p)], threads=6)       # the same file twice: two raw files interleaved
+    counts, pos, hits = ix.end()
+    assert ix.fastq_blocks - before >= 2 * (len(data) // (1 << 20))
+    want2 = np.minimum(want.astype(np.int64) * 2, 255).astype(np.uint8)
+    assert rb == 2 * bases and (pos, hits) == (2 * wpos, 2 * whits) and np.array_equal(counts, want2)
+    monkeypatch.setenv("VG_RAW_FASTQ", "0")
+    before = ix.fastq_blocks
+    ix.begin()
+    rb0 = ix.count_files([str(p)], threads=2)
+    counts0, pos0, hits0 = ix.end()
+    assert ix.fastq_blocks == before
+    assert rb0 == bases and (pos0, hits0) == (wpos, whits) and np.array_equal(counts0, want)
+    ix.close()
+
+
+@pytest.mark.parametrize("flaw", ["multiline", "short_qual", "truncated_tail", "fasta_inside", "nul"])
+def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, tmp_path, flaw):
+    """An irregular record deep inside a plain FASTQ file: the blocks before it are counted on the device,
+    everything from its block on by the kseq reader -- together exactly what kseq makes of the file."""
+    t = helpers.tiny()
+    rng = random.Random(11)
+    recs = _fastq_text(rng, t["genome"], 30_000)
+    g = t["genome"]
+    s = g[1000:1100].tobytes()
+    bad = {"multiline": b"@m\n" + s[:50] + b"\n" + s[50:] + b"\n+\n" + b"I" * 50 + b"\n" + b"I" * 50 + b"\n",
+           "short_qual": b"@q\n" + s + b"\n+\n" + b"I" * 40 + b"\n",      # kseq stops reading the file here
+           "truncated_tail": b"",
+           "fasta_inside": b">f\n" + s + b"\n",
+           "nul": b"@z\n" + s[:30] + b"\x00" + s[31:] + b"\n+\n" + b"I" * 100 + b"\n"}[flaw]
+    data = b"".join(recs[:20_000]) + bad + b"".join(recs[20_000:])
+    if flaw == "truncated_tail":
+        data = data[:-37]
+    p = tmp_path / (flaw + ".fq")
+    p.write_bytes(data)
+    lines, nreads, bases, status = oracle.fastq_to_lines(data)
+    want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    before = ix.fastq_blocks
+    ix.begin()
+    rb = ix.count_files([str(p)], threads=4)
+    counts, pos, hits = ix.end()
+    assert ix.fastq_blocks - before >= 1
+    assert rb == bases and (pos, hits) == (wpos, whits) and np.array_equal(counts, want), flaw
+    ix.close()
+
+
 def test_count_files_vs_reference_live(ctx, vglib, reference, tmp_path):
     """Same graph.bin, same FASTQ files: reference CPU path vs CUDA path, per k-mer."""
     t = helpers.tiny()

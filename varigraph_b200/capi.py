@@ -51,6 +51,7 @@ def _load() -> ctypes.CDLL:
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
         "vg_count_files": (c_int, [c_void_p, P(c_char_p), c_int, c_int, P(c_uint64)]),
         "vg_count_flush": (c_int, [c_void_p]),
+        "vg_index_fastq_blocks": (c_uint64, [c_void_p]),
         "vg_index_set_flags": (c_int, [c_void_p, c_void_p]),
         "vg_count_histogram": (c_int, [c_void_p, c_void_p]),
         "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
@@ -234,6 +235,10 @@ class Index:
     @property
     def launches(self) -> int:
         return int(lib.vg_index_launches(self._h))
+
+    @property
+    def fastq_blocks(self) -> int:
+        return int(lib.vg_index_fastq_blocks(self._h))
 
     def begin(self) -> None:
         _chk(lib.vg_count_begin(self._h))

@@ -183,11 +183,12 @@ static void part_grow(vg_index* ix, cudaStream_t s) {
 }
 
 // Count every k-mer of a device-resident chunk on stream s (direct or partitioned).
-static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nbytes, cudaStream_t s) {
+static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nbytes, cudaStream_t s,
+                              const unsigned int* d_skip = nullptr) {
     vg_ctx* c = ix->ctx;
     PartState& ps = ix->part;
     if (!ps.enabled) {
-        CU(vg::launch_count(ix->view, d_bases, nbytes, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, s));
+        CU(vg::launch_count(ix->view, d_bases, nbytes, &ix->d_misc->stats, c->ctas_per_sm, c->nsm, s, d_skip));
         ix->launches += 1;
         return VG_OK;
     }
@@ -206,7 +207,7 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
             room = (int64_t)(ps.round_keys / tile_bytes);
         }
         const int64_t nt = std::min<int64_t>(T - t, room);
-        CU(vg::launch_scatter(ix->view, ps.view, ps.filter, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s));
+        CU(vg::launch_scatter(ix->view, ps.view, ps.filter, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s, d_skip));
         ix->launches += 1;
         ps.pending += (uint64_t)nt * tile_bytes;
         t += nt;
@@ -214,14 +215,42 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
     return VG_OK;
 }
 
-// Enqueue one staged piece that already sits in ring slot `si`'s pinned buffer (or at `src`).
-int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len) {
+// Scratch of the on-device FASTQ parser, sized for one staging chunk.
+int vg::ctx_ensure_fastq(vg_ctx* c) {
+    if (c->d_masked) return VG_OK;
+    vg::FastqScratch& f = c->fq;
+    f.max_tiles = (uint32_t)(c->chunk_bytes / 4096 + 2);
+    f.max_lines = (uint32_t)(c->chunk_bytes / 8 + 64);  // four-line FASTQ has lines of ~100 bytes; beyond this: host parser
+    CU(cudaMalloc((void**)&c->d_masked, c->chunk_bytes + 256));
+    CU(cudaMalloc((void**)&f.tile_count, (size_t)f.max_tiles * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&f.tile_base, (size_t)f.max_tiles * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&f.nlpos, (size_t)f.max_lines * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&f.blk, sizeof(vg::FastqBlockState)));
+    return VG_OK;
+}
+
+int vg::enqueue_raw_piece(vg_index* ix, int si, uint64_t len, vg::FastqFileState* d_file, uint32_t block_no) {
     vg_ctx* c = ix->ctx;
     vg::StageSlot& sl = c->ring[(size_t)si];
-    CU(cudaMemcpyAsync(sl.d_buf, src, len, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(sl.d_buf, sl.h_pin, len, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(sl.copied, c->copy_stream));
     CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
-    int rc = count_device_chunk(ix, sl.d_buf, len, c->compute_stream);
+    CU(vg::launch_fastq_block(sl.d_buf, (uint32_t)len, c->d_masked, c->fq, d_file, block_no, c->compute_stream));
+    ix->launches += 5;
+    return vg::enqueue_piece(ix, si, nullptr, len, &d_file->bad);
+}
+
+// Enqueue one staged piece that already sits in ring slot `si`'s pinned buffer (or at `src`); src == nullptr:
+// the piece is already on the device in ctx->d_masked (and is skipped if *d_skip turns out non-zero).
+int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len, const unsigned int* d_skip) {
+    vg_ctx* c = ix->ctx;
+    vg::StageSlot& sl = c->ring[(size_t)si];
+    if (src) {
+        CU(cudaMemcpyAsync(sl.d_buf, src, len, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(sl.copied, c->copy_stream));
+        CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
+    }
+    int rc = count_device_chunk(ix, src ? sl.d_buf : c->d_masked, len, c->compute_stream, d_skip);
     if (rc) return rc;
     CU(cudaEventRecord(sl.done, c->compute_stream));
     // Staged input arrives at PCIe speed, slower than the kernels: sweep every 384 M k-mers (tunable:
@@ -306,6 +335,11 @@ int vg_ctx_destroy(vg_ctx* c) {
         cudaEventDestroy(s.copied);
         cudaEventDestroy(s.done);
     }
+    cudaFree(c->d_masked);
+    cudaFree(c->fq.tile_count);
+    cudaFree(c->fq.tile_base);
+    cudaFree(c->fq.nlpos);
+    cudaFree(c->fq.blk);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_compute_stream);
     delete c;

@@ -182,6 +182,8 @@ __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) { return (1u <
 struct Chunk {
     const uint8_t* al;
     int64_t lo, hi;
+    const unsigned int* skip;  // optional device flag: non-zero = do not count this chunk (a FASTQ block that
+                               // failed the on-device format check; the host re-parses it with kseq semantics)
 };
 
 struct KmerParams {

@@ -63,6 +63,8 @@ struct vg_ctx {
     cudaStream_t own_compute_stream = nullptr;
     std::vector<vg::StageSlot> ring;
     int next_slot = 0;
+    uint8_t* d_masked = nullptr;         // on-device FASTQ parsing: a block with only its sequence lines left
+    vg::FastqScratch fq{};
     bool has_l2_window = false;          // L2 persisting window over the presence pre-filter
     cudaAccessPolicyWindow l2_window{};
 };
@@ -116,6 +118,7 @@ struct vg_index {
     vg::DeviceMisc* d_misc = nullptr;
     uint64_t duplicates = 0;
     uint64_t launches = 0;
+    uint64_t fastq_blocks = 0;     // raw FASTQ blocks parsed, checked and counted on the device so far
     bool counting = false;
     bool foreign_streams = false;
 };
@@ -132,6 +135,9 @@ namespace vg {
 void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
 int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier
 int sharded_end(vg_index* ix, uint8_t* c_out);        // vg_comm.cpp: extract own keys, combine over NVLink
-int enqueue_piece(vg_index* ix, int slot, const char* src, uint64_t len);
+int enqueue_piece(vg_index* ix, int slot, const char* src, uint64_t len, const unsigned int* d_skip = nullptr);
+// raw four-line FASTQ text in ring slot `slot`'s pinned buffer: copy, parse and check on the device, count
+int enqueue_raw_piece(vg_index* ix, int slot, uint64_t len, FastqFileState* d_file, uint32_t block_no);
+int ctx_ensure_fastq(vg_ctx* c);
 int count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
 }  // namespace vg

@@ -64,6 +64,30 @@ struct PartView {
 };
 constexpr uint32_t kMaxPartitions = 1024;
 
+// On-device FASTQ parsing: per-file and per-block state (device memory) and the scratch of one context.
+struct FastqFileState {
+    unsigned int bad;               // a block failed the four-line check: it and every later block are not counted
+    unsigned int first_bad_block;
+    unsigned int blocks_ok;
+    unsigned int pad;
+    unsigned long long read_bases;  // sum of seq.l over the counted blocks (mReadBase)
+};
+struct FastqBlockState {
+    unsigned int nlines, bad;
+    unsigned long long read_bases;
+};
+struct FastqScratch {
+    uint32_t* tile_count;           // newlines per 4 KiB tile
+    uint32_t* tile_base;            // lines that start before each tile
+    uint32_t* nlpos;                // block offset of the newline that ends each line
+    FastqBlockState* blk;
+    uint32_t max_tiles, max_lines;
+};
+// raw block (record-aligned four-line FASTQ text, 16-byte aligned, len < 2^32) -> d_masked (only the sequence
+// lines survive, everything else is '\n'), the format check and the per-file bookkeeping; all on stream s.
+cudaError_t launch_fastq_block(const uint8_t* d_raw, uint32_t len, uint8_t* d_masked, const FastqScratch& sc,
+                               FastqFileState* d_file, uint32_t block_no, cudaStream_t s);
+
 struct CbfView {
     uint8_t* cells;                 // m saturating u8 counters
     uint64_t m;
@@ -85,13 +109,14 @@ cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t
 cudaError_t launch_select_owned(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint64_t first_idx,
                                 uint64_t* d_own, uint64_t* d_own_idx, unsigned long long* d_n_own, cudaStream_t s);
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);
+// d_skip (optional): device flag, non-zero = count nothing (see Chunk::skip)
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
-                         int ctas_per_sm, int nsm, cudaStream_t s);
+                         int ctas_per_sm, int nsm, cudaStream_t s, const unsigned int* d_skip = nullptr);
 // Scatter the k-mers ending in tiles [first_tile, first_tile + ntiles) of the chunk (d_bases, nbytes)
 // into the partition buffers; launch_probe_partitions then probes every partition and resets them.
 cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
                            uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
-                           cudaStream_t s);
+                           cudaStream_t s, const unsigned int* d_skip = nullptr);
 cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, cudaStream_t s);
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s);

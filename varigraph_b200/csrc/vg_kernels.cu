@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
 count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
     __shared__ uint8_t lut[256];
     __shared__ unsigned long long blk[2];
+    if (c.skip && *c.skip) return;
     lut_init(lut);
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
     __syncthreads();
@@ -382,6 +383,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     uint8_t* lut = reinterpret_cast<uint8_t*>(fit_s + P);
     __shared__ unsigned long long blk_pos;
     __shared__ uint32_t max_cnt;
+    if (c.skip && *c.skip) return;
     lut_init(lut);
     if (threadIdx.x == 0) blk_pos = 0, max_cnt = 0;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
@@ -866,15 +868,179 @@ __global__ void __launch_bounds__(kCtaThreads) random_sector_kernel(const uint64
 }
 
 // ---------------------------------------------------------------------------
+// on-device FASTQ parsing: the host ships raw text of plain four-line FASTQ, cut at
+// record boundaries; these kernels find the lines, check EVERY record against what kseq would accept
+// as a four-line record (include/kseq.h:192-232), blank everything but the sequence lines and sum
+// seq.l (mReadBase, src/fastq_kmer.cpp:105).  A block that fails the check is not counted (Chunk::skip),
+// nor is any later block of its file: the host re-parses from there with the kseq reader, so the result
+// is the reference's for any input.
+// ---------------------------------------------------------------------------
+// bit j of the result: byte j of the 16-byte segment at `off` is '\n' (bytes at or beyond len: never)
+__device__ __forceinline__ uint32_t seg_newlines(const uint8_t* raw, uint32_t off, uint32_t len, uint4& w) {
+    w = make_uint4(0, 0, 0, 0);
+    if (off >= len) return 0;
+    w = *reinterpret_cast<const uint4*>(raw + off);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        m |= ((((__vcmpeq4(ws[i], 0x0a0a0a0au) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+    if (len - off < 16) m &= (1u << (len - off)) - 1u;
+    return m;
+}
+
+// exclusive prefix sum over the CTA's threads (blockDim.x == kCtaThreads); total in `total`
+__device__ __forceinline__ uint32_t cta_exclusive_sum(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kCtaThreads / 32; ++i) {
+        const uint32_t ws = warp_sums[i];
+        if ((uint32_t)i < warp) before += ws;
+        all += ws;
+    }
+    total = all;
+    __syncthreads();
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(kCtaThreads) fastq_count_lines_kernel(const uint8_t* raw, uint32_t len, uint32_t* tile_count) {
+    __shared__ uint32_t ws[kCtaThreads / 32];
+    uint4 w;
+    const uint32_t m = seg_newlines(raw, blockIdx.x * kTileBytes + threadIdx.x * kSegBytes, len, w);
+    uint32_t total;
+    cta_exclusive_sum(__popc(m), ws, total);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+}
+
+// One CTA: tile_base[t] = lines that start before tile t; blk = {lines in the block, bad flag, read bases} reset.
+__global__ void __launch_bounds__(1024) fastq_scan_tiles_kernel(const uint32_t* tile_count, uint32_t ntiles, uint32_t* tile_base,
+                                                              uint32_t max_lines, FastqBlockState* blk) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (ntiles + 1023) / 1024, t0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per && t0 + i < ntiles; ++i) sum += tile_count[t0 + i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const uint32_t v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        blk->nlines = run;
+        blk->bad = run > max_lines ? 1u : 0u;  // more lines than nlpos holds: not FASTQ as we know it
+        blk->read_bases = 0;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t i = 0; i < per && t0 + i < ntiles; ++i) {
+        tile_base[t0 + i] = run;
+        run += tile_count[t0 + i];
+    }
+}
+
+// masked[i] = raw[i] on sequence lines (line index % 4 == 1), '\n' elsewhere; nlpos[line] = where it ends.
+__global__ void __launch_bounds__(kCtaThreads) fastq_mask_kernel(const uint8_t* raw, uint32_t len, const uint32_t* tile_base,
+                                                               uint8_t* masked, uint32_t* nlpos, uint32_t max_lines,
+                                                               FastqBlockState* blk) {
+    __shared__ uint32_t ws[kCtaThreads / 32];
+    const uint32_t off = blockIdx.x * kTileBytes + threadIdx.x * kSegBytes;
+    uint4 w;
+    const uint32_t m = seg_newlines(raw, off, len, w);
+    uint32_t total;
+    uint32_t line = tile_base[blockIdx.x] + cta_exclusive_sum(__popc(m), ws, total);
+    const uint32_t in[4] = {w.x, w.y, w.z, w.w};
+    uint32_t out[4];
+    bool nul = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 4 * i + j;
+            const uint32_t ch = (in[i] >> (8 * j)) & 0xffu;
+            const bool live = off + b < len;
+            nul |= live && ch == 0;
+            o |= ((live && (line & 3u) == 1u) ? ch : (uint32_t)'\n') << (8 * j);
+            if ((m >> b) & 1u) {
+                if (line < max_lines) nlpos[line] = off + b;
+                ++line;
+            }
+        }
+        out[i] = o;
+    }
+    *reinterpret_cast<uint4*>(masked + off) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (nul) atomicOr(&blk->bad, 1u);  // the reference cuts a sequence at a NUL byte: leave that to the host parser
+}
+
+// One thread per line: is every record what kseq reads as header / sequence / '+' / quality of equal length?
+__global__ void fastq_validate_kernel(const uint8_t* raw, const uint32_t* nlpos, uint32_t max_lines, FastqBlockState* blk) {
+    const uint32_t nlines = blk->nlines;
+    if (nlines > max_lines) return;  // already marked bad
+    uint32_t bases = 0;
+    bool bad = false;
+    const uint32_t L = blockIdx.x * blockDim.x + threadIdx.x;
+    if (L < nlines) {
+        auto line_len = [&](uint32_t l, uint32_t& start) {  // kseq's getline: one trailing CR goes, unless the line is just "\r"
+            const uint32_t p = nlpos[l];
+            start = l ? nlpos[l - 1] + 1 : 0;
+            const uint32_t n = p - start;
+            return (n > 1 && raw[p - 1] == '\r') ? n - 1 : n;
+        };
+        uint32_t s;
+        const uint32_t n = line_len(L, s);
+        const uint32_t raw_n = nlpos[L] - s;
+        const uint8_t c0 = raw_n ? raw[s] : 0;
+        switch (L & 3u) {
+            case 0: bad = c0 != '@'; break;
+            case 1: bad = raw_n && (c0 == '@' || c0 == '+' || c0 == '>'); bases = n; break;
+            case 2: bad = c0 != '+'; break;
+            default: {
+                uint32_t s2;
+                bad = n != line_len(L - 2, s2);
+            }
+        }
+    }
+    if (L == 0 && (nlines & 3u)) bad = true;  // the block does not end on a record boundary
+    if (__any_sync(kFullMask, bad) && (threadIdx.x & 31) == 0) atomicOr(&blk->bad, 1u);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bases += __shfl_xor_sync(kFullMask, bases, d);
+    if ((threadIdx.x & 31) == 0 && bases) atomicAdd(&blk->read_bases, (unsigned long long)bases);
+}
+
+__global__ void fastq_commit_kernel(const FastqBlockState* blk, FastqFileState* file, uint32_t block_no) {
+    if (blk->bad || file->bad) {
+        if (!file->bad) {
+            file->bad = 1;
+            file->first_bad_block = block_no;
+        }
+    } else {
+        file->read_bases += blk->read_bases;
+        file->blocks_ok += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-static inline Chunk make_chunk(const uint8_t* p, uint64_t nbytes) {
+static inline Chunk make_chunk(const uint8_t* p, uint64_t nbytes, const unsigned int* skip = nullptr) {
     uintptr_t a = (uintptr_t)p;
     uintptr_t al = a & ~(uintptr_t)15;
     Chunk c;
     c.al = (const uint8_t*)al;
     c.lo = (int64_t)(a - al);
     c.hi = c.lo + (int64_t)nbytes;
+    c.skip = skip;
     return c;
 }
 static inline int64_t tiles_for(const Chunk& c) { return (c.hi + kTileBytes - 1) / kTileBytes; }
@@ -951,9 +1117,9 @@ cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s) {
 }
 
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
-                         int ctas_per_sm, int nsm, cudaStream_t s) {
+                         int ctas_per_sm, int nsm, cudaStream_t s, const unsigned int* d_skip) {
     if (nbytes == 0) return cudaSuccess;
-    Chunk c = make_chunk(d_bases, nbytes);
+    Chunk c = make_chunk(d_bases, nbytes, d_skip);
     int64_t ntiles = tiles_for(c);
     // persistent grid: exactly the CTAs that are resident at once, each striding over the tiles
     using KernelT = void (*)(IndexView, Chunk, int64_t, CountStats*);
@@ -981,9 +1147,9 @@ cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint6
 
 cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
                            uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
-                           cudaStream_t s) {
+                           cudaStream_t s, const unsigned int* d_skip) {
     if (ntiles <= 0) return cudaSuccess;
-    Chunk c = make_chunk(d_bases, nbytes);
+    Chunk c = make_chunk(d_bases, nbytes, d_skip);
     using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
     KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true> : (KernelT)scatter_kernel<false>;
     // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
@@ -1081,6 +1247,21 @@ cudaError_t launch_histogram(const uint8_t* d_counts, const uint8_t* d_flags, ui
     cudaError_t e = cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s);
     if (e != cudaSuccess || n == 0) return e;
     histogram_kernel<<<grid_1d(n, 256, 148 * 8), 256, 0, s>>>(d_counts, d_flags, n, d_hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fastq_block(const uint8_t* d_raw, uint32_t len, uint8_t* d_masked, const FastqScratch& sc,
+                               FastqFileState* d_file, uint32_t block_no, cudaStream_t s) {
+    if (len == 0) return cudaSuccess;
+    const uint32_t ntiles = (len + kTileBytes - 1) / kTileBytes;
+    if (ntiles > sc.max_tiles) return cudaErrorInvalidValue;
+    fastq_count_lines_kernel<<<ntiles, kCtaThreads, 0, s>>>(d_raw, len, sc.tile_count);
+    fastq_scan_tiles_kernel<<<1, 1024, 0, s>>>(sc.tile_count, ntiles, sc.tile_base, sc.max_lines, sc.blk);
+    fastq_mask_kernel<<<ntiles, kCtaThreads, 0, s>>>(d_raw, len, sc.tile_base, d_masked, sc.nlpos, sc.max_lines, sc.blk);
+    // one thread per possible line; the kernel reads the true number from blk
+    const uint32_t lines_cap = len < sc.max_lines ? len : sc.max_lines;
+    fastq_validate_kernel<<<(lines_cap + 255) / 256, 256, 0, s>>>(d_raw, sc.nlpos, sc.max_lines, sc.blk);
+    fastq_commit_kernel<<<1, 1, 0, s>>>(sc.blk, d_file, block_no);
     return cudaGetLastError();
 }
 
