@@ -374,7 +374,7 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, const std::vect
                const std::vector<RawItem>& items, vg::FastqFileState* d_files, int threads, uint64_t* read_bases) {
     vg_ctx* ctx = ix->ctx;
     int nk = std::min<int>(threads, (int)kseqs.size());
-    int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, 8), (int)items.size()));
+    int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, 16), (int)items.size()));
     const int nworkers = nk + nr;
     if (nworkers == 0) return VG_OK;
     const int nslots = std::max(3, nworkers + 2);
