@@ -327,7 +327,7 @@ def main() -> None:
     ap.add_argument("--index", default="replicated", choices=["replicated", "sharded"],
                     help="N > 1: a replica of the index per GPU (default) or one index cut over the GPUs")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N > 1, replicated: how counts are combined")
-    ap.add_argument("--round-mb", type=int, default=512, help="sharded index: bases per rank and round")
+    ap.add_argument("--round-mb", type=int, default=1024, help="sharded index: bases per rank and round")
     a = ap.parse_args()
     global K
     K = a.kmer

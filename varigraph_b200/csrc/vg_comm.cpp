@@ -416,7 +416,7 @@ int vg::sharded_flush(vg_index* ix, cudaStream_t s) {
         int rc = barrier_on(cm, s);
         if (rc) return rc;
         CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
-        ix->launches += (uint64_t)ps.view.P_local * cm->world + 2;
+        ix->launches += (uint64_t)ps.view.P_local + 2;
         rc = barrier_on(cm, s);
         if (rc) return rc;
     } else {  // a group of one: the key lists and cursors are local

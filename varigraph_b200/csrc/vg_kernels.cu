@@ -601,12 +601,13 @@ __device__ __forceinline__ void retire_slice(const IndexView& ix, uint32_t b0, u
 
 // One step of the partition sweep: retire the previous slice [r0, r1) (its side counters are in
 // ctr_prev), pull slice [b0, b1) into L2 with sequential prefetches, then probe the slice's key
-// list into ctr_cur.  Either part may be empty.
-template <int kBatch>
+// list into ctr_cur.  Either part may be empty.  kMulti (sharded index): the slice has `nsub` key lists, one
+// per source GPU, `cap` keys apart, their fill counts `count_stride` apart.
+template <int kBatch, bool kMulti>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
-probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsigned long long* count_ptr, uint64_t cap,
-                   uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0, uint32_t r1, uint32_t* ctr_prev,
-                   CountStats* stats) {
+probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ lists, const unsigned long long* count_ptr, uint32_t nsub,
+                   uint32_t count_stride, uint64_t cap, uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0,
+                   uint32_t r1, uint32_t* ctr_prev, CountStats* stats) {
     __shared__ unsigned long long blk_hit;
     if (threadIdx.x == 0) blk_hit = 0;
     {
@@ -618,12 +619,15 @@ probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsign
     }
     if (r1 > r0) retire_slice(ix, r0, r1, ctr_prev);
     __syncthreads();
-    const uint64_t n = b1 > b0 ? min((uint64_t)*count_ptr, cap) : 0;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp_gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     constexpr uint64_t kPerWarp = 32ull * kBatch;
     uint32_t n_hit = 0;
+#pragma unroll 1
+    for (uint32_t sub = 0; sub < (kMulti ? nsub : 1u); ++sub) {
+    const uint64_t* list = kMulti ? lists + (uint64_t)sub * cap : lists;
+    const uint64_t n = b1 > b0 ? min((uint64_t)count_ptr[kMulti ? (size_t)sub * count_stride : 0], cap) : 0;
     uint64_t keys[kBatch], next[kBatch];
     auto fetch = [&](uint64_t base, uint64_t (&dst)[kBatch]) {
         uint32_t e = 0;
@@ -648,6 +652,7 @@ probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ list, const unsign
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) keys[b] = next[b];
         emit = nemit;
+    }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_hit += __shfl_xor_sync(kFullMask, n_hit, d);
@@ -1206,7 +1211,12 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
     const bool sharded = pv.world > 1;
     const uint32_t nsub = sharded ? pv.world : 1u;
     // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice.
-    // A sharded index has one key list per source GPU and slice: one launch each, the first also retires.
+    // A sharded index has one key list per source GPU and slice: the kMulti kernel walks them all.
+    auto launch = [&](auto kern, const uint64_t* lists, const unsigned long long* cnt, uint32_t b0, uint32_t b1,
+                      uint32_t* cur, uint32_t r0, uint32_t r1, uint32_t* prv) {
+        if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
+        kern<<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, lists, cnt, nsub, pv.P_local, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+    };
     for (uint32_t p = 0; p <= pv.P_local; ++p) {
         uint32_t b0 = 0, b1 = 0, r0 = 0, r1 = 0;
         if (p < pv.P_local) slice(p, b0, b1);
@@ -1214,17 +1224,14 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
         uint32_t* cur = pv.ctr + (size_t)(p & 1) * ctr_elems;
         uint32_t* prv = pv.ctr + (size_t)((p + 1) & 1) * ctr_elems;
         const uint32_t q = p < pv.P_local ? p : 0;
-        for (uint32_t sub = 0; sub < (p < pv.P_local ? nsub : 1u); ++sub) {
-            const uint64_t* list = pv.keybuf + ((uint64_t)q * nsub + sub) * pv.cap;
-            const unsigned long long* cnt = sharded ? pv.incount + (size_t)sub * pv.P_local + q : pv.cursor + q;
-            if (sub) r0 = r1 = 0;
-            if (b4) {
-                if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<4>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-                probe_slice_kernel<4><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
-            } else {
-                if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_slice_kernel<8>, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-                probe_slice_kernel<8><<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, list, cnt, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
-            }
+        const uint64_t* lists = pv.keybuf + (uint64_t)q * nsub * pv.cap;
+        const unsigned long long* cnt = (sharded ? pv.incount : pv.cursor) + q;
+        if (sharded) {
+            if (b4) launch(probe_slice_kernel<4, true>, lists, cnt, b0, b1, cur, r0, r1, prv);
+            else launch(probe_slice_kernel<8, true>, lists, cnt, b0, b1, cur, r0, r1, prv);
+        } else {
+            if (b4) launch(probe_slice_kernel<4, false>, lists, cnt, b0, b1, cur, r0, r1, prv);
+            else launch(probe_slice_kernel<8, false>, lists, cnt, b0, b1, cur, r0, r1, prv);
         }
     }
     cudaError_t e = cudaGetLastError();
