@@ -1,11 +1,10 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-run() { python bench.py --no-cpu-baseline --steps 10 --warmup 3 2>/dev/null | python -c "
+run() { python bench.py --no-cpu-baseline --steps 10 --warmup 3 "$@" 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value %.4g e2e %.4g ms %.2f pass_ms %.2f P=%d eq=%s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['config']['table_partitions'],d['e2e']['counts_equal_device_path']))"; }
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 echo "== default"; run
-echo "== filter 5 bits"; VG_PREFILTER_BYTES=36942558 run
-echo "== filter 6 bits"; VG_PREFILTER_BYTES=44331070 run
-echo "== filter 8 bits"; VG_PREFILTER_BYTES=59108094 run
+echo "== default again"; run
+echo "== k=28"; run --kmer 28

@@ -373,14 +373,13 @@ template <bool kOdd>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(16) uint64_t smem_bins[];  // indexed directly: STS / LDS with the base folded in
     const uint32_t P = pv.P, cap = cfg.cap;
-    uint64_t* bins = reinterpret_cast<uint64_t*>(smem_raw);
-    unsigned long long* base_s = reinterpret_cast<unsigned long long*>(bins + (size_t)P * cfg.stride);
+    unsigned long long* base_s = reinterpret_cast<unsigned long long*>(smem_bins + (size_t)P * cfg.stride);
     uint32_t* hist = reinterpret_cast<uint32_t*>(base_s + P);
     uint32_t* cnt_s = hist + P;
     uint32_t* fit_s = cnt_s + P;
-    uint8_t* lut = reinterpret_cast<uint8_t*>(fit_s + P);
+    __shared__ uint8_t lut[256];  // static: its address is a constant, one add less per base looked up
     __shared__ unsigned long long blk_pos;
     __shared__ uint32_t max_cnt;
     if (c.skip && *c.skip) return;
@@ -390,7 +389,13 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     __syncthreads();
     KmerParams kp{ix.k, ix.mask};
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);  // 32-bit shared-memory address
+    // 32-bit shared-window address of the bins, made opaque: left to itself the compiler re-derives it
+    // (S2UR SR_CgaCtaId + three uniform ops) in front of every single bin store
+    uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(smem_bins);
+    asm volatile("" : "+r"(bins_s));
+    uint32_t stride = cfg.stride;  // likewise: otherwise a constant-bank load sits between every rank and its store
+    asm volatile("" : "+r"(stride));
+    const uint32_t base_a = bins_s + ((P * stride) << 3);  // base_s[], same address space, same reason
     uint32_t n_pos = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
@@ -423,7 +428,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                 if ((emit >> j) & 1u) {
                     const uint32_t p = ps[j];
                     const uint32_t r = atomicAdd(&hist[p], 1u);
-                    if (r < cap) st_shared_u64(bins_s + ((p * cfg.stride + r) << 3), keys[j]);
+                    if (r < cap) st_shared_u64(bins_s + ((p * stride + r) << 3), keys[j]);
                     else over |= 1u << j;
                 }
             }
@@ -477,8 +482,8 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
         for (uint32_t q = threadIdx.x; q < nslots; q += blockDim.x) {
             const uint32_t p = __umulhi(q, magic), i = q - p * row;
             if (i < cnt_s[p]) {
-                const uint64_t key = ld_shared_u64(bins_s + ((p * cfg.stride + i) << 3));
-                if (i < fit_s[p]) reinterpret_cast<uint64_t*>(base_s[p])[i] = key;
+                const uint64_t key = ld_shared_u64(bins_s + ((p * stride + i) << 3));
+                if (i < fit_s[p]) reinterpret_cast<uint64_t*>(ld_shared_u64(base_a + (p << 3)))[i] = key;
                 else probe_one_direct(ix, pv, key, stats);  // slice list full (a very skewed round): still exact
             }
         }
@@ -1165,7 +1170,7 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     static const size_t budget = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52) * 1024; }();
     const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
     const uint32_t want = (uint32_t)(expect * capx) + 8;
-    auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 256; };
+    auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 16; };
     static bool magic_on[64] = {};  // constant memory is per device
     int dev = 0;
     cudaGetDevice(&dev);
