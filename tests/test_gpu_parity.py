@@ -414,6 +414,32 @@ def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, t
     ix.close()
 
 
+def test_count_files_raw_fastq_long_records_go_to_kseq(ctx, vglib, oracle, tmp_path):
+    """Records longer than the boundary-search window cannot be cut into raw blocks: the first block goes to
+    the device, the rest of the file to the kseq reader from the last boundary on; same result."""
+    t = helpers.tiny()
+    g = t["genome"]
+    rng = random.Random(3)
+    recs = _fastq_text(rng, g, 9000)                      # ~1.5 MB of short records first
+    longs = []
+    for i in range(6):                                      # then 160 kb reads: > half the 256 KiB window
+        seq = np.concatenate([g[rng.randint(0, g.size - 40_000):][:40_000] for _ in range(4)]).tobytes()
+        longs.append(b"@long%d\n" % i + seq + b"\n+\n" + b"I" * len(seq) + b"\n")
+    data = b"".join(recs) + b"".join(longs) + b"".join(recs[:50])
+    p = tmp_path / "long.fq"
+    p.write_bytes(data)
+    lines, nreads, bases, status = oracle.fastq_to_lines(data)
+    want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    before = ix.fastq_blocks
+    ix.begin()
+    rb = ix.count_files([str(p)], threads=4)
+    counts, pos, hits = ix.end()
+    assert ix.fastq_blocks - before >= 1
+    assert rb == bases and (pos, hits) == (wpos, whits) and np.array_equal(counts, want)
+    ix.close()
+
+
 def test_count_files_vs_reference_live(ctx, vglib, reference, tmp_path):
     """Same graph.bin, same FASTQ files: reference CPU path vs CUDA path, per k-mer."""
     t = helpers.tiny()

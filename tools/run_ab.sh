@@ -4,6 +4,6 @@ run() { python bench.py --no-cpu-baseline --steps 10 --warmup 3 "$@" 2>/dev/null
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value %.4g e2e %.4g ms %.2f pass_ms %.2f P=%d eq=%s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['config']['table_partitions'],d['e2e']['counts_equal_device_path']))"; }
-echo "== no prefilter"; VG_PREFILTER=0 run
-echo "== P=94 (16 MB slices)"; VG_SLICE_BYTES=16777216 run
-echo "== filter 6 bits"; VG_PREFILTER_BYTES=44331070 run
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+echo "== default"; run
+echo "== default again"; run

@@ -34,8 +34,19 @@ __device__ __forceinline__ uint8_t nt4_entry(uint32_t b) {
     return (uint8_t)(code | (valid << 2) | (nl << 3));
 }
 
+// Shared-memory tables of a CTA: lut[0..255] the byte table above, then four 16-bit tables, one per byte
+// position j of a 32-bit word of text (j = 0 is the first base): code << 2(3-j) | valid << (8 + 3-j).  OR-ing
+// the four lookups of a word yields its four 2-bit codes (first base highest) in bits 0-7 and its four
+// validity bits in bits 8-11, already in place -- no per-base shifting.
+constexpr int kLutBytes = 256 + 4 * 256 * 2;
 __device__ __forceinline__ void lut_init(uint8_t* lut) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = nt4_entry((uint32_t)i);
+    uint16_t* w4 = reinterpret_cast<uint16_t*>(lut + 256);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t e = nt4_entry((uint32_t)i);
+        lut[i] = (uint8_t)e;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w4[j * 256 + i] = (uint16_t)(((e & 3u) << (2 * (3 - j))) | (((e >> 2) & 1u) << (8 + 3 - j)));
+    }
     __syncthreads();
 }
 
@@ -155,9 +166,10 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
     return r;
 }
 
-// Home bucket of a key (a canonical k-mer, i.e. structured input: fold the high half down before the
-// Fibonacci multiply, take the product's high word, range-reduce without a division).
-__device__ __forceinline__ uint64_t key_mix(uint64_t key56) { return (key56 ^ (key56 >> 29)) * 0x9E3779B97F4A7C15ULL; }
+// Home bucket of a key (a canonical k-mer): high word of the Fibonacci product, range-reduced without a division.
+// Fibonacci multiply: the product's high word (bucket, filter word) depends on every bit of the k-mer, the top
+// of its low word (filter bits) on the 16 most recent bases.
+__device__ __forceinline__ uint64_t key_mix(uint64_t key56) { return key56 * 0x9E3779B97F4A7C15ULL; }
 __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets) {
     return __umulhi((uint32_t)(key_mix(key56) >> 32), nbuckets);
 }
@@ -174,7 +186,11 @@ __device__ __forceinline__ void prefilter_slot_mixed(uint64_t mixed, uint32_t nw
 __device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& bits) {
     prefilter_slot_mixed(key_mix(key56), nwords, word, bits);
 }
-__device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) { return (1u << (bits & 31u)) | (1u << (bits >> 5)); }
+// two bits of the word: position s = bits & 31 and s + d (mod 32), d = bits >> 5 (d == 0: just one)
+__device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
+    const uint32_t pair = 1u | (1u << (bits >> 5));
+    return __funnelshift_l(pair, pair, bits & 31u);
+}
 
 // ---- the view of a staged chunk --------------------------------------------
 // `al` is the 16-byte aligned-down base; live bytes are [lo, hi) relative to it.
@@ -200,14 +216,14 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, int64_t off, const ui
     if (off + kSegBytes <= c.lo || off >= c.hi || off < 0) return;
     uint4 w = ld_stream16(c.al + off);
     uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t e = lut[(ws[i] >> (8 * j)) & 0xffu];
-            packed = (packed << 2) | (e & 3u);
-            vmask = (vmask << 1) | ((e >> 2) & 1u);
-        }
+        const uint32_t t = ws[i];
+        const uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] |
+                           w4[768 + (t >> 24)];
+        packed = (packed << 8) | (v & 0xffu);
+        vmask = (vmask << 4) | (v >> 8);
     }
     if (off < c.lo || off + kSegBytes > c.hi) {
         uint32_t keep = 0;

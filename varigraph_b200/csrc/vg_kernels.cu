@@ -221,7 +221,7 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
 template <bool kOdd, int kBatch>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
 count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
-    __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ unsigned long long blk[2];
     if (c.skip && *c.skip) return;
     lut_init(lut);
@@ -379,7 +379,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     uint32_t* hist = reinterpret_cast<uint32_t*>(base_s + P);
     uint32_t* cnt_s = hist + P;
     uint32_t* fit_s = cnt_s + P;
-    __shared__ uint8_t lut[256];  // static: its address is a constant, one add less per base looked up
+    __shared__ __align__(16) uint8_t lut[kLutBytes];  // static: its address is a constant, one add less per base looked up
     __shared__ unsigned long long blk_pos;
     __shared__ uint32_t max_cnt;
     if (c.skip && *c.skip) return;
@@ -784,7 +784,7 @@ __global__ void histogram_kernel(const uint8_t* __restrict__ counts, const uint8
 // ---------------------------------------------------------------------------
 template <bool kOdd>
 __global__ void __launch_bounds__(kCtaThreads) positions_kernel(KmerParams kp, Chunk c, int64_t ntiles, uint64_t* out) {
-    __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
     lut_init(lut);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = t * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
@@ -817,7 +817,7 @@ __device__ __forceinline__ void cell_sat_inc(uint8_t* cells, uint64_t pos) {
 template <bool kOdd>
 __global__ void __launch_bounds__(kCtaThreads) cbf_add_kernel(CbfView cbf, KmerParams kp, Chunk c, int64_t first_tile,
                                                             int64_t ntiles, unsigned long long* added) {
-    __shared__ uint8_t lut[256];
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
     lut_init(lut);
     FastMod64 fm{cbf.magic_hi, cbf.magic_lo, cbf.m};
     uint32_t n = 0;
