@@ -125,7 +125,7 @@ static int part_setup(vg_index* ix) {
     // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
     // the streaming traffic; larger indexes go without.  VG_PREFILTER=0 disables it.
     const char* pe = getenv("VG_PREFILTER");
-    if (!(pe && atoi(pe) == 0) && ix->n > 0) {
+    if (!(pe && atoi(pe) == 0) && ix->n > 0 && ix->view.k >= 2) {  // keyed by (k-1)-mers
         uint64_t bytes = 0;
         if (ix->n / 2 <= (64ull << 20)) bytes = ix->n / 2;
         if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
@@ -133,7 +133,7 @@ static int part_setup(vg_index* ix) {
             const uint32_t nwords = (uint32_t)std::min<uint64_t>(bytes / 4, 0x7fffffffull);
             if (cudaMalloc((void**)&ps.d_filter, (size_t)nwords * 4) == cudaSuccess) {
                 CU(cudaMemsetAsync(ps.d_filter, 0, (size_t)nwords * 4, c->compute_stream));
-                CU(vg::launch_prefilter_build(ps.d_filter, nwords, ix->d_key56, ix->n, c->compute_stream));
+                CU(vg::launch_prefilter_build(ps.d_filter, nwords, ix->d_key56, ix->n, ix->view.k, c->compute_stream));
                 CU(cudaStreamSynchronize(c->compute_stream));
                 ps.filter.words = ps.d_filter;
                 ps.filter.nwords = nwords;

@@ -192,6 +192,16 @@ __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
     return __funnelshift_l(pair, pair, bits & 31u);
 }
 
+// The presence pre-filter is keyed by canonical (k-1)-mers: the prefix and the suffix of every index k-mer.
+// The k-mers ending at read positions i and i+1 share the (k-1)-mer ending at i (suffix of one, prefix of
+// the other), so ONE filter lookup can rule out both.  With fwd / rev the encoder's registers at position
+// i: the suffix of fwd is its low 2(k-1) bits, and its reverse complement is rev without its lowest base.
+// Only the k-1 most recent bases enter, so the value is right whenever either of the two k-mers is emitted.
+__device__ __forceinline__ uint64_t shared_smer(uint64_t fwd, uint64_t rev, uint64_t smask) {
+    const uint64_t a = fwd & smask, b = rev >> 2;
+    return a < b ? a : b;
+}
+
 // ---- the view of a staged chunk --------------------------------------------
 // `al` is the 16-byte aligned-down base; live bytes are [lo, hi) relative to it.
 // Everything outside behaves like '\n'.
@@ -279,9 +289,10 @@ struct OddEncoder {
 
     // Consumes the next N own positions: keys[j] = the canonical k-mer ending there (kHashed: its
     // hash64, i.e. the reference's key >> 8); returns the N-bit emit mask (bit j: the reference encoder
-    // emits; keys[j] is meaningless where it does not).
-    template <int N, bool kHashed = true>
-    __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N]) {
+    // emits; keys[j] is meaningless where it does not).  With kPairs, pairs[q] = the canonical (k-1)-mer
+    // ending at position 2q: the suffix of k-mer 2q and the prefix of k-mer 2q+1 (see shared_smer).
+    template <int N, bool kHashed = true, bool kPairs = false>
+    __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N], uint64_t* pairs = nullptr) {
         const uint32_t top = 2 * (kp.k - 1);
         uint32_t emit = 0;
         if (kp.k >= 17) {  // uniform: 2(k-1) >= 32, so the incoming complement only touches the high word
@@ -295,6 +306,7 @@ struct OddEncoder {
                 rev = ((uint64_t)((rhi >> 2) | ((3u ^ cb) << tsh)) << 32) | __funnelshift_r(rlo, rhi, 2);
                 const uint64_t canon = fwd < rev ? fwd : rev;
                 keys[j] = kHashed ? hash64_wide(canon, mask_hi) : canon;
+                if (kPairs && !(j & 1)) pairs[j >> 1] = shared_smer(fwd, rev, kp.mask >> 2);
                 emit |= ((all_k >> 15) & 1u) << j;
                 all_k <<= 1;
             }
@@ -308,6 +320,7 @@ struct OddEncoder {
             rev = (rev >> 2) | ((3ULL ^ cb) << top);
             const uint64_t canon = fwd < rev ? fwd : rev;
             keys[j] = kHashed ? hash64(canon, kp.mask) : canon;
+            if (kPairs && !(j & 1)) pairs[j >> 1] = shared_smer(fwd, rev, kp.mask >> 2);
             emit |= ((all_k >> 15) & 1u) << j;
             all_k <<= 1;
         }
@@ -357,9 +370,12 @@ __device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, con
     return lut[c.al[pos]];
 }
 
+// pairs (optional, 8 entries): pairs[q] = shared_smer of the registers after byte 2q of the segment -- right
+// whenever the k-mer ending there or the next one is emitted (then the k-1 most recent valid bases are the
+// k-1 bytes ending there).
 template <bool kHashed = true>
 __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
-                                           const uint8_t* lut, uint64_t (&keys)[16]) {
+                                           const uint8_t* lut, uint64_t (&keys)[16], uint64_t* pairs = nullptr) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) keys[j] = 0;
     if (off >= c.hi || off + kSegBytes <= c.lo) return 0;
@@ -409,13 +425,14 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
         if (e & 8u) {  // hard boundary: a new read starts after it
             st.fwd = st.rev = 0;
             st.run = 0;
-            continue;
+        } else {
+            uint64_t key;
+            if (roll_push<kHashed>(st, e, kp, key)) {
+                keys[j] = key;
+                emit |= 1u << j;
+            }
         }
-        uint64_t key;
-        if (roll_push<kHashed>(st, e, kp, key)) {
-            keys[j] = key;
-            emit |= 1u << j;
-        }
+        if (pairs && !(j & 1)) pairs[j >> 1] = shared_smer(st.fwd, st.rev, kp.mask >> 2);
     }
     return emit;
 }

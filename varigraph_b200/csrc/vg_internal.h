@@ -117,7 +117,8 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
 cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
                            uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
                            cudaStream_t s, const unsigned int* d_skip = nullptr);
-cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, cudaStream_t s);
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k,
+                                   cudaStream_t s);
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);

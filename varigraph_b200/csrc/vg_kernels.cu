@@ -338,12 +338,22 @@ __device__ __forceinline__ uint64_t* list_of(const PartView& pv, uint32_t p) {
     return pv.keybuf + (uint64_t)p * pv.cap;
 }
 
-__global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n) {
+// Both (k-1)-mers of every index k-mer, canonical (see shared_smer).
+__global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n,
+                                       uint32_t k) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t w, bits;
-    prefilter_slot(key56[i], nwords, w, bits);
-    atomicOr(words + w, prefilter_mask(bits));
+    const uint64_t key = key56[i];
+    if (key == kKey56Max) return;
+    const uint64_t smask = (1ULL << (2 * (k - 1))) - 1;
+    const uint64_t sub[2] = {key >> 2, key & smask};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint64_t rc = revcomp2k(sub[h], k - 1);
+        uint32_t w, bits;
+        prefilter_slot(sub[h] < rc ? sub[h] : rc, nwords, w, bits);
+        atomicOr(words + w, prefilter_mask(bits));
+    }
 }
 
 __device__ __forceinline__ void st_shared_u64(uint32_t addr, uint64_t v) {
@@ -400,33 +410,26 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         // ---- encode, filter, bin -----------------------------------------------------------------
-        auto bin8 = [&](const uint64_t (&keys)[8], uint32_t emit) {
-            uint32_t ps[8];      // table slice of each key (with the pre-filter: | its filter bits << 10 at first)
-            if (pf.words) {  // L2-resident presence pre-filter: never a false negative
-                uint32_t fw[8];
+        auto bin8 = [&](const uint64_t (&keys)[8], const uint64_t (&pairs)[4], uint32_t emit) {
+            if (pf.words) {  // L2-resident presence pre-filter, one lookup per two positions: never a false negative
+                uint32_t fw[4], fb[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint64_t x = key_mix(keys[j]);  // one product serves the filter and the table slice
-                    uint32_t w, fb;
-                    prefilter_slot_mixed(x, pf.nwords, w, fb);
-                    ps[j] = (__umulhi((uint32_t)(x >> 32), ix.nb_total) >> pv.shift) | (fb << 10);
-                    fw[j] = ((emit >> j) & 1u) ? __ldg(pf.words + w) : 0u;
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w;
+                    prefilter_slot(pairs[q], pf.nwords, w, fb[q]);
+                    fw[q] = ((emit >> (2 * q)) & 3u) ? __ldg(pf.words + w) : 0u;
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t m = prefilter_mask(ps[j] >> 10);
-                    if ((fw[j] & m) != m) emit &= ~(1u << j);
-                    ps[j] &= 1023u;
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t m = prefilter_mask(fb[q]);
+                    if ((fw[q] & m) != m) emit &= ~(3u << (2 * q));
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) ps[j] = bucket_of(keys[j], ix.nb_total) >> pv.shift;
             }
             uint32_t over = 0;   // keys whose bin is full (rare): handled after the hot loop
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if ((emit >> j) & 1u) {
-                    const uint32_t p = ps[j];
+                    const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
                     const uint32_t r = atomicAdd(&hist[p], 1u);
                     if (r < cap) st_shared_u64(bins_s + ((p * stride + r) << 3), keys[j]);
                     else over |= 1u << j;
@@ -439,30 +442,35 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
                         uint64_t* slots;
                         uint32_t b;
                         owner_table(ix, pv, keys[j], slots, b);
-                        scatter_one_global(&pv.cursor[ps[j]], list_of(pv, ps[j]), pv.cap, slots, ix.nbuckets, b, keys[j], stats);
+                        const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
+                        scatter_one_global(&pv.cursor[p], list_of(pv, p), pv.cap, slots, ix.nbuckets, b, keys[j], stats);
                     }
             }
         };
         if (kOdd) {
             OddEncoder enc;
             enc.init(c, off, kp, lut);
-            uint64_t keys[8];
-            uint32_t emit = enc.next<8, false>(kp, keys);
+            uint64_t keys[8], pairs[4];
+            uint32_t emit = enc.next<8, false, true>(kp, keys, pairs);
             n_pos += __popc(emit);
-            bin8(keys, emit);
-            emit = enc.next<8, false>(kp, keys);
+            bin8(keys, pairs, emit);
+            emit = enc.next<8, false, true>(kp, keys, pairs);
             n_pos += __popc(emit);
-            bin8(keys, emit);
+            bin8(keys, pairs, emit);
         } else {
-            uint64_t k16[16], keys[8];
-            const uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16);
+            uint64_t k16[16], p8[8], keys[8], pairs[4];
+            const uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16, p8);
             n_pos += __popc(emit);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[j];
-            bin8(keys, emit & 0xffu);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pairs[q] = p8[q];
+            bin8(keys, pairs, emit & 0xffu);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[8 + j];
-            bin8(keys, emit >> 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pairs[q] = p8[4 + q];
+            bin8(keys, pairs, emit >> 8);
         }
         __syncthreads();
         // ---- copy-out: reserve (one global atomic per slice and tile, all slices at once) ... ----------
@@ -1149,9 +1157,10 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
 
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes) { return tiles_for(make_chunk(d_bases, nbytes)); }
 
-cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, cudaStream_t s) {
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k,
+                                   cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    prefilter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(words, nwords, d_key56, n);
+    prefilter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(words, nwords, d_key56, n, k);
     return cudaGetLastError();
 }
 
