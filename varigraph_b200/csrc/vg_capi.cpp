@@ -125,7 +125,7 @@ static int part_setup(vg_index* ix) {
     // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
     // the streaming traffic; larger indexes go without.  VG_PREFILTER=0 disables it.
     const char* pe = getenv("VG_PREFILTER");
-    if (!(pe && atoi(pe) == 0) && ix->n > 0 && ix->view.k >= 2) {  // keyed by (k-1)-mers
+    if (!(pe && atoi(pe) == 0) && ix->n > 0 && ix->view.k >= 8) {  // keyed by sub-words of the k-mers
         uint64_t bytes = 0;
         if (ix->n / 2 <= (64ull << 20)) bytes = ix->n / 2;
         if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);

@@ -314,7 +314,7 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     // ---- presence pre-filter over ALL keys (every rank filters its own reads before the exchange) ----
     const char* pe = getenv("VG_PREFILTER");
     uint32_t nwords = 0;
-    if (!(pe && atoi(pe) == 0) && n > 0 && k >= 2) {
+    if (!(pe && atoi(pe) == 0) && n > 0 && k >= 8) {
         uint64_t bytes = n / 2 <= (64ull << 20) ? n / 2 : 0;
         if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
         if (bytes >= 64) {

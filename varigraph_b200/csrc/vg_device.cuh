@@ -197,8 +197,13 @@ __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
 // the other), so ONE filter lookup can rule out both.  With fwd / rev the encoder's registers at position
 // i: the suffix of fwd is its low 2(k-1) bits, and its reverse complement is rev without its lowest base.
 // Only the k-1 most recent bases enter, so the value is right whenever either of the two k-mers is emitted.
-__device__ __forceinline__ uint64_t shared_smer(uint64_t fwd, uint64_t rev, uint64_t smask) {
-    const uint64_t a = fwd & smask, b = rev >> 2;
+#ifndef VG_FILTER_SPAN
+#define VG_FILTER_SPAN 4
+#endif
+constexpr int kFilterSpan = VG_FILTER_SPAN;  // read positions one filter lookup speaks for (a power of two <= 8)
+constexpr int kFilterDrop = kFilterSpan - 1;  // the filter's words are (k - kFilterDrop)-mers
+__device__ __forceinline__ uint64_t shared_smer(uint64_t fwd, uint64_t rev, uint64_t kmask) {
+    const uint64_t a = fwd & (kmask >> (2 * kFilterDrop)), b = rev >> (2 * kFilterDrop);
     return a < b ? a : b;
 }
 
@@ -306,7 +311,7 @@ struct OddEncoder {
                 rev = ((uint64_t)((rhi >> 2) | ((3u ^ cb) << tsh)) << 32) | __funnelshift_r(rlo, rhi, 2);
                 const uint64_t canon = fwd < rev ? fwd : rev;
                 keys[j] = kHashed ? hash64_wide(canon, mask_hi) : canon;
-                if (kPairs && !(j & 1)) pairs[j >> 1] = shared_smer(fwd, rev, kp.mask >> 2);
+                if (kPairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(fwd, rev, kp.mask);
                 emit |= ((all_k >> 15) & 1u) << j;
                 all_k <<= 1;
             }
@@ -320,7 +325,7 @@ struct OddEncoder {
             rev = (rev >> 2) | ((3ULL ^ cb) << top);
             const uint64_t canon = fwd < rev ? fwd : rev;
             keys[j] = kHashed ? hash64(canon, kp.mask) : canon;
-            if (kPairs && !(j & 1)) pairs[j >> 1] = shared_smer(fwd, rev, kp.mask >> 2);
+            if (kPairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(fwd, rev, kp.mask);
             emit |= ((all_k >> 15) & 1u) << j;
             all_k <<= 1;
         }
@@ -432,7 +437,7 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
                 emit |= 1u << j;
             }
         }
-        if (pairs && !(j & 1)) pairs[j >> 1] = shared_smer(st.fwd, st.rev, kp.mask >> 2);
+        if (pairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(st.fwd, st.rev, kp.mask);
     }
     return emit;
 }

@@ -338,20 +338,20 @@ __device__ __forceinline__ uint64_t* list_of(const PartView& pv, uint32_t p) {
     return pv.keybuf + (uint64_t)p * pv.cap;
 }
 
-// Both (k-1)-mers of every index k-mer, canonical (see shared_smer).
+// Every (k - kFilterDrop)-mer of every index k-mer, canonical (see shared_smer).
 __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n,
                                        uint32_t k) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t key = key56[i];
     if (key == kKey56Max) return;
-    const uint64_t smask = (1ULL << (2 * (k - 1))) - 1;
-    const uint64_t sub[2] = {key >> 2, key & smask};
+    const uint32_t ks = k - kFilterDrop;
+    const uint64_t smask = (1ULL << (2 * ks)) - 1;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint64_t rc = revcomp2k(sub[h], k - 1);
+    for (int h = 0; h <= kFilterDrop; ++h) {
+        const uint64_t sub = (key >> (2 * h)) & smask, rc = revcomp2k(sub, ks);
         uint32_t w, bits;
-        prefilter_slot(sub[h] < rc ? sub[h] : rc, nwords, w, bits);
+        prefilter_slot(sub < rc ? sub : rc, nwords, w, bits);
         atomicOr(words + w, prefilter_mask(bits));
     }
 }
@@ -410,19 +410,21 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         // ---- encode, filter, bin -----------------------------------------------------------------
-        auto bin8 = [&](const uint64_t (&keys)[8], const uint64_t (&pairs)[4], uint32_t emit) {
-            if (pf.words) {  // L2-resident presence pre-filter, one lookup per two positions: never a false negative
-                uint32_t fw[4], fb[4];
+        constexpr int kGroups = 8 / kFilterSpan;
+        constexpr uint32_t kGroupMask = (1u << kFilterSpan) - 1u;
+        auto bin8 = [&](const uint64_t (&keys)[8], const uint64_t (&pairs)[kGroups], uint32_t emit) {
+            if (pf.words) {  // L2-resident presence pre-filter, one lookup per kFilterSpan positions: never a false negative
+                uint32_t fw[kGroups], fb[kGroups];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kGroups; ++q) {
                     uint32_t w;
                     prefilter_slot(pairs[q], pf.nwords, w, fb[q]);
-                    fw[q] = ((emit >> (2 * q)) & 3u) ? __ldg(pf.words + w) : 0u;
+                    fw[q] = ((emit >> (kFilterSpan * q)) & kGroupMask) ? __ldg(pf.words + w) : 0u;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kGroups; ++q) {
                     const uint32_t m = prefilter_mask(fb[q]);
-                    if ((fw[q] & m) != m) emit &= ~(3u << (2 * q));
+                    if ((fw[q] & m) != m) emit &= ~(kGroupMask << (kFilterSpan * q));
                 }
             }
             uint32_t over = 0;   // keys whose bin is full (rare): handled after the hot loop
@@ -450,7 +452,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
         if (kOdd) {
             OddEncoder enc;
             enc.init(c, off, kp, lut);
-            uint64_t keys[8], pairs[4];
+            uint64_t keys[8], pairs[kGroups];
             uint32_t emit = enc.next<8, false, true>(kp, keys, pairs);
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
@@ -458,18 +460,18 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
         } else {
-            uint64_t k16[16], p8[8], keys[8], pairs[4];
+            uint64_t k16[16], p8[2 * kGroups], keys[8], pairs[kGroups];
             const uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16, p8);
             n_pos += __popc(emit);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pairs[q] = p8[q];
+            for (int q = 0; q < kGroups; ++q) pairs[q] = p8[q];
             bin8(keys, pairs, emit & 0xffu);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[8 + j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pairs[q] = p8[4 + q];
+            for (int q = 0; q < kGroups; ++q) pairs[q] = p8[kGroups + q];
             bin8(keys, pairs, emit >> 8);
         }
         __syncthreads();
