@@ -174,17 +174,13 @@ __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets)
     return __umulhi((uint32_t)(key_mix(key56) >> 32), nbuckets);
 }
 
-// ---- presence pre-filter (word-blocked Bloom, 2 bits per key in one 32-bit word) -------------
-// word: which 32-bit word; bits: the key's two bit positions, packed as lo5 | hi5 << 5.  Both come from
-// the SAME product as the key's bucket (key_mix): the word from its high half (like the bucket -- that
-// correlation is harmless, keys still spread evenly over the words), the bits from the top of its low
-// half, so the scatter pays one 64-bit multiply per k-mer for the filter and the table slice together.
-__device__ __forceinline__ void prefilter_slot_mixed(uint64_t mixed, uint32_t nwords, uint32_t& word, uint32_t& bits) {
+// ---- presence pre-filter (word-blocked Bloom, 2 bits per entry in one 32-bit word) -----------
+// word: which 32-bit word; bits: the entry's two bit positions (see prefilter_mask).  The word comes from the
+// high half of the Fibonacci product, the bits from the top of its low half.
+__device__ __forceinline__ void prefilter_slot(uint64_t entry, uint32_t nwords, uint32_t& word, uint32_t& bits) {
+    const uint64_t mixed = key_mix(entry);
     word = __umulhi((uint32_t)(mixed >> 32), nwords);
     bits = (uint32_t)mixed >> 22;
-}
-__device__ __forceinline__ void prefilter_slot(uint64_t key56, uint32_t nwords, uint32_t& word, uint32_t& bits) {
-    prefilter_slot_mixed(key_mix(key56), nwords, word, bits);
 }
 // two bits of the word: position s = bits & 31 and s + d (mod 32), d = bits >> 5 (d == 0: just one)
 __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
@@ -192,11 +188,12 @@ __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
     return __funnelshift_l(pair, pair, bits & 31u);
 }
 
-// The presence pre-filter is keyed by canonical (k-1)-mers: the prefix and the suffix of every index k-mer.
-// The k-mers ending at read positions i and i+1 share the (k-1)-mer ending at i (suffix of one, prefix of
-// the other), so ONE filter lookup can rule out both.  With fwd / rev the encoder's registers at position
-// i: the suffix of fwd is its low 2(k-1) bits, and its reverse complement is rev without its lowest base.
-// Only the k-1 most recent bases enter, so the value is right whenever either of the two k-mers is emitted.
+// The presence pre-filter is keyed by canonical (k-d)-mers, d = kFilterDrop: every one of the d+1 such words
+// inside every index k-mer.  The k-mers ending at read positions i ... i+d all contain the (k-d)-mer ending
+// at i, so ONE filter lookup can rule out all d+1 of them -- and the scatter kernel is bound by exactly these
+// gathers (one L1TEX wavefront each).  With fwd / rev the encoder's registers at position i: that word is the
+// low 2(k-d) bits of fwd, and its reverse complement is rev without its d lowest bases.  Only the k-d most
+// recent bases enter, so the value is right whenever any of the d+1 k-mers is emitted.
 #ifndef VG_FILTER_SPAN
 #define VG_FILTER_SPAN 4
 #endif
@@ -294,8 +291,8 @@ struct OddEncoder {
 
     // Consumes the next N own positions: keys[j] = the canonical k-mer ending there (kHashed: its
     // hash64, i.e. the reference's key >> 8); returns the N-bit emit mask (bit j: the reference encoder
-    // emits; keys[j] is meaningless where it does not).  With kPairs, pairs[q] = the canonical (k-1)-mer
-    // ending at position 2q: the suffix of k-mer 2q and the prefix of k-mer 2q+1 (see shared_smer).
+    // emits; keys[j] is meaningless where it does not).  With kPairs, pairs[q] = the pre-filter entry that
+    // speaks for positions q * kFilterSpan ... (q + 1) * kFilterSpan - 1 (see shared_smer).
     template <int N, bool kHashed = true, bool kPairs = false>
     __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N], uint64_t* pairs = nullptr) {
         const uint32_t top = 2 * (kp.k - 1);
@@ -375,9 +372,9 @@ __device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, con
     return lut[c.al[pos]];
 }
 
-// pairs (optional, 8 entries): pairs[q] = shared_smer of the registers after byte 2q of the segment -- right
-// whenever the k-mer ending there or the next one is emitted (then the k-1 most recent valid bases are the
-// k-1 bytes ending there).
+// pairs (optional, 16 / kFilterSpan entries): pairs[q] = shared_smer of the registers after byte q * kFilterSpan
+// of the segment -- right whenever one of the kFilterSpan k-mers ending from there on is emitted (then the
+// k - kFilterDrop most recent valid bases are the bytes ending there).
 template <bool kHashed = true>
 __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
                                            const uint8_t* lut, uint64_t (&keys)[16], uint64_t* pairs = nullptr) {
