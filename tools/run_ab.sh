@@ -5,6 +5,6 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value %.4g e2e %.4g ms %.2f pass_ms %.2f P=%d eq=%s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['config']['table_partitions'],d['e2e']['counts_equal_device_path']))"; }
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-echo "== default"; run
-echo "== k=28"; run --kmer 28
-echo "== k=21"; run --kmer 21
+echo "== pairs"; run
+echo "== 256-bit loads"; VG_PROBE_PAIRS=0 run
+echo "== pairs again"; run
