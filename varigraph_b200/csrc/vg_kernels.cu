@@ -523,31 +523,53 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
                                               uint32_t b0, uint32_t b1, uint32_t* ctr, uint32_t& n_hit) {
     uint32_t bk[kBatch], st[kBatch];  // st: bit 31 hit, bit 30 counter already saturated, bits 0-1 slot
     uint32_t pend = 0;                // positions whose search continues in the next bucket
+    // A scattered 256-bit load costs 1.5 L1TEX cycles per lane, a 128-bit one 1.0 (tools/gather_bench.cu), and
+    // at load factor 0.3 most keys sit in the first two slots of their bucket (buckets fill front to back):
+    // look at slots 0-1 first, fetch slots 2-3 only where slot 1 is taken and nothing matched yet.
+    uint32_t more = 0;                // positions that need the second half of their bucket
+    auto half = [&](const uint64_t (&v)[2], uint64_t key, uint32_t first_slot, bool& second_taken) {
+        const uint32_t want_hi = (uint32_t)(key >> 24), want_lo = (uint32_t)(key << 8);
+        const uint32_t d0 = (uint32_t)v[0] ^ want_lo, d1 = (uint32_t)v[1] ^ want_lo;
+        const bool m0 = (uint32_t)(v[0] >> 32) == want_hi && d0 < 256u;
+        const bool m1 = (uint32_t)(v[1] >> 32) == want_hi && d1 < 256u;
+        const uint32_t cnt = m1 ? d1 : d0;  // want_lo's low byte is 0: d == count
+        second_taken = v[1] != kSlotEmpty;
+        return (m0 || m1) ? (0x80000000u | (cnt == 255u ? 0x40000000u : 0u) | (first_slot + (m1 ? 1u : 0u))) : 0u;
+    };
     {
-        uint64_t v[kBatch][4];
+        uint64_t v[kBatch][2];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
             bk[b] = bucket_of(keys[b], ix.nb_total) - ix.b_base;
-            if ((emit >> b) & 1u) ld_bucket(ix.slots + 4ull * bk[b], v[b]);
+            v[b][0] = v[b][1] = kSlotEmpty;
+            if ((emit >> b) & 1u) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ix.slots + 4ull * bk[b]);
+                v[b][0] = t.x;
+                v[b][1] = t.y;
+            }
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            const uint64_t key = keys[b];
-            const bool have = (emit >> b) & 1u;
-            const uint32_t want_hi = (uint32_t)(key >> 24);
-            const uint32_t want_lo = (uint32_t)(key << 8);
-            const uint32_t d0 = (uint32_t)v[b][0] ^ want_lo, d1 = (uint32_t)v[b][1] ^ want_lo;
-            const uint32_t d2 = (uint32_t)v[b][2] ^ want_lo, d3 = (uint32_t)v[b][3] ^ want_lo;
-            const bool m0 = (uint32_t)(v[b][0] >> 32) == want_hi && d0 < 256u;
-            const bool m1 = (uint32_t)(v[b][1] >> 32) == want_hi && d1 < 256u;
-            const bool m2 = (uint32_t)(v[b][2] >> 32) == want_hi && d2 < 256u;
-            const bool m3 = (uint32_t)(v[b][3] >> 32) == want_hi && d3 < 256u;
-            const bool full = v[b][3] != kSlotEmpty;  // buckets fill front to back
-            const bool hit = have && (m0 || m1 || m2 || m3);
-            const uint32_t hs = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
-            const uint32_t cnt = m1 ? d1 : (m2 ? d2 : (m3 ? d3 : d0));  // want_lo's low byte is 0: d == count
-            st[b] = hit ? (0x80000000u | (cnt == 255u ? 0x40000000u : 0u) | hs) : 0u;
-            if (have && !hit && full) pend |= 1u << b;
+            bool taken;
+            st[b] = half(v[b], keys[b], 0u, taken);
+            if (((emit >> b) & 1u) && !st[b] && taken) more |= 1u << b;
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            v[b][0] = v[b][1] = kSlotEmpty;
+            if ((more >> b) & 1u) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ix.slots + 4ull * bk[b] + 2);
+                v[b][0] = t.x;
+                v[b][1] = t.y;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            if ((more >> b) & 1u) {
+                bool full;
+                st[b] = half(v[b], keys[b], 2u, full);
+                if (!st[b] && full) pend |= 1u << b;
+            }
         }
     }
     while (__any_sync(kFullMask, pend != 0)) {
