@@ -641,7 +641,7 @@ __device__ __forceinline__ void retire_slice(const IndexView& ix, uint32_t b0, u
 // list into ctr_cur.  Either part may be empty.  kMulti (sharded index): the slice has `nsub` key lists, one
 // per source GPU, `cap` keys apart, their fill counts `count_stride` apart.
 template <int kBatch, bool kMulti>
-__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
+__global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 4)
 probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ lists, const unsigned long long* count_ptr, uint32_t nsub,
                    uint32_t count_stride, uint64_t cap, uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0,
                    uint32_t r1, uint32_t* ctr_prev, CountStats* stats) {
