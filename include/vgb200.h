@@ -89,6 +89,10 @@ int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threa
  * the host kseq reader, so results never depend on the road taken.  This counts the raw blocks the
  * device accepted so far (diagnostic; VG_RAW_FASTQ=0 disables the raw road). */
 uint64_t vg_index_fastq_blocks(const vg_index* ix);
+/* Host-only diagnostic (no GPU needed): the byte offset at which the raw road would cut `path` at or after
+ * `at` -- the first line start whose line begins with '@' and whose next-but-one line begins with '+' within
+ * `window` bytes; -1 if there is none, -2 if the file cannot be read. */
+int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint64_t window);
 
 /* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
  * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */

@@ -72,3 +72,30 @@ def test_product_never_touches_oracle():
                 if re.search(r"vg_oracle|libvgoracle|libvgref|oracle_binding|vgo_", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_fastq_record_boundary_heuristic(vglib, tmp_path):
+    """Host half of the raw FASTQ road: block cuts land on record starts even when quality lines begin
+    with '@' or '+', with CRLF line ends, and give up (-1) where no four-line record starts in the window."""
+    recs = []
+    for i in range(200):
+        seq = b"ACGT" * (5 + i % 7)
+        qual = (b"@" if i % 3 == 0 else b"+" if i % 3 == 1 else b"I") + b"#" * (len(seq) - 1)
+        eol = b"\r\n" if i % 2 else b"\n"
+        recs.append(b"@r%d x" % i + eol + seq + eol + b"+" + eol + qual + eol)
+    data = b"".join(recs)
+    p = tmp_path / "b.fq"
+    p.write_bytes(data)
+    starts = set(np.cumsum([0] + [len(r) for r in recs]).tolist())
+    f = vglib.lib.vg_fastq_record_boundary
+    assert f(str(p).encode(), 0, 4096) == 0
+    assert f(str(p).encode(), len(data) + 5, 4096) == len(data)
+    for at in range(1, len(data) - 400, 37):
+        b = f(str(p).encode(), at, 4096)
+        assert b in starts and b >= at and not any(at <= s < b for s in starts), (at, b)
+    # a window too short to see a whole record, and a file that is not FASTQ at all
+    assert f(str(p).encode(), 10, 8) == -1
+    q = tmp_path / "x.txt"
+    q.write_bytes(b"@not fastq\n" * 50)
+    assert f(str(q).encode(), 5, 4096) == -1
+    assert f(str(tmp_path / "missing").encode(), 5, 4096) == -2

@@ -517,6 +517,21 @@ int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int thre
 
 extern "C" uint64_t vg_index_fastq_blocks(const vg_index* ix) { return ix ? ix->fastq_blocks : 0; }
 
+// Host-only test hook (needs no GPU): where the raw road would cut `path` at or after byte `at`.
+extern "C" int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint64_t window) {
+    if (!path) return -2;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return -2;
+    struct stat st;
+    int64_t r = -2;
+    if (fstat(fd, &st) == 0) {
+        std::vector<char> buf;
+        r = record_boundary(fd, at, (uint64_t)st.st_size, window, buf);
+    }
+    close(fd);
+    return r;
+}
+
 extern "C" int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
     if (!ix || !paths || npaths <= 0) return vg::fail(VG_E_INVALID, "Parameter error: -f");
     if (!ix->counting) return vg::fail(VG_E_STATE, "vg_count_files before vg_count_begin");
