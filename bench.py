@@ -439,8 +439,11 @@ def main() -> None:
         if comm is not None:  # every rank sums its peers' u8 vectors over NVLink
             comm.allreduce_counts(ix, want_host=False, dev_out=out8.data_ptr())
             return out8[:max(nkeys, 1)]
-        ix.extract_device(out32.data_ptr(), 4)
-        return vdist.reduce_counts(out32)  # N > 1 with --reduce nccl: all-reduce of u32, clamp to 255
+        if world > 1:  # --reduce nccl: all-reduce of u32, clamp to 255
+            ix.extract_device(out32.data_ptr(), 4)
+            return vdist.reduce_counts(out32)
+        ix.extract_device(out8.data_ptr(), 1)  # the sample's result: u8 counts in key order, on the device
+        return out8[:max(nkeys, 1)]
 
     def barrier():
         if world > 1:
