@@ -221,7 +221,8 @@ int vg::ctx_ensure_fastq(vg_ctx* c) {
     vg::FastqScratch& f = c->fq;
     f.max_tiles = (uint32_t)(c->chunk_bytes / 4096 + 2);
     f.max_lines = (uint32_t)(c->chunk_bytes / 8 + 64);  // four-line FASTQ has lines of ~100 bytes; beyond this: host parser
-    CU(cudaMalloc((void**)&c->d_masked, c->chunk_bytes + 256));
+    // fastq_mask_kernel writes whole 4 KiB tiles: up to one tile beyond the block's last byte
+    CU(cudaMalloc((void**)&c->d_masked, c->chunk_bytes + 8192));
     CU(cudaMalloc((void**)&f.tile_count, (size_t)f.max_tiles * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&f.tile_base, (size_t)f.max_tiles * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&f.nlpos, (size_t)f.max_lines * sizeof(uint32_t)));
