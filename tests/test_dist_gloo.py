@@ -65,3 +65,46 @@ def test_two_rank_reduce_matches_single_process(tmp_path, oracle, saturate):
     assert (int(z["pos"]), int(z["hits"])) == (wpos, whits)
     if saturate:
         assert want.max() == 255
+
+
+class _FakeShardedIndex:
+    """Stands in for a sharded vg_index on the CPU: a round takes `round_bytes`, flush() is the collective."""
+    def __init__(self, round_bytes):
+        self.round_bytes, self.used, self.flushes, self.got = round_bytes, 0, 0, []
+
+    def room(self):
+        return self.round_bytes - self.used
+
+    def submit(self, b):
+        assert 0 < b.size <= self.room() and b[-1] == 10
+        self.used += b.size
+        self.got.append(bytes(b))
+
+    def flush(self):
+        self.used = 0
+        self.flushes += 1
+
+
+def _rounds_worker(rank, world, port, sizes, out_path):
+    from tests import multi_worker
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(rank)
+    reads = [bytes(rng.choice(list(b"ACGT"), size=rng.integers(1, 90)).tolist()) + b"\n" for _ in range(sizes[rank])]
+    lines = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    ix = _FakeShardedIndex(1000)
+    rounds = multi_worker.submit_in_rounds(ix, lines, dist)
+    ok = b"".join(ix.got) == lines.tobytes() and rounds == ix.flushes
+    np.savez(f"{out_path}.{rank}.npz", rounds=rounds, ok=ok, nbytes=lines.size)
+    dist.destroy_process_group()
+
+
+def test_sharded_rounds_are_collective(tmp_path):
+    """Ranks with very different amounts of reads still make the same number of collective flushes, and
+    every rank submits all of its reads, cut at read boundaries, never beyond the room of a round."""
+    out = str(tmp_path / "rounds")
+    mp.spawn(_rounds_worker, args=(2, _free_port(), (400, 7), out), nprocs=2, join=True)
+    z = [np.load(f"{out}.{r}.npz") for r in range(2)]
+    assert bool(z[0]["ok"]) and bool(z[1]["ok"])
+    assert int(z[0]["rounds"]) == int(z[1]["rounds"]) >= int(z[0]["nbytes"]) // 1000
