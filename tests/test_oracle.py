@@ -162,3 +162,54 @@ def test_fastq_parser_vs_reference_live(oracle, reference, tmp_path):
             assert np.array_equal(mine, ref_counts), name
     finally:
         reference.graph_destroy(h)
+
+
+def test_fastq_parser_vs_reference_random_damage(oracle, reference, tmp_path):
+    """Differential test of the kseq restatement: well-formed FASTQ with random damage (lost or doubled
+    newlines, stray '@' '+' '>' NUL CR bytes, cut tails) -- the reference reads each file, the oracle
+    parser must stage exactly the reads the reference counted (same per-k-mer counts, same mReadBase)."""
+    import random
+    t = helpers.tiny()
+    graph = tmp_path / "graph.bin"
+    graph.write_bytes(t["graph_bin"])
+    h, keys, k = reference.graph_load(str(graph))
+    rng = random.Random(2026)
+    try:
+        body = [r.tobytes() for r in t["m1"][:30]]
+        checked = 0
+        for trial in range(60):
+            recs = [b"@q%d\n%s\n+\n%s\n" % (i, s, bytes(rng.choice(b"I@+>#") for _ in s)) for i, s in enumerate(body)]
+            data = bytearray(b"".join(recs))
+            for _ in range(rng.randint(1, 4)):
+                at = rng.randrange(len(data))
+                kind = rng.randrange(6)
+                if kind == 0:                       # lose a newline (or any byte)
+                    nl = data.find(b"\n", at)
+                    if nl >= 0:
+                        del data[nl]
+                elif kind == 1:                     # an extra newline
+                    data.insert(at, 10)
+                elif kind == 2:                     # a stray marker or control byte
+                    data.insert(at, rng.choice(b"@+>\r\x00 "))
+                elif kind == 3:                     # overwrite with one
+                    data[at] = rng.choice(b"@+>\rN\x00")
+                elif kind == 4:                     # cut the tail
+                    del data[max(at, len(data) // 2):]
+                else:                               # CRLF line end
+                    nl = data.find(b"\n", at)
+                    if nl >= 0:
+                        data.insert(nl, 13)
+            data = bytes(data)
+            lines, nreads, bases, status = oracle.fastq_to_lines(data)
+            if lines.startswith(b"\n") or b"\n\n" in lines:
+                continue  # an empty read: the reference itself aborts there (assert len > 0, src/kmer.cpp:124)
+            checked += 1
+            path = tmp_path / ("dmg%d.fq" % trial)
+            path.write_bytes(data)
+            ref_counts, ref_bases, _ = reference.count_files(h, keys.size, [str(path)], threads=2)
+            mine, _, _ = oracle.count_lines(keys, lines, k)
+            assert bases == ref_bases, (trial, data[:200])
+            assert np.array_equal(mine, ref_counts), trial
+        assert checked >= 30
+    finally:
+        reference.graph_destroy(h)
