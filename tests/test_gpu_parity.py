@@ -414,6 +414,48 @@ def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, t
     ix.close()
 
 
+def test_count_files_raw_fastq_random_damage(ctx, vglib, oracle, tmp_path):
+    """Random damage anywhere in a multi-block plain FASTQ file (lost / extra newlines, stray marker bytes,
+    NUL, CR, a cut tail): device parsing plus kseq fallback must give exactly what kseq makes of the file."""
+    t = helpers.tiny()
+    rng = random.Random(77)
+    recs = _fastq_text(rng, t["genome"], 14_000)           # ~2.5 MB: several 1 MB staging blocks
+    clean = b"".join(recs)
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    for trial in range(12):
+        data = bytearray(clean)
+        for _ in range(rng.randint(1, 3)):
+            at = rng.randrange(len(data))
+            kind = rng.randrange(6)
+            if kind == 0:
+                nl = data.find(b"\n", at)
+                if nl >= 0:
+                    del data[nl]
+            elif kind == 1:
+                data.insert(at, 10)
+            elif kind == 2:
+                data.insert(at, rng.choice(b"@+>\r\x00 "))
+            elif kind == 3:
+                data[at] = rng.choice(b"@+>\rN\x00")
+            elif kind == 4:
+                del data[max(at, len(data) // 2):]
+            else:
+                nl = data.find(b"\n", at)
+                if nl >= 0:
+                    data.insert(nl, 13)
+        data = bytes(data)
+        p = tmp_path / ("dmg%d.fq" % trial)
+        p.write_bytes(data)
+        lines, nreads, bases, status = oracle.fastq_to_lines(data)
+        want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
+        ix.begin()
+        rb = ix.count_files([str(p)], threads=3)
+        counts, pos, hits = ix.end()
+        assert rb == bases and (pos, hits) == (wpos, whits) and np.array_equal(counts, want), trial
+        p.unlink()
+    ix.close()
+
+
 def test_count_files_raw_fastq_long_records_go_to_kseq(ctx, vglib, oracle, tmp_path):
     """Records longer than the boundary-search window cannot be cut into raw blocks: the first block goes to
     the device, the rest of the file to the kseq reader from the last boundary on; same result."""
