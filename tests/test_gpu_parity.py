@@ -633,6 +633,31 @@ def test_genotype_vcf_identical_to_reference(tmp_path):
     assert out["gpu"] == t["vcf"]  # and equal to the committed golden VCF
 
 
+def test_genotype_two_samples_in_one_run(tmp_path):
+    """BASELINE config 5 in miniature: several samples in one `genotype` run share the device index; the
+    counters are reset between samples (vg_count_begin), so each sample's VCF equals the reference's."""
+    ref_bin, b200 = _integrated()
+    t = helpers.tiny()
+    (tmp_path / "graph.bin").write_bytes(t["graph_bin"])
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t)
+    half = len(t["m1"]) // 2
+    g1, g2 = str(tmp_path / "T_1.fq.gz"), str(tmp_path / "T_2.fq")       # second sample: half the pairs, one file plain
+    synth.write_fastq(g1, t["m1"][:half], "c")
+    synth.write_fastq(g2, t["m2"][:half], "d")
+    (tmp_path / "samples.cfg").write_text(f"S0 {f1} {f2}\nS1 {g1} {g2}\n")
+    out = {}
+    for name, exe, extra in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", "0", "--buffer", "1"])):
+        d = tmp_path / name
+        d.mkdir()
+        _run([exe, "genotype", "--load-graph", str(tmp_path / "graph.bin"), "-s", str(tmp_path / "samples.cfg"), "-t", "4"] + extra,
+             cwd=str(d))
+        for smp in ("S0", "S1"):
+            with gzip.open(d / f"{smp}.varigraph.vcf.gz", "rb") as f:
+                out[name, smp] = f.read()
+    assert out["gpu", "S0"] == out["cpu", "S0"] == t["vcf"]
+    assert out["gpu", "S1"] == out["cpu", "S1"] and out["gpu", "S1"] != out["gpu", "S0"]
+
+
 def test_construct_on_gpu_then_identical_genotypes(tmp_path):
     """`construct` with the CBF filled on the device, then both binaries genotype from that graph."""
     ref_bin, b200 = _integrated()
