@@ -300,7 +300,8 @@ def reference_run(a, keys_np: np.ndarray, lines_np: np.ndarray, steps: int, warm
 
 
 def oracle_positions(orc, keys_np, sub) -> int:
-    """Emitted k-mer positions of a chunk (N-free reads give reads x 124; errors put N in some)."""
+    """Emitted k-mer positions of a chunk (N-free reads give reads x 124; errors put N in some).  Plain numpy
+    (the odd-k run-length rule of SURVEY appendix A.4); `orc` and `keys_np` are unused."""
     b = np.ascontiguousarray(sub)
     valid = np.isin(b, np.frombuffer(b"ACGTacgtUu", dtype=np.uint8))
     # run length of consecutive valid bytes ending at each byte; positions with run >= K emit (odd K)
