@@ -1,33 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- read k-mers/sec counted against the graph index (BASELINE.json's metric).
 
-Workload (config.workload): BASELINE.json configs[1], "human chr20-shaped synthetic graph (64 Mb,
-~1.5M variants), 30x PE150 on 1 B200", generated here from fixed seeds with torch (plumbing, not
-the product): iid genome, SNV/MNP variants every ~43 bp, index = canonical k-mer hashes of every
-reference- and alt-allele window overlapping a variant, reads drawn from two haplotypes with 0.3 %
-substitution errors (1/5 of them N).  A *step* is one whole sample: zero the counters, count every
-read k-mer of the sample against the index, produce the count vector.
+Workloads (config.workload), generated here from fixed seeds with torch (plumbing, not the product):
+  chr20 (default)  BASELINE.json configs[1]: "human chr20-shaped synthetic graph (64 Mb, ~1.5M variants), 30x PE150
+                   on 1 B200" -- iid genome, SNV/MNP variants every ~43 bp
+  human            BASELINE.json configs[2]: "human-genome-shaped graph (3.1 Gb, ~25M SNV/indel/SV), 30x PE150 across
+                   8xB200" -- the same generator run in 128 Mb windows, variants every ~124 bp, ~1.4e9 index k-mers
+                   that never leave the device (vg_index_create_device)
+index = canonical k-mer hashes of every reference- and alt-allele window overlapping a variant; reads drawn from two
+haplotypes with 0.3 % substitution errors (1/5 of them N).  A *step* is one whole sample: zero the counters, count
+every read k-mer of the sample against the index, produce the count vector.
 
   value     k-mer positions / s, reads already resident in HBM (CUDA events, max over ranks)
-  e2e       the same through the host-buffer C-ABI call (vg_count_begin / vg_count_submit from
-            pinned host memory / vg_count_end into host memory), H2D + D2H inside the timed region
-  roofline  the fused count kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-            with B_alg = 1 + 32 + 32 h bytes per position, plus the measured
-            random-32-byte-sector gather rate of the same box as a second denominator
+  e2e       the same through the reference-facing call: vg_count_files over plain FASTQ files on tmpfs (what the
+            reference arm reads) -> counts in host memory; file reads, H2D and D2H inside the timed region
+  e2e_staged  vg_count_begin / vg_count_submit from pinned host memory holding parsed "read\\n" records /
+            vg_count_end_slots into host memory (round 1's e2e)
+  roofline  the count pass against the measured HBM copy bandwidth (MEASURED_PEAKS.json) with
+            B_alg = 1 + 32 + 32 h bytes per position; per-kernel times from the library's own CUDA
+            events, the L1TEX gather rate that actually binds the kernels, and the measured random-sector rate
   cpu_baseline  the reference's own FastqKmer::build_fastq_index (oracle/_ref) on a bounded sample
   --impl reference   times that reference CPU path alone, same config/metric/unit
 
-N > 1 (torchrun): reads are sharded over ranks (each rank counts its own 30x sample: weak scaling),
-the index is replicated, and the only exchange is one reduce of the count vectors per sample:
-min(255, sum over ranks), exact.  By default every rank reads its peers' u8 vectors over
-NVLink (vg_count_allreduce: CUDA IPC peer memory, a device-side barrier, no NCCL in the data path);
---reduce nccl uses an NCCL all-reduce of u32 instead (also the fallback if peer mapping fails).
---index sharded cuts the index itself over the ranks (the index > HBM layout): the scatter kernel
-stores every k-mer straight into the owning GPU's key list over NVLink, rounds of --round-mb.
+N > 1 (torchrun): reads are sharded over the ranks and the index is replicated; the only exchange is one reduce of the
+count vectors per sample: min(255, sum over ranks), exact, each rank reading its peers' vectors over
+NVLink (vg_count_allreduce: CUDA IPC peer memory, a device-side barrier, no NCCL in the data path; --reduce nccl is
+the alternative).  --scaling weak (default, the driver's line): every rank counts its own --coverage sample;
+--scaling strong: ONE --coverage sample is cut over the ranks.  --index sharded cuts the index itself over the ranks
+(the index > HBM layout): the scatter kernel stores every k-mer straight into the owning GPU's key list over NVLink.
+At N == 8 the default run adds a "human_scale" object: the human workload, strong scaling, measured in the same job.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -80,16 +86,10 @@ def t_window_keys(codes: torch.Tensor, k: int) -> torch.Tensor:
     return (t_hash64(canon, (1 << (2 * k)) - 1) << 8) | k
 
 
-def make_graph(dev, genome_len: int, nvar: int, seed: int):
-    """-> (ref codes u8[L], alt codes u8[L], var_pos int64[nvar], var_len int64[nvar], keys int64 unique)"""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    L = genome_len
-    ref = torch.randint(0, 4, (L,), generator=g, device=dev, dtype=torch.uint8)
+def make_variants(dev, L: int, nvar: int, g: torch.Generator, ref: torch.Tensor):
     pos = torch.randint(1000, L - 1000, (int(nvar * 1.03),), generator=g, device=dev)
     pos = torch.unique(pos)[:nvar]
-    # keep variants at least 10 bp apart so spans never overlap
-    keep = torch.ones_like(pos, dtype=torch.bool)
+    keep = torch.ones_like(pos, dtype=torch.bool)  # variants at least 10 bp apart so spans never overlap
     keep[1:] = (pos[1:] - pos[:-1]) >= 10
     pos = pos[keep]
     nv = pos.numel()
@@ -102,6 +102,17 @@ def make_graph(dev, genome_len: int, nvar: int, seed: int):
         sel = vlen > j
         p = pos[sel] + j
         alt[p] = (ref[p] + torch.randint(1, 4, (p.numel(),), generator=g, device=dev, dtype=torch.uint8)) % 4
+    return alt, pos, vlen
+
+
+def make_graph(dev, genome_len: int, nvar: int, seed: int):
+    """-> (ref codes u8[L], alt codes u8[L], var_pos int64[nvar], var_len int64[nvar], keys int64 unique)"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    L = genome_len
+    ref = torch.randint(0, 4, (L,), generator=g, device=dev, dtype=torch.uint8)
+    alt, pos, vlen = make_variants(dev, L, nvar, g, ref)
+    nv = pos.numel()
     n = L - K + 1
     d = torch.zeros(L + 2, dtype=torch.int32, device=dev)
     d.index_add_(0, (pos - K + 1).clamp_(min=0), torch.ones(nv, dtype=torch.int32, device=dev))
@@ -115,22 +126,61 @@ def make_graph(dev, genome_len: int, nvar: int, seed: int):
     return ref, alt, pos, vlen, keys
 
 
+def make_graph_windows(dev, genome_len: int, nvar: int, seed: int, window: int = 128_000_000):
+    """The same graph shape for genomes of any length, built in windows so that no temporary exceeds a few GB.
+    The keys stay where they are made (device).  Not de-duplicated: a random genome repeats a 27-mer a few dozen times
+    in 1.4e9 windows; the device index reports and tolerates duplicates (they share a slot)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    L = genome_len
+    ref = torch.empty(L, dtype=torch.uint8, device=dev)
+    for s in range(0, L, 1 << 30):
+        e = min(L, s + (1 << 30))
+        ref[s:e] = torch.randint(0, 4, (e - s,), generator=g, device=dev, dtype=torch.uint8)
+    alt, pos, vlen = make_variants(dev, L, nvar, g, ref)
+    lo_all = (pos - K + 1).clamp(min=0)          # first window start that overlaps each variant
+    hi_all = pos + vlen                          # one past the last
+    est = int((hi_all - lo_all).sum().item()) * 2 + 1024
+    keys = torch.empty(est, dtype=torch.int64, device=dev)
+    nkeys = 0
+    n = L - K + 1
+    for s in range(0, n, window):
+        e = min(n, s + window)
+        i0 = int(torch.searchsorted(hi_all, torch.tensor([s], device=dev), right=True).item())
+        i1 = int(torch.searchsorted(lo_all, torch.tensor([e], device=dev), right=False).item())
+        if i1 <= i0:
+            continue
+        d = torch.zeros(e - s + 1, dtype=torch.int32, device=dev)
+        one = torch.ones(i1 - i0, dtype=torch.int32, device=dev)
+        d.index_add_(0, (lo_all[i0:i1] - s).clamp(min=0), one)
+        d.index_add_(0, (hi_all[i0:i1] - s).clamp(max=e - s), -one)
+        cover = torch.cumsum(d, 0, dtype=torch.int32)[: e - s] > 0
+        del d, one
+        for codes in (ref, alt):
+            kk = t_window_keys(codes[s: e + K - 1], K)[cover]
+            keys[nkeys: nkeys + kk.numel()] = kk
+            nkeys += kk.numel()
+            del kk
+        del cover
+    return ref, alt, pos, vlen, keys[:nkeys]
+
+
 def make_reads(dev, ref, alt, pos, vlen, coverage: float, seed: int) -> torch.Tensor:
     """PE150 from two haplotypes -> uint8 [nreads * 151] staged chunk ('read\\n' records) on `dev`."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     L = ref.numel()
-    haps = []
-    for _ in range(2):
+    flat = torch.empty(2 * L, dtype=torch.uint8, device=dev)
+    for hidx in range(2):
         carry = torch.rand(pos.numel(), generator=g, device=dev) < 0.3
         d = torch.zeros(L + 1, dtype=torch.int32, device=dev)
         one = torch.ones(int(carry.sum()), dtype=torch.int32, device=dev)
         d.index_add_(0, pos[carry], one)
         d.index_add_(0, pos[carry] + vlen[carry], -one)
-        m = torch.cumsum(d, 0)[:L] > 0
-        haps.append(torch.where(m, alt, ref))
-        del d, m
-    hap2 = torch.stack(haps)  # [2, L]
+        m = torch.cumsum(d, 0, dtype=torch.int32)[:L] > 0
+        del d
+        flat[hidx * L: (hidx + 1) * L] = torch.where(m, alt, ref)
+        del m
     npairs = int(round(coverage * L / (2 * READ_LEN)))
     ascii_lut = torch.tensor([65, 67, 71, 84, 78], dtype=torch.uint8, device=dev)  # A C G T N
     out = torch.empty((2 * npairs, READ_LEN + 1), dtype=torch.uint8, device=dev)
@@ -143,7 +193,6 @@ def make_reads(dev, ref, alt, pos, vlen, coverage: float, seed: int) -> torch.Te
         ins = torch.randint(300, 501, (nb,), generator=g, device=dev)
         start = (torch.rand(nb, generator=g, device=dev, dtype=torch.float64) * (L - 502)).to(torch.int64)
         base = h * L
-        flat = hap2.reshape(-1)
         m1 = flat[(base + start)[:, None] + ar[None, :]]
         m2 = 3 - flat[(base + start + ins - 1)[:, None] - ar[None, :]]
         both = torch.cat([m1, m2.to(torch.uint8)])
@@ -152,21 +201,26 @@ def make_reads(dev, ref, alt, pos, vlen, coverage: float, seed: int) -> torch.Te
         both = torch.where(err, sub, both)
         out[2 * b0: 2 * b0 + 2 * nb, :READ_LEN] = ascii_lut[both.to(torch.int64)]
         del m1, m2, both, err, sub
+    del flat
     return out.reshape(-1)
 
 
-def write_fastq_sample(path: str, lines: np.ndarray, nreads: int) -> int:
-    """First `nreads` reads of a staged chunk -> plain FASTQ; returns bases written."""
-    rec = lines[: nreads * (READ_LEN + 1)].reshape(nreads, READ_LEN + 1)
+def write_fastq_sample(path: str, lines: np.ndarray, nreads: int, first: int = 0) -> int:
+    """Reads [first, first + nreads) of a staged chunk -> plain four-line FASTQ; returns bases written."""
+    rec = lines[first * (READ_LEN + 1): (first + nreads) * (READ_LEN + 1)].reshape(nreads, READ_LEN + 1)
     head = np.frombuffer(b"@r\n", dtype=np.uint8)
     plus = np.frombuffer(b"+\n", dtype=np.uint8)
-    out = np.empty((nreads, 3 + READ_LEN + 1 + 2 + READ_LEN + 1), dtype=np.uint8)
-    out[:, :3] = head
-    out[:, 3:3 + READ_LEN + 1] = rec
-    out[:, 3 + READ_LEN + 1: 3 + READ_LEN + 3] = plus
-    out[:, 3 + READ_LEN + 3: -1] = ord("I")
-    out[:, -1] = 10
-    out.tofile(path)
+    with open(path, "wb") as f:
+        B = 1 << 20
+        for s in range(0, nreads, B):
+            nb = min(B, nreads - s)
+            out = np.empty((nb, 3 + READ_LEN + 1 + 2 + READ_LEN + 1), dtype=np.uint8)
+            out[:, :3] = head
+            out[:, 3:3 + READ_LEN + 1] = rec[s: s + nb]
+            out[:, 3 + READ_LEN + 1: 3 + READ_LEN + 3] = plus
+            out[:, 3 + READ_LEN + 3: -1] = ord("I")
+            out[:, -1] = 10
+            out.tofile(f)
     return nreads * READ_LEN
 
 
@@ -247,22 +301,41 @@ def dist_info():
     return rank, world, local
 
 
-def workload_name(a) -> str:
-    return (f"chr20-shaped synthetic graph ({a.genome_mb} Mb, ~{a.variants / 1e6:.2f}M variants), "
-            f"{a.coverage:g}x PE150, k={K}")
+SPECS = {
+    "chr20": dict(genome_mb=64, variants=1_500_000, coverage=30.0, label="chr20-shaped"),
+    "human": dict(genome_mb=3100, variants=25_000_000, coverage=30.0, label="human-genome-shaped"),
+}
+
+
+def workload_name(w) -> str:
+    return (f"{w['label']} synthetic graph ({w['genome_mb']} Mb, ~{w['variants'] / 1e6:.2f}M variants), "
+            f"{w['coverage']:g}x PE150, k={K}")
+
+
+def tmpfs_dir():
+    return tempfile.mkdtemp(prefix="vgbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+
+
+def rm_tree(d):
+    try:
+        for f in os.listdir(d):
+            os.remove(os.path.join(d, f))
+        os.rmdir(d)
+    except OSError:
+        pass
 
 
 # ------------------------------------------------------------------------------------------------
 # the reference arm: FastqKmer::build_fastq_index on the host cores
 # ------------------------------------------------------------------------------------------------
-def reference_run(a, keys_np: np.ndarray, lines_np: np.ndarray, steps: int, warmup: int, want_counts=False):
+def reference_run(cpu_sample_reads, keys_np: np.ndarray, lines_np: np.ndarray, steps: int, warmup: int, want_counts=False):
     from tests import oracle_binding as ob
     cores = os.cpu_count() or 1
-    nreads = min(a.cpu_sample_reads, lines_np.size // (READ_LEN + 1))
-    tmpdir = tempfile.mkdtemp(prefix="vgbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    nreads = min(cpu_sample_reads, lines_np.size // (READ_LEN + 1))
+    tmpdir = tmpfs_dir()
     fq = os.path.join(tmpdir, "sample.fq")
     write_fastq_sample(fq, lines_np, nreads)
-    sample = f"first {nreads} reads of the sample as plain FASTQ on tmpfs, full index ({keys_np.size} k-mers)"
+    sample = f"first {nreads} reads of the sample as plain FASTQ on tmpfs, index of {keys_np.size} k-mers"
     out = {}
     try:
         if ob.Reference.available:
@@ -285,103 +358,41 @@ def reference_run(a, keys_np: np.ndarray, lines_np: np.ndarray, steps: int, warm
                 if i >= warmup:
                     times.append(time.perf_counter() - t0)
             kind, cores = "port", 1
-        orc = ob.Oracle()
-        pos = oracle_positions(orc, keys_np, lines_np[: nreads * (READ_LEN + 1)])
+        pos = emitted_positions(lines_np[: nreads * (READ_LEN + 1)])
         sec = float(np.mean(times))
         out = {"value": pos / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                "seconds_per_step": sec, "positions": pos, "counts": counts, "nreads": nreads}
     finally:
-        try:
-            os.remove(fq)
-            os.rmdir(tmpdir)
-        except OSError:
-            pass
+        rm_tree(tmpdir)
     return out
 
 
-def oracle_positions(orc, keys_np, sub) -> int:
+def emitted_positions(sub) -> int:
     """Emitted k-mer positions of a chunk (N-free reads give reads x 124; errors put N in some).  Plain numpy
-    (the odd-k run-length rule of SURVEY appendix A.4); `orc` and `keys_np` are unused."""
+    (the odd-k run-length rule of SURVEY appendix A.4)."""
     b = np.ascontiguousarray(sub)
     valid = np.isin(b, np.frombuffer(b"ACGTacgtUu", dtype=np.uint8))
-    # run length of consecutive valid bytes ending at each byte; positions with run >= K emit (odd K)
     idx = np.arange(b.size, dtype=np.int64)
     last_bad = np.maximum.accumulate(np.where(~valid, idx, -1))
     return int(((idx - last_bad) >= K).sum())
 
 
 # ------------------------------------------------------------------------------------------------
-def main() -> None:
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genome-mb", type=int, default=64)
-    ap.add_argument("--variants", type=int, default=1_500_000)
-    ap.add_argument("--coverage", type=float, default=30.0)
-    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--buffer-mb", type=int, default=64)
-    ap.add_argument("--load-factor", type=float, default=0.0)
-    ap.add_argument("--kmer", type=int, default=27, help="k (BASELINE configs use the default 27)")
-    ap.add_argument("--index", default="replicated", choices=["replicated", "sharded"],
-                    help="N > 1: a replica of the index per GPU (default) or one index cut over the GPUs")
-    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N > 1, replicated: how counts are combined")
-    ap.add_argument("--round-mb", type=int, default=1024, help="sharded index: bases per rank and round")
-    a = ap.parse_args()
-    global K
-    K = a.kmer
-    rank, world, local = dist_info()
-    steps, warmup = a.steps, max(a.warmup, 3 if a.impl == "b200" else a.warmup)
-    L = a.genome_mb * 1_000_000
-
-    if a.impl == "reference":
-        if rank != 0:
-            return
-        dev = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
-        ref, alt, pos, vlen, keys = make_graph(dev, L, a.variants, seed=20261017)
-        keys_np = keys.cpu().numpy().view(np.uint64)
-        nreads = a.cpu_sample_reads
-        cov = nreads * READ_LEN / L * 1.02 + 0.01
-        lines_np = make_reads(dev, ref, alt, pos, vlen, min(cov, a.coverage), seed=1000).cpu().numpy()
-        del ref, alt, pos, vlen, keys
-        r = reference_run(a, keys_np, lines_np, steps, a.warmup)
-        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-                "warmup": a.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "impl": "reference",
-                "config": {"workload": workload_name(a), "index_kmers": int(keys_np.size)},
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                                 "sample": r["sample"]},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
-        return
-
-    # ---- our arm -----------------------------------------------------------------------------
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; varigraph_b200 has no CPU path (use --impl reference)")
-    import torch.distributed as dist
-    from varigraph_b200 import capi
-    from varigraph_b200 import dist as vdist
-    torch.cuda.set_device(local)
+# one workload on our arm -> the JSON line's fields
+# ------------------------------------------------------------------------------------------------
+def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_files_e2e=True, want_cpu=True,
+            staged_cap_bytes=None):
     dev = torch.device("cuda", local)
-    numa = None
-    if world > 1:
-        numa = vdist.bind_to_gpu_numa(local)  # before any pinned allocation: staging memory next to the GPU
-        dist.init_process_group("nccl", device_id=dev)
-
-    ref, alt, pos, vlen, keys = make_graph(dev, L, a.variants, seed=20261017)
-    keys_np = keys.cpu().numpy().view(np.uint64)
-    nkeys = int(keys_np.size)
-    del keys
-    lines_dev = make_reads(dev, ref, alt, pos, vlen, a.coverage, seed=1000 + rank)
-    del ref, alt, pos, vlen
-    torch.cuda.empty_cache()
-    nbytes = lines_dev.numel()
-    lines_host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    lines_host.copy_(lines_dev)
+    L = w["genome_mb"] * 1_000_000
+    big = L > 512_000_000
+    strong = a.scaling == "strong" or w.get("strong", False)
+    cov_rank = w["coverage"] / world if strong else w["coverage"]
+    t_gen0 = time.perf_counter()
+    if big:
+        ref, alt, pos, vlen, keys = make_graph_windows(dev, L, w["variants"], seed=20261017)
+    else:
+        ref, alt, pos, vlen, keys = make_graph(dev, L, w["variants"], seed=20261017)
+    nkeys = int(keys.numel())
     torch.cuda.synchronize()
 
     ctx = capi.Context(local, buffer_mb=a.buffer_mb)
@@ -398,7 +409,7 @@ def main() -> None:
             return got
         round_bytes = a.round_mb << 20
         table_est = int(nkeys / world / (4 * (a.load_factor or 0.3)) * 32 * 1.1) + (64 << 20)
-        arena = (nkeys + (1 << 20)) + ((table_est + round_bytes * 10 + (128 << 20)) if sharded else 0)
+        arena = (nkeys + (1 << 20)) + ((table_est + table_est // 8 + nkeys + round_bytes * 10 + (128 << 20)) if sharded else 0)
         ok = torch.ones(1, device=dev)
         try:
             comm = capi.Comm(ctx, rank, world, arena, exchange)
@@ -412,13 +423,45 @@ def main() -> None:
             comm = None
         else:
             reduce_how = "p2p"
-    ix = capi.Index(ctx, keys_np, K, a.load_factor, comm=comm if sharded else None,
-                    round_bytes=(a.round_mb << 20) if sharded else 0)
-    out32 = torch.empty(max(nkeys, 1), dtype=torch.int32, device=dev)
-    out8 = torch.empty(max(nkeys, 1) + 32, dtype=torch.uint8, device=dev)
-    counts_host = torch.empty(max(nkeys, 1), dtype=torch.uint8, pin_memory=True)
-    # sharded index: the sample goes in rounds of at most --round-mb, cut at read boundaries
+    # a sample of the index for the in-run parity check against the reference (every key when the index is small)
+    keys_np = None
+    if big:
+        sel = (((keys >> 8) * -7046029254386353131) >> 58) == 0  # 1/64 of the keys, by hash (0x9E3779B97F4A7C15 as int64)
+        sample_keys_np = keys[sel].cpu().numpy().view(np.uint64)
+        sample_idx = torch.nonzero(sel).reshape(-1)
+        del sel
+    else:
+        keys_np = keys.cpu().numpy().view(np.uint64)
+        sample_keys_np, sample_idx = keys_np, None
+    t_build0 = time.perf_counter()
+    if sharded:
+        if keys_np is None:
+            keys_np = keys.cpu().numpy().view(np.uint64)
+        ix = capi.Index(ctx, keys_np, K, a.load_factor, comm=comm, round_bytes=(a.round_mb << 20))
+    elif big:
+        ix = capi.Index(ctx, (keys.data_ptr(), nkeys), K, a.load_factor)
+    else:
+        ix = capi.Index(ctx, keys_np, K, a.load_factor)
+    t_build = time.perf_counter() - t_build0
+    del keys
+    torch.cuda.empty_cache()
+    lines_dev = make_reads(dev, ref, alt, pos, vlen, cov_rank, seed=1000 + rank)
+    del ref, alt, pos, vlen
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen0
+    nbytes = lines_dev.numel()
     rec = READ_LEN + 1
+    # host copy of the reads (pinned): all of them, or (staged_cap_bytes) the first few GB for the rate
+    host_bytes = nbytes if staged_cap_bytes is None else min(nbytes, staged_cap_bytes // rec * rec)
+    lines_host = torch.empty(host_bytes, dtype=torch.uint8, pin_memory=True)
+    lines_host.copy_(lines_dev[:host_bytes])
+    torch.cuda.synchronize()
+
+    nslots = ix.slots if not sharded else 0
+    out32 = torch.empty(max(nkeys, 1), dtype=torch.int32, device=dev) if (world > 1 and comm is None) else None
+    out8 = torch.empty(max(nkeys, 1) + 32, dtype=torch.uint8, device=dev) if world > 1 else None
+    counts_host = torch.empty(max(nkeys, nslots, 1), dtype=torch.uint8, pin_memory=True)
     per_round = max(1, ((a.round_mb << 20) - (1 << 20)) // rec) * rec
     round_cuts = [(o, min(per_round, nbytes - o)) for o in range(0, nbytes, per_round)] if sharded else []
 
@@ -443,8 +486,7 @@ def main() -> None:
         if world > 1:  # --reduce nccl: all-reduce of u32, clamp to 255
             ix.extract_device(out32.data_ptr(), 4)
             return vdist.reduce_counts(out32)
-        ix.extract_device(out8.data_ptr(), 1)  # the sample's result: u8 counts in key order, on the device
-        return out8[:max(nkeys, 1)]
+        return ix.slots_device()  # the sample's result: the u8 count vector, on the device, in slot order
 
     def barrier():
         if world > 1:
@@ -467,7 +509,7 @@ def main() -> None:
     e1.record(stream)
     barrier()
     t_mark1 = clocks.mark()
-    launches_timed = ix.launches - launches0 + steps  # + the extract kernel of each step
+    launches_timed = ix.launches - launches0
     if comm is not None:
         launches_timed += comm.launches * steps // (steps + warmup)
     total_ms = e0.elapsed_time(e1)
@@ -481,11 +523,36 @@ def main() -> None:
     total_positions = float(tp.item())
     value = total_positions / (ms_per_step * 1e-3)
     clk = clocks.stop(t_mark0, t_mark1)
-    dc = device_step(want=True)
-    device_counts = dc if isinstance(dc, np.ndarray) else dc.cpu().numpy()
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------
-    def e2e_step():
+    # ---- the same pass once more with the library's per-phase CUDA events (diagnostic, untimed) ----------
+    phases = None
+    if not sharded:
+        ix.set_timing(True)
+        for _ in range(2):
+            device_step()
+        torch.cuda.synchronize()
+        phases = ix.timing()
+        ix.set_timing(False)
+
+    # ---- counts of the device path, key order, for the checks below ---------------------------------------
+    if sharded:
+        device_counts = device_step(want=True)
+    elif world > 1:
+        device_counts = device_step().cpu().numpy()
+    else:
+        ix.begin()
+        ix.submit_device(lines_dev.data_ptr(), nbytes)
+        if big:
+            device_counts = None  # checked on the sample below
+            ix.end(want_counts=False)
+        else:
+            device_counts = ix.end()[0]
+
+    # ---- e2e_staged: parsed reads in pinned host memory through the C ABI, copies inside the timed region ----
+    ctx.set_stream(0)  # the staged path pipelines copy and compute on the context's own streams
+    host_positions = positions if host_bytes == nbytes else None
+
+    def staged_step():
         ix.begin()
         if sharded:
             for o, ln in round_cuts:
@@ -493,7 +560,7 @@ def main() -> None:
                 ix.flush()
             capi._chk(capi.lib.vg_count_end(ix._h, counts_host.data_ptr(), None, None))
             return
-        ix.submit_ptr(lines_host.data_ptr(), nbytes)
+        ix.submit_ptr(lines_host.data_ptr(), host_bytes)
         if comm is not None:
             capi._chk(capi.lib.vg_count_allreduce(comm._h, ix._h, counts_host.data_ptr(), None))
             capi._chk(capi.lib.vg_count_end(ix._h, None, None, None))
@@ -503,82 +570,291 @@ def main() -> None:
             torch.cuda.synchronize()
             capi.lib.vg_count_end(ix._h, None, None, None)
         else:
-            capi._chk(capi.lib.vg_count_end(ix._h, counts_host.data_ptr(), None, None))
+            capi._chk(capi.lib.vg_count_end_slots(ix._h, counts_host.data_ptr(), None, None))
 
-    ctx.set_stream(0)  # the staged path pipelines copy and compute on the context's own streams
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total_positions / float(te.item())
-    e2e_counts_ok = bool(np.array_equal(counts_host.numpy()[:nkeys], device_counts[:nkeys]))
+    e2e_staged = None
+    if host_bytes == nbytes or not sharded:
+        for _ in range(2):
+            staged_step()
+        if host_positions is None:
+            host_positions = ix.stats()[0]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            staged_step()
+        barrier()
+        st_s = (time.perf_counter() - t0) / steps
+        te = torch.tensor([st_s], dtype=torch.float64, device=dev)
+        hp = torch.tensor([float(host_positions)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(hp, op=dist.ReduceOp.SUM)
+        staged_ok = None
+        if device_counts is not None and host_bytes == nbytes:
+            got = counts_host.numpy()
+            if world == 1:
+                got = got[:nslots][ix.slot_perm()]
+            staged_ok = bool(np.array_equal(got[:nkeys], device_counts[:nkeys]))
+        e2e_staged = {"value": float(hp.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(host_bytes),
+                      "d2h_bytes_per_step": int(nslots if world == 1 else nkeys), "counts_equal_device_path": staged_ok,
+                      "input": "parsed 'read\\n' records in pinned host memory"
+                               + ("" if host_bytes == nbytes else f" (first {host_bytes} bytes of each rank's reads)")}
 
-    # ---- roofline of the fused count kernel --------------------------------------------------
+    # ---- e2e: the reference-facing call, from the FASTQ files the reference arm reads ----------------------
+    e2e = None
+    if want_files_e2e and not sharded:
+        tmpdir = tmpfs_dir()
+        try:
+            lines_np = lines_host.numpy()
+            nreads = host_bytes // rec
+            half = nreads // 2
+            fqs = [os.path.join(tmpdir, f"r{rank}_1.fq"), os.path.join(tmpdir, f"r{rank}_2.fq")]
+            write_fastq_sample(fqs[0], lines_np, half, 0)
+            write_fastq_sample(fqs[1], lines_np, nreads - half, half)
+            file_bytes = sum(os.path.getsize(f) for f in fqs)
+            threads = max(1, (os.cpu_count() or 1) // world)
+
+            def files_step():
+                ix.begin()
+                rb = ix.count_files(fqs, threads=threads)
+                if comm is not None:
+                    capi._chk(capi.lib.vg_count_allreduce(comm._h, ix._h, counts_host.data_ptr(), None))
+                    capi._chk(capi.lib.vg_count_end(ix._h, None, None, None))
+                elif world > 1:
+                    ix.extract_device(out32.data_ptr(), 4, stream.cuda_stream)
+                    counts_host.copy_(vdist.reduce_counts(out32), non_blocking=True)
+                    torch.cuda.synchronize()
+                    capi.lib.vg_count_end(ix._h, None, None, None)
+                else:
+                    capi._chk(capi.lib.vg_count_end_slots(ix._h, counts_host.data_ptr(), None, None))
+                return rb
+
+            for _ in range(2):
+                rb = files_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                files_step()
+            barrier()
+            f_s = (time.perf_counter() - t0) / steps
+            te = torch.tensor([f_s], dtype=torch.float64, device=dev)
+            hp = torch.tensor([float(host_positions)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+                dist.all_reduce(hp, op=dist.ReduceOp.SUM)
+            files_ok = None
+            if device_counts is not None and host_bytes == nbytes:
+                got = counts_host.numpy()
+                if world == 1:
+                    got = got[:nslots][ix.slot_perm()]
+                files_ok = bool(np.array_equal(got[:nkeys], device_counts[:nkeys])) and rb == nreads * READ_LEN
+            e2e = {"value": float(hp.item()) / float(te.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(ix.h2d_bytes_last), "d2h_bytes_per_step": int(nslots if world == 1 else nkeys),
+                   "counts_equal_device_path": files_ok, "file_bytes_per_step": int(file_bytes), "host_threads": threads,
+                   "input": "two plain four-line FASTQ files per rank on tmpfs through vg_count_files "
+                            "(the same kind of file the reference arm reads)"}
+        finally:
+            rm_tree(tmpdir)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- roofline of the count pass ------------------------------------------------------------------------
     h = hits / max(positions, 1)
     b_alg = 1.0 + 32.0 + 32.0 * h
     achieved = positions * b_alg / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
-    rnd_gbs = rnd_sec = None
+    rnd_gbs = rnd_sec = h2d_gbs = None
     if rank == 0:
         try:
             free, _ = torch.cuda.mem_get_info()
             tb = min(8 << 30, int(free * 0.5))
             rnd_gbs, rnd_sec = ctx.probe_random_sectors(tb, 64)
         except Exception as ex:  # diagnostic only
-            rnd_gbs = rnd_sec = None
             sys.stderr.write(f"random-sector probe failed: {ex}\n")
+        try:  # the H2D ceiling of this box for one GPU: a plain pinned copy
+            nb = min(host_bytes, 1 << 30)
+            tgt = torch.empty(nb, dtype=torch.uint8, device=dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tgt.copy_(lines_host[:nb], non_blocking=True)
+            c0.record(stream)
+            for _ in range(3):
+                tgt.copy_(lines_host[:nb], non_blocking=True)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            h2d_gbs = 3 * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            del tgt
+        except Exception as ex:
+            sys.stderr.write(f"H2D probe failed: {ex}\n")
+    if e2e is not None:
+        e2e["h2d_ceiling_gbs_one_gpu"] = h2d_gbs
+    if e2e_staged is not None:
+        e2e_staged["h2d_ceiling_gbs_one_gpu"] = h2d_gbs
     probes_per_s = positions / (kernel_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(ix.partitions > 0), "peak_source": peak_src, "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
+                "traffic": ncu_traffic(ix.partitions > 0), "peak_source": peak_src,
+                "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
                            else "vg::count_kernel (K1+K2+K3 fused)"),
                 "kernel_ms": kernel_ms, "bytes_per_position": b_alg, "hit_fraction": h,
                 "random_sector_peak_gbs": rnd_gbs,
-                "frac_of_random_sector_peak": (probes_per_s * (1 + h) / rnd_sec) if rnd_sec else None}
+                "frac_of_random_sector_peak": (probes_per_s * (1 + h) / rnd_sec) if rnd_sec else None,
+                "phases_ms": phases}
 
-    # ---- CPU baseline beside it (rank 0, N == 1) ---------------------------------------------
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    # ---- CPU baseline beside it + the same sample through the CUDA path (rank 0) -----------------------------
+    cpu = parity = None
+    if rank == 0 and want_cpu and not a.no_cpu_baseline:
         lines_np = lines_host.numpy()
-        r = reference_run(a, keys_np, lines_np, steps=1, warmup=0, want_counts=True)
+        r = reference_run(a.cpu_sample_reads, sample_keys_np, lines_np, steps=1, warmup=0, want_counts=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        # the same sample through the CUDA path must give the reference's counts exactly
+    if want_cpu and not a.no_cpu_baseline and not sharded:
+        # the same reads through the CUDA path must give the reference's counts exactly (rank 0 checks; with N > 1
+        # the other ranks submit nothing and the reduce is part of what is checked)
+        nr = min(a.cpu_sample_reads, host_bytes // rec)
         ix.begin()
-        ix.submit(lines_np[: r["nreads"] * (READ_LEN + 1)])
-        mine, mp, _ = ix.end()
-        parity = {"sample_counts_bit_exact": bool(np.array_equal(mine, r["counts"])),
-                  "sample_positions_equal": bool(mp == r["positions"])}
+        if rank == 0:
+            ix.submit_ptr(lines_host.data_ptr(), nr * rec)
+        if comm is not None:
+            mine = comm.allreduce_counts(ix, want_host=True)
+            mp = ix.end(want_counts=False)[1]
+        elif world > 1:
+            ix.extract_device(out32.data_ptr(), 4)
+            mine = vdist.reduce_counts(out32).cpu().numpy()
+            mp = ix.end(want_counts=False)[1]
+        else:
+            mine, mp, _ = ix.end()
+        if rank == 0 and cpu is not None:
+            if sample_idx is not None:
+                mine = mine[sample_idx.cpu().numpy()]
+            parity = {"sample_counts_bit_exact": bool(np.array_equal(mine, r["counts"])),
+                      "sample_positions_equal": bool(mp == r["positions"]),
+                      "index_entries_checked": int(sample_keys_np.size)}
 
+    line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "index_kmers": nkeys, "index_table_bytes": ix.table_bytes, "table_partitions": ix.partitions,
-                           "reads_per_gpu": nbytes // (READ_LEN + 1), "positions_per_gpu": positions,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": workload_name(w), "index_kmers": nkeys, "index_table_bytes": ix.table_bytes,
+                           "table_partitions": ix.partitions, "index_duplicate_kmers": ix.duplicates,
+                           "reads_per_gpu": nbytes // rec, "positions_per_gpu": positions,
+                           "coverage_per_gpu": cov_rank,
                            "parallelism": (f"reads sharded x{world}, index "
                                            + (f"sharded x{world} (k-mer all-to-all fused into the scatter over NVLink, "
                                               f"{len(round_cuts)} rounds)" if sharded else f"replicated, counts reduced by {reduce_how}")
                                            if world > 1 else "1 GPU"),
                            "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush",
-                           "host_binding": numa},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-                        "d2h_bytes_per_step": int(nkeys + 16), "counts_equal_device_path": e2e_counts_ok},
-                "gpu_launches": int(launches_timed) + steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                           "generate_s": t_gen, "index_build_s": t_build},
+                "e2e": e2e if e2e is not None else e2e_staged, "e2e_staged": e2e_staged,
+                "gpu_launches": int(launches_timed), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "parity": parity}
-        print(json.dumps(line), flush=True)
     if world > 1:
         barrier()  # nobody unmaps a peer's arena while it is still in use
     ix.close()
     if comm is not None:
         comm.close()
     ctx.close()
+    del lines_dev, lines_host, counts_host, out8, out32
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="chr20", choices=sorted(SPECS))
+    ap.add_argument("--genome-mb", type=int, default=None)
+    ap.add_argument("--variants", type=int, default=None)
+    ap.add_argument("--coverage", type=float, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank counts its own --coverage sample; strong: one --coverage sample cut over the ranks")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files-e2e", action="store_true")
+    ap.add_argument("--human", default="auto", choices=["auto", "on", "off"],
+                    help="add the human-scale section to the line (auto: at N == 8)")
+    ap.add_argument("--human-coverage", type=float, default=30.0)
+    ap.add_argument("--buffer-mb", type=int, default=64)
+    ap.add_argument("--load-factor", type=float, default=0.0)
+    ap.add_argument("--kmer", type=int, default=27, help="k (BASELINE configs use the default 27)")
+    ap.add_argument("--index", default="replicated", choices=["replicated", "sharded"],
+                    help="N > 1: a replica of the index per GPU (default) or one index cut over the GPUs")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N > 1, replicated: how counts are combined")
+    ap.add_argument("--round-mb", type=int, default=1024, help="sharded index: bases per rank and round")
+    a = ap.parse_args()
+    global K
+    K = a.kmer
+    rank, world, local = dist_info()
+    steps, warmup = a.steps, max(a.warmup, 3 if a.impl == "b200" else a.warmup)
+    w = dict(SPECS[a.config])
+    for key, val in (("genome_mb", a.genome_mb), ("variants", a.variants), ("coverage", a.coverage)):
+        if val is not None:
+            w[key] = val
+    L = w["genome_mb"] * 1_000_000
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        dev = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
+        if L > 512_000_000:
+            raise SystemExit("bench.py --impl reference: the reference's host map does not hold a human-scale index here; "
+                             "use the default workload")
+        ref, alt, pos, vlen, keys = make_graph(dev, L, w["variants"], seed=20261017)
+        keys_np = keys.cpu().numpy().view(np.uint64)
+        nreads = a.cpu_sample_reads
+        cov = nreads * READ_LEN / L * 1.02 + 0.01
+        lines_np = make_reads(dev, ref, alt, pos, vlen, min(cov, w["coverage"]), seed=1000).cpu().numpy()
+        del ref, alt, pos, vlen, keys
+        r = reference_run(a.cpu_sample_reads, keys_np, lines_np, steps, a.warmup)
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+                "warmup": a.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+                "scaling": a.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "impl": "reference",
+                "config": {"workload": workload_name(w), "index_kmers": int(keys_np.size)},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- our arm -----------------------------------------------------------------------------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; varigraph_b200 has no CPU path (use --impl reference)")
+    import torch.distributed as dist
+    from varigraph_b200 import capi
+    from varigraph_b200 import dist as vdist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:
+        numa = vdist.bind_to_gpu_numa(local)  # before any pinned allocation: staging memory next to the GPU
+        dist.init_process_group("nccl", device_id=dev)
+
+    big = L > 512_000_000
+    line = measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist,
+                   want_files_e2e=not a.no_files_e2e and not big, want_cpu=(world == 1 or big),
+                   staged_cap_bytes=(2 << 30) if big else None)
+    if line is not None:
+        line["config"]["host_binding"] = numa
+    # ---- the north-star configuration beside the driver's line: human-scale graph, one 30x sample over the box ----
+    if a.config == "chr20" and (a.human == "on" or (a.human == "auto" and world == 8)):
+        hw = dict(SPECS["human"], coverage=a.human_coverage, strong=True)
+        human = None
+        try:
+            hl = measure(a, hw, max(2, min(steps, 3)), 1, rank, world, local, dist, capi, vdist, want_files_e2e=False,
+                         want_cpu=True, staged_cap_bytes=2 << 30)
+            if hl is not None:
+                human = {k: hl[k] for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config",
+                                            "e2e_staged", "roofline", "cpu_baseline", "parity", "gpu_launches", "clocks")}
+        except Exception as ex:  # the driver's line must survive whatever happens here
+            human = {"error": f"{type(ex).__name__}: {ex}"}
+        if line is not None:
+            line["human_scale"] = human
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

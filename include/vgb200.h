@@ -54,11 +54,23 @@ int vg_ctx_set_stream(vg_ctx* ctx, void* cuda_stream);
  * Built once per load() (src/varigraph.cpp:65-83).  load_factor in (0, 0.9], 0 = default. */
 int vg_index_create(vg_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
                     vg_index** out);
+/* The same from keys that already sit in the memory of ctx's GPU (a graph loaded or generated there): no
+ * host copy of the key array is ever made -- 16 GB per process at human scale (2e9 k-mers). */
+int vg_index_create_device(vg_ctx* ctx, const uint64_t* dev_keys, uint64_t n, uint32_t k, double load_factor,
+                           vg_index** out);
 int vg_index_destroy(vg_index* ix);
 uint64_t vg_index_size(const vg_index* ix);          /* n */
 uint64_t vg_index_table_bytes(const vg_index* ix);   /* bytes of the slot table in HBM */
 uint32_t vg_index_partitions(const vg_index* ix);    /* table slices of the partitioned probe, 0 = direct */
 uint64_t vg_index_launches(const vg_index* ix);      /* kernels launched for this index so far */
+uint64_t vg_index_duplicates(const vg_index* ix);    /* keys given more than once at create (they share a slot) */
+uint64_t vg_count_h2d_bytes(const vg_index* ix);     /* bytes copied host -> device since the last vg_count_begin */
+/* Diagnostic: with timing on, every scatter launch and every sweep over the table slices is bracketed by CUDA
+ * events on the context stream and waited for (so it serialises the host: not for production runs);
+ * vg_index_timing returns the device milliseconds and launch counts accumulated since vg_index_set_timing. */
+int vg_index_set_timing(vg_index* ix, int on);
+int vg_index_timing(const vg_index* ix, double* scatter_ms, double* sweep_ms, uint64_t* scatter_launches,
+                    uint64_t* sweeps);
 
 /* ---- one sample's count phase ----------------------------------------------------------
  * Together these replace FastqKmer::build_fastq_index (src/fastq_kmer.cpp:41-187) /
@@ -101,6 +113,23 @@ int vg_count_flush(vg_index* ix);
 /* Waits for the sample's kernels, then writes c in the key order given at create.
  * c_out (n bytes, host), positions, hits may each be NULL. */
 int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hits);
+
+/* The same result without the gather into key order.  An index of 8 MB or more keeps its counters in ONE dense
+ * u8 vector, one entry per distinct k-mer, in the order the k-mers sit in the device table ("slot order"); the
+ * counting kernels accumulate straight into it, so a sample's result exists the moment its last kernel ends.
+ *   vg_index_slots      m, the length of that vector (<= n; == n when the keys are distinct)
+ *   vg_index_slot_perm  perm[i] = position of keys[i] in it (n entries, fixed for the life of the index;
+ *                       0xffffffff for a key no read can produce, whose count is always 0).  The host side
+ *                       permutes its pointers into the map once per graph (what DeviceGraphIndex does with
+ *                       mGraphKmerHashHapStrMap's entries) and afterwards writes c[perm[i]] back per sample.
+ *   vg_count_end_slots  vg_count_end, with c in slot order (m bytes)
+ *   vg_count_slots_device  implies vg_count_flush; *dev_counts = the vector on the device (m bytes, valid until
+ *                       the next vg_count_begin, ordered after the sample's kernels on the context stream)
+ * (a tiny index that is probed directly reports slot order == key order).  Not for sharded indexes. */
+uint64_t vg_index_slots(const vg_index* ix);
+int vg_index_slot_perm(vg_index* ix, uint32_t* perm_out);
+int vg_count_end_slots(vg_index* ix, uint8_t* c_slots_out, uint64_t* positions, uint64_t* hits);
+int vg_count_slots_device(vg_index* ix, const uint8_t** dev_counts);
 
 /* Device-side result for a multi-GPU reduce: counts in key order as u8 (elem_bytes 1) or u32
  * (elem_bytes 4, what ncclAllReduce(sum) wants) into dev_out, on `cuda_stream`. */

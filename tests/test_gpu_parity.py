@@ -274,6 +274,48 @@ def test_partitioned_overflow_and_saturation(ctx, vglib, oracle, force_partition
     ix.close()
 
 
+@pytest.mark.parametrize("partitioned", [True, False])
+def test_slot_order_result(ctx, vglib, oracle, force_partition, partitioned):
+    """vg_count_end_slots + vg_index_slot_perm give the key-order counts back (duplicate and never-produced
+    keys included), two samples in a row (the count vector is re-zeroed by vg_count_begin), and the device
+    histogram over the slot-order vector with per-key flags equals numpy's."""
+    if partitioned:
+        force_partition()
+    k = 27
+    g = synth.make_genome(90_000, seed=77)
+    pos = oracle.positions(g[:40_000], k)
+    keys = np.unique(pos[pos != NOKMER])
+    keys = np.concatenate([keys, keys[:5]])  # duplicate keys share a slot
+    ix = vglib.Index(ctx, keys, k)
+    assert (ix.partitions > 0) == partitioned
+    perm = ix.slot_perm()
+    m = ix.slots
+    assert perm.size == keys.size and perm.max() < m and m <= keys.size
+    if partitioned:
+        assert m == keys.size - 5 and np.unique(perm).size == m and np.array_equal(perm[-5:], perm[:5])
+    for seed in (78, 79):
+        lines = synth.random_reads_lines(3000, 150, g, seed=seed)
+        want, wpos, whits = oracle.count_lines(keys, lines, k)
+        ix.begin()
+        ix.submit(lines)
+        flags = (np.arange(keys.size) % 3 == 0).astype(np.uint8)
+        flags[-5:] = flags[:5]
+        ix.set_flags(flags)
+        hist = ix.histogram()
+        cs, positions, hits = ix.end_slots()
+        assert cs.size == m and positions == wpos
+        assert np.array_equal(cs[perm], want)
+        sel = np.zeros(m, dtype=bool)
+        sel[perm[flags != 0]] = True
+        assert np.array_equal(hist, np.bincount(cs[sel], minlength=256).astype(np.uint64))
+        ix.set_flags(None)
+        ix.begin()
+        ix.submit(lines)
+        ck, _, _ = ix.end()
+        assert np.array_equal(ck, want)
+    ix.close()
+
+
 def test_partitioned_equals_direct_at_scale(vglib, monkeypatch):
     """A table far larger than L2: the default (partitioned) path and forced direct probing agree."""
     import torch

@@ -41,11 +41,16 @@ def _load() -> ctypes.CDLL:
         "vg_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
         "vg_probe_random_sectors": (c_int, [c_void_p, c_uint64, c_uint32, P(c_double), P(c_double)]),
         "vg_index_create": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, P(c_void_p)]),
+        "vg_index_create_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, P(c_void_p)]),
         "vg_index_destroy": (c_int, [c_void_p]),
         "vg_index_size": (c_uint64, [c_void_p]),
         "vg_index_table_bytes": (c_uint64, [c_void_p]),
         "vg_index_partitions": (c_uint32, [c_void_p]),
         "vg_index_launches": (c_uint64, [c_void_p]),
+        "vg_index_duplicates": (c_uint64, [c_void_p]),
+        "vg_count_h2d_bytes": (c_uint64, [c_void_p]),
+        "vg_index_set_timing": (c_int, [c_void_p, c_int]),
+        "vg_index_timing": (c_int, [c_void_p, P(c_double), P(c_double), P(c_uint64), P(c_uint64)]),
         "vg_count_begin": (c_int, [c_void_p]),
         "vg_count_submit": (c_int, [c_void_p, c_void_p, c_uint64]),
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
@@ -57,6 +62,10 @@ def _load() -> ctypes.CDLL:
         "vg_count_histogram": (c_int, [c_void_p, c_void_p]),
         "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
         "vg_count_extract_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+        "vg_index_slots": (c_uint64, [c_void_p]),
+        "vg_index_slot_perm": (c_int, [c_void_p, c_void_p]),
+        "vg_count_end_slots": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
+        "vg_count_slots_device": (c_int, [c_void_p, P(c_void_p)]),
         "vg_count_stats": (c_int, [c_void_p, P(c_uint64), P(c_uint64)]),
         "vg_encode_positions_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p]),
         "vg_encode_positions": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
@@ -204,10 +213,15 @@ class Index:
     With `comm` the index is sharded over the group's GPUs (vg_index_create_sharded): flush() and
     end() are then collective and a round takes at most `round_bytes` of bases (see room())."""
 
-    def __init__(self, ctx: Context, keys: np.ndarray, k: int, load_factor: float = 0.0, comm: "Comm" = None,
+    def __init__(self, ctx: Context, keys, k: int, load_factor: float = 0.0, comm: "Comm" = None,
                  round_bytes: int = 0):
-        keys = np.ascontiguousarray(keys, dtype=np.uint64)
         h = c_void_p()
+        if isinstance(keys, tuple):  # (device pointer, n): keys resident in the memory of ctx's GPU
+            dev_ptr, n = keys
+            _chk(lib.vg_index_create_device(ctx._h, c_void_p(dev_ptr), n, k, load_factor, byref(h)))
+            self._h, self.ctx, self.comm, self.n, self.k = h, ctx, None, int(n), k
+            return
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
         if comm is None:
             _chk(lib.vg_index_create(ctx._h, _ptr(keys), keys.size, k, load_factor, byref(h)))
         else:
@@ -236,6 +250,26 @@ class Index:
     @property
     def launches(self) -> int:
         return int(lib.vg_index_launches(self._h))
+
+    @property
+    def duplicates(self) -> int:
+        return int(lib.vg_index_duplicates(self._h))
+
+    @property
+    def h2d_bytes_last(self) -> int:
+        return int(lib.vg_count_h2d_bytes(self._h))
+
+    def set_timing(self, on: bool) -> None:
+        _chk(lib.vg_index_set_timing(self._h, 1 if on else 0))
+
+    def timing(self) -> dict:
+        """Per-launch device milliseconds of the two phases since set_timing(True)."""
+        sc, sw, ns, nw = c_double(0), c_double(0), c_uint64(0), c_uint64(0)
+        _chk(lib.vg_index_timing(self._h, byref(sc), byref(sw), byref(ns), byref(nw)))
+        return {"scatter_ms_total": sc.value, "scatter_launches": int(ns.value), "sweep_ms_total": sw.value,
+                "sweeps": int(nw.value),
+                "scatter_ms_per_sample": sc.value / max(1, int(nw.value)) if nw.value else sc.value,
+                "sweep_ms_per_sweep": sw.value / max(1, int(nw.value))}
 
     @property
     def fastq_blocks(self) -> int:
@@ -282,6 +316,30 @@ class Index:
         pos, hits = c_uint64(0), c_uint64(0)
         _chk(lib.vg_count_end(self._h, _ptr(out) if want_counts else None, byref(pos), byref(hits)))
         return out, int(pos.value), int(hits.value)
+
+    @property
+    def slots(self) -> int:
+        """Length of the slot-order count vector (vg_index_slots)."""
+        return int(lib.vg_index_slots(self._h))
+
+    def slot_perm(self) -> np.ndarray:
+        """perm[i] = position of keys[i] in the slot-order count vector (0xffffffff: never counted)."""
+        out = np.empty(self.n, dtype=np.uint32)
+        _chk(lib.vg_index_slot_perm(self._h, _ptr(out)))
+        return out
+
+    def end_slots(self, want_counts: bool = True):
+        """-> (counts u8[slots] in slot order or None, positions, hits)"""
+        out = np.empty(self.slots, dtype=np.uint8) if want_counts else None
+        pos, hits = c_uint64(0), c_uint64(0)
+        _chk(lib.vg_count_end_slots(self._h, _ptr(out) if want_counts else None, byref(pos), byref(hits)))
+        return out, int(pos.value), int(hits.value)
+
+    def slots_device(self) -> int:
+        """Device pointer of the slot-order count vector after a flush (asynchronous on the context stream)."""
+        p = c_void_p()
+        _chk(lib.vg_count_slots_device(self._h, byref(p)))
+        return int(p.value or 0)
 
     def stats(self):
         pos, hits = c_uint64(0), c_uint64(0)

@@ -120,6 +120,40 @@ static int part_setup(vg_index* ix) {
         cudaGetLastError();
         return VG_OK;
     }
+    {   // slot order: rank_base (exclusive scan of the bucket occupancies), the count vector, key -> slot
+        const uint32_t nblocks = (uint32_t)((ix->view.nbuckets + 1023ull) / 1024);
+        uint32_t* d_sums = nullptr;
+        unsigned long long* d_total = nullptr;
+        unsigned long long total = 0;
+        e = cudaMalloc((void**)&ix->view.rank_base, (size_t)ix->view.nbuckets * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_sums, ((size_t)nblocks + 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_total, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = vg::launch_rank_scan(ix->view, d_sums, d_total, c->compute_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, c->compute_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute_stream);
+        cudaFree(d_sums);
+        cudaFree(d_total);
+        ix->m_slots = total;
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->view.cvec, (size_t)((total + 31) & ~15ull));
+        if (e == cudaSuccess) e = cudaMemsetAsync(ix->view.cvec, 0, (size_t)((total + 31) & ~15ull), c->compute_stream);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_perm, std::max<uint64_t>(ix->n, 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = vg::launch_slot_perm(ix->view, ix->d_key56, ix->n, ix->d_perm, c->compute_stream);
+        if (e != cudaSuccess) {
+            cudaFree(ps.view.keybuf);
+            cudaFree(ps.view.cursor);
+            cudaFree(ps.view.ctr);
+            cudaFree(ix->view.rank_base);
+            cudaFree(ix->view.cvec);
+            cudaFree(ix->d_perm);
+            ix->view.rank_base = nullptr;
+            ix->view.cvec = nullptr;
+            ix->d_perm = nullptr;
+            ix->m_slots = 0;
+            ps = PartState();
+            cudaGetLastError();
+            return VG_OK;
+        }
+    }
     ps.enabled = true;
     // Presence pre-filter: 4 bits per key (measured best on B200: 30 MB for the chr20 index beats both
     // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
@@ -143,14 +177,35 @@ static int part_setup(vg_index* ix) {
             }
         }
     }
+    // the keys themselves are no longer needed: every later lookup by key goes through d_perm
+    CU(cudaStreamSynchronize(c->compute_stream));
+    cudaFree(ix->d_key56);
+    ix->d_key56 = nullptr;
     return VG_OK;
+}
+
+// vg_index_set_timing: bracket a phase with events and add its device time up (synchronises: diagnostic only)
+static void phase_begin(PartState& ps, cudaStream_t s) {
+    if (ps.timing) cudaEventRecord(ps.ev0, s);
+}
+static void phase_end(PartState& ps, cudaStream_t s, double& acc, uint64_t& n) {
+    if (!ps.timing) return;
+    float ms = 0;
+    if (cudaEventRecord(ps.ev1, s) == cudaSuccess && cudaEventSynchronize(ps.ev1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ps.ev0, ps.ev1) == cudaSuccess) {
+        acc += ms;
+        n += 1;
+    }
+    cudaGetLastError();
 }
 
 static int part_flush(vg_index* ix, cudaStream_t s) {
     PartState& ps = ix->part;
     if (ix->sharded) return VG_OK;  // a sharded round ends only in the collective calls (vg_count_flush / _end)
     if (!ps.enabled || ps.pending == 0) return VG_OK;
+    phase_begin(ps, s);
     CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+    phase_end(ps, s, ps.ms_sweep, ps.n_sweep);
     ix->launches += ps.view.P + 1;
     ps.pending = 0;
     return VG_OK;
@@ -207,7 +262,9 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
             room = (int64_t)(ps.round_keys / tile_bytes);
         }
         const int64_t nt = std::min<int64_t>(T - t, room);
+        phase_begin(ps, s);
         CU(vg::launch_scatter(ix->view, ps.view, ps.filter, d_bases, nbytes, t, nt, &ix->d_misc->stats, c->nsm, s, d_skip));
+        phase_end(ps, s, ps.ms_scatter, ps.n_scatter);
         ix->launches += 1;
         ps.pending += (uint64_t)nt * tile_bytes;
         t += nt;
@@ -234,6 +291,7 @@ int vg::enqueue_raw_piece(vg_index* ix, int si, uint64_t len, vg::FastqFileState
     vg_ctx* c = ix->ctx;
     vg::StageSlot& sl = c->ring[(size_t)si];
     CU(cudaMemcpyAsync(sl.d_buf, sl.h_pin, len, cudaMemcpyHostToDevice, c->copy_stream));
+    ix->h2d_bytes += len;
     CU(cudaEventRecord(sl.copied, c->copy_stream));
     CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
     CU(vg::launch_fastq_block(sl.d_buf, (uint32_t)len, c->d_masked, c->fq, d_file, block_no, c->compute_stream));
@@ -247,6 +305,7 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len, const
     vg_ctx* c = ix->ctx;
     vg::StageSlot& sl = c->ring[(size_t)si];
     if (src) {
+        ix->h2d_bytes += len;
         CU(cudaMemcpyAsync(sl.d_buf, src, len, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(sl.copied, c->copy_stream));
         CU(cudaStreamWaitEvent(c->compute_stream, sl.copied, 0));
@@ -268,6 +327,13 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len, const
     }
     sl.busy = true;
     return VG_OK;
+}
+
+// Counts in the key order given at create, on the device: a gather through d_perm out of the count vector
+// (partitioned) or one probe per key (direct probing of a tiny table, counts in the slots).
+cudaError_t vg::counts_in_key_order(vg_index* ix, void* d_out, int elem_bytes, cudaStream_t s) {
+    if (ix->view.cvec) return vg::launch_gather_counts(ix->view.cvec, ix->d_perm, nullptr, ix->n, d_out, elem_bytes, s);
+    return vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, d_out, elem_bytes, s);
 }
 
 extern "C" {
@@ -410,7 +476,9 @@ int vg_ctx_synchronize(vg_ctx* c) {
 // ---------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------
-int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor, vg_index** out) {
+// keys: host memory, or (keys_on_device) device memory of ctx's GPU
+static int index_create(vg_ctx* c, const uint64_t* keys, bool keys_on_device, uint64_t n, uint32_t k, double load_factor,
+                        vg_index** out) {
     if (!c || !out || (!keys && n)) return fail(VG_E_INVALID, "vg_index_create: NULL argument");
     *out = nullptr;
     if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28 (reference asserts k<=28, src/kmer.cpp:124)", k);
@@ -419,7 +487,8 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     DeviceGuard g(c->device);
     uint64_t nb64 = (uint64_t)((double)n / (4.0 * load_factor)) + 1;
     if (nb64 < 64) nb64 = 64;
-    if (nb64 >= 0xffffffffull) return fail(VG_E_INVALID, "index of %llu keys needs too many buckets", (unsigned long long)n);
+    if (nb64 >= 0xffffffffull || n >= 0xffffffffull)
+        return fail(VG_E_INVALID, "index of %llu keys needs too many buckets", (unsigned long long)n);
 
     vg_index* ix = new vg_index();
     ix->ctx = c;
@@ -449,25 +518,39 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     cudaStream_t s = c->compute_stream;
     CUB(vg::launch_table_fill_empty(ix->view.slots, nslots, s));
 
-    // keys -> key56, staged through a bounded host buffer
-    const uint64_t piece = 1ull << 22;
-    std::vector<uint64_t> tmp((size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
-    for (uint64_t off = 0; off < n; off += piece) {
-        uint64_t m = std::min<uint64_t>(piece, n - off);
-        for (uint64_t i = 0; i < m; ++i) {
-            uint64_t key = keys[off + i];
-            if ((key & 0xffu) != k)
-                return bail(fail(VG_E_INVALID, "keys[%llu]=0x%llx: low byte is not k=%u (src/kmer.cpp:138)",
-                                 (unsigned long long)(off + i), (unsigned long long)key, k));
-            uint64_t h = key >> 8;
-            if (h > ix->view.mask)
-                return bail(fail(VG_E_INVALID, "keys[%llu]: hash exceeds 2k bits", (unsigned long long)(off + i)));
-            tmp[(size_t)i] = h;
+    if (keys_on_device) {  // validated and un-hashed where they lie
+        unsigned long long* d_bad = nullptr;
+        unsigned long long bad = ~0ull;
+        CUB(cudaMalloc((void**)&d_bad, sizeof bad));
+        cudaError_t e = cudaMemcpyAsync(d_bad, &bad, sizeof bad, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = vg::launch_keys_to_key56(keys, n, k, ix->view.mask, ix->d_key56, d_bad, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_bad);
+        CUB(e);
+        if (bad != ~0ull)
+            return bail(fail(VG_E_INVALID, "keys[%llu]: low byte is not k=%u or the hash exceeds 2k bits (src/kmer.cpp:138)", bad, k));
+    } else {
+        // keys -> key56, staged through a bounded host buffer
+        const uint64_t piece = 1ull << 22;
+        std::vector<uint64_t> tmp((size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
+        for (uint64_t off = 0; off < n; off += piece) {
+            uint64_t m = std::min<uint64_t>(piece, n - off);
+            for (uint64_t i = 0; i < m; ++i) {
+                uint64_t key = keys[off + i];
+                if ((key & 0xffu) != k)
+                    return bail(fail(VG_E_INVALID, "keys[%llu]=0x%llx: low byte is not k=%u (src/kmer.cpp:138)",
+                                     (unsigned long long)(off + i), (unsigned long long)key, k));
+                uint64_t h = key >> 8;
+                if (h > ix->view.mask)
+                    return bail(fail(VG_E_INVALID, "keys[%llu]: hash exceeds 2k bits", (unsigned long long)(off + i)));
+                tmp[(size_t)i] = h;
+            }
+            CUB(cudaMemcpyAsync(ix->d_key56 + off, tmp.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            CUB(cudaStreamSynchronize(s));
         }
-        CUB(cudaMemcpyAsync(ix->d_key56 + off, tmp.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        CUB(cudaStreamSynchronize(s));
+        CUB(vg::launch_unhash(ix->d_key56, n, ix->view.mask, s));
     }
-    CUB(vg::launch_unhash(ix->d_key56, n, ix->view.mask, s));
     CUB(vg::launch_insert(ix->view, ix->d_key56, n, &ix->d_misc->report, s));
     vg::DeviceMisc misc;
     CUB(cudaMemcpyAsync(&misc, ix->d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));
@@ -481,6 +564,13 @@ int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, dou
     return VG_OK;
 }
 
+int vg_index_create(vg_ctx* c, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor, vg_index** out) {
+    return index_create(c, keys, false, n, k, load_factor, out);
+}
+int vg_index_create_device(vg_ctx* c, const uint64_t* dev_keys, uint64_t n, uint32_t k, double load_factor, vg_index** out) {
+    return index_create(c, dev_keys, true, n, k, load_factor, out);
+}
+
 int vg_index_destroy(vg_index* ix) {
     if (!ix) return VG_OK;
     DeviceGuard g(ix->ctx->device);
@@ -489,7 +579,10 @@ int vg_index_destroy(vg_index* ix) {
         cudaFree(ix->view.slots);
         cudaFree(ix->d_counts);
         cudaFree(ix->part.view.keybuf);
+        cudaFree(ix->view.rank_base);
+        cudaFree(ix->view.cvec);
     }
+    cudaFree(ix->d_perm);
     cudaFree(ix->d_key56);
     cudaFree(ix->d_idx);
     cudaFree(ix->d_combined);
@@ -499,11 +592,37 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->part.view.cursor);
     cudaFree(ix->part.view.ctr);
     cudaFree(ix->part.d_filter);
+    if (ix->part.ev0) cudaEventDestroy(ix->part.ev0);
+    if (ix->part.ev1) cudaEventDestroy(ix->part.ev1);
     delete ix;
     return VG_OK;
 }
 
 uint64_t vg_index_size(const vg_index* ix) { return ix ? ix->n : 0; }
+uint64_t vg_index_duplicates(const vg_index* ix) { return ix ? ix->duplicates : 0; }
+uint64_t vg_count_h2d_bytes(const vg_index* ix) { return ix ? ix->h2d_bytes : 0; }
+
+int vg_index_set_timing(vg_index* ix, int on) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    PartState& ps = ix->part;
+    DeviceGuard g(ix->ctx->device);
+    if (on && !ps.ev0) {
+        CU(cudaEventCreate(&ps.ev0));
+        CU(cudaEventCreate(&ps.ev1));
+    }
+    ps.timing = on != 0;
+    ps.ms_scatter = ps.ms_sweep = 0;
+    ps.n_scatter = ps.n_sweep = 0;
+    return VG_OK;
+}
+int vg_index_timing(const vg_index* ix, double* scatter_ms, double* sweep_ms, uint64_t* scatter_launches, uint64_t* sweeps) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    if (scatter_ms) *scatter_ms = ix->part.ms_scatter;
+    if (sweep_ms) *sweep_ms = ix->part.ms_sweep;
+    if (scatter_launches) *scatter_launches = ix->part.n_scatter;
+    if (sweeps) *sweeps = ix->part.n_sweep;
+    return VG_OK;
+}
 uint32_t vg_index_partitions(const vg_index* ix) { return ix && ix->part.enabled ? ix->part.view.P : 0; }
 uint64_t vg_index_launches(const vg_index* ix) { return ix ? ix->launches : 0; }
 uint64_t vg_index_table_bytes(const vg_index* ix) { return ix ? 32ull * ix->view.nbuckets : 0; }
@@ -515,8 +634,10 @@ int vg_count_begin(vg_index* ix) {
     if (!ix) return fail(VG_E_INVALID, "index is NULL");
     vg_ctx* c = ix->ctx;
     DeviceGuard g(c->device);
-    CU(vg::launch_clear_counts(ix->view, c->compute_stream));
+    if (ix->view.cvec) CU(cudaMemsetAsync(ix->view.cvec, 0, (size_t)ix->m_slots, c->compute_stream));  // the table itself is read-only
+    else CU(vg::launch_clear_counts(ix->view, c->compute_stream));
     CU(cudaMemsetAsync(&ix->d_misc->stats, 0, sizeof(vg::CountStats), c->compute_stream));
+    ix->h2d_bytes = 0;
     if (ix->part.enabled) {
         CU(cudaMemsetAsync(ix->part.view.cursor, 0, ix->part.view.P * sizeof(unsigned long long), c->compute_stream));
         ix->part.pending = 0;
@@ -637,7 +758,7 @@ int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* c
         CU(cudaStreamSynchronize(c->compute_stream));
     }
     if (ix->sharded) return fail(VG_E_STATE, "sharded index: the counts of all keys come from vg_count_end");
-    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, dev_out, elem_bytes, s));
+    CU(vg::counts_in_key_order(ix, dev_out, elem_bytes, s));
     return VG_OK;
 }
 
@@ -651,7 +772,19 @@ int vg_index_set_flags(vg_index* ix, const uint8_t* flags) {
         ix->d_flags = nullptr;
         return VG_OK;
     }
-    if (!ix->d_flags) CU(cudaMalloc((void**)&ix->d_flags, std::max<uint64_t>(ix->n, 4)));
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: take the histogram of vg_count_end's counts");
+    if (!ix->d_flags) CU(cudaMalloc((void**)&ix->d_flags, std::max<uint64_t>(std::max(ix->n, ix->m_slots), 4)));
+    if (ix->view.cvec) {  // keep the flags in slot order, next to the counts they select
+        uint8_t* d_tmp = nullptr;
+        CU(cudaMalloc((void**)&d_tmp, std::max<uint64_t>(ix->n, 4)));
+        cudaError_t e = cudaMemcpyAsync(d_tmp, flags, ix->n, cudaMemcpyHostToDevice, c->compute_stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ix->d_flags, 0, (size_t)ix->m_slots, c->compute_stream);
+        if (e == cudaSuccess) e = vg::launch_scatter_bytes(d_tmp, ix->d_perm, ix->n, ix->d_flags, c->compute_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute_stream);
+        cudaFree(d_tmp);
+        if (e != cudaSuccess) return fail(VG_E_CUDA, "vg_index_set_flags: %s", cudaGetErrorString(e));
+        return VG_OK;
+    }
     CU(cudaMemcpyAsync(ix->d_flags, flags, ix->n, cudaMemcpyHostToDevice, c->compute_stream));
     CU(cudaStreamSynchronize(c->compute_stream));
     return VG_OK;
@@ -666,8 +799,12 @@ int vg_count_histogram(vg_index* ix, uint64_t* hist256) {
     if (rc) return rc;
     if (ix->sharded) return fail(VG_E_STATE, "sharded index: take the histogram of vg_count_end's counts");
     if (!ix->d_hist) CU(cudaMalloc((void**)&ix->d_hist, 256 * sizeof(unsigned long long)));
-    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
-    CU(vg::launch_histogram(ix->d_counts, ix->d_flags, ix->n, ix->d_hist, c->compute_stream));
+    if (ix->view.cvec) {  // straight over the count vector: one entry per distinct k-mer of the index
+        CU(vg::launch_histogram(ix->view.cvec, ix->d_flags, ix->m_slots, ix->d_hist, c->compute_stream));
+    } else {
+        CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
+        CU(vg::launch_histogram(ix->d_counts, ix->d_flags, ix->n, ix->d_hist, c->compute_stream));
+    }
     unsigned long long h[256];
     CU(cudaMemcpyAsync(h, ix->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->compute_stream));
     CU(cudaStreamSynchronize(c->compute_stream));
@@ -690,8 +827,60 @@ int vg_count_end(vg_index* ix, uint8_t* c_out, uint64_t* positions, uint64_t* hi
     if (rc) return rc;
     for (auto& sl : c->ring) sl.busy = false;
     if (c_out && ix->n && !ix->sharded) {
-        CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
+        CU(vg::counts_in_key_order(ix, ix->d_counts, 1, c->compute_stream));
         CU(cudaMemcpyAsync(c_out, ix->d_counts, ix->n, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(cudaStreamSynchronize(c->compute_stream));
+    }
+    ix->counting = false;
+    ix->foreign_streams = false;
+    return VG_OK;
+}
+
+// ---- the result in slot order --------------------------------------------------------------------------
+uint64_t vg_index_slots(const vg_index* ix) { return ix ? (ix->view.cvec ? ix->m_slots : ix->n) : 0; }
+
+int vg_index_slot_perm(vg_index* ix, uint32_t* perm_out) {
+    if (!ix || (!perm_out && ix->n)) return fail(VG_E_INVALID, "vg_index_slot_perm: NULL argument");
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: counts come in key order from vg_count_end");
+    if (!ix->view.cvec) {  // direct probing of a tiny table: slot order is key order
+        for (uint64_t i = 0; i < ix->n; ++i) perm_out[i] = (uint32_t)i;
+        return VG_OK;
+    }
+    DeviceGuard g(ix->ctx->device);
+    CU(cudaMemcpy(perm_out, ix->d_perm, ix->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return VG_OK;
+}
+
+int vg_count_slots_device(vg_index* ix, const uint8_t** dev_counts) {
+    if (!ix || !dev_counts) return fail(VG_E_INVALID, "vg_count_slots_device: NULL argument");
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: the counts of all keys come from vg_count_end");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    int rc = part_flush(ix, c->compute_stream);
+    if (rc) return rc;
+    if (ix->view.cvec) {
+        *dev_counts = ix->view.cvec;
+    } else {
+        CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, ix->n, ix->d_counts, 1, c->compute_stream));
+        *dev_counts = ix->d_counts;
+    }
+    return VG_OK;
+}
+
+int vg_count_end_slots(vg_index* ix, uint8_t* c_slots_out, uint64_t* positions, uint64_t* hits) {
+    if (!ix) return fail(VG_E_INVALID, "index is NULL");
+    if (!ix->counting) return fail(VG_E_STATE, "vg_count_end_slots before vg_count_begin");
+    if (ix->sharded) return fail(VG_E_STATE, "sharded index: use vg_count_end");
+    vg_ctx* c = ix->ctx;
+    DeviceGuard g(c->device);
+    int rc = vg_count_stats(ix, positions, hits);
+    if (rc) return rc;
+    for (auto& sl : c->ring) sl.busy = false;
+    if (c_slots_out && vg_index_slots(ix)) {
+        const uint8_t* src = nullptr;
+        rc = vg_count_slots_device(ix, &src);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c_slots_out, src, vg_index_slots(ix), cudaMemcpyDeviceToHost, c->compute_stream));
         CU(cudaStreamSynchronize(c->compute_stream));
     }
     ix->counting = false;

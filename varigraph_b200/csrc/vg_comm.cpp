@@ -196,7 +196,7 @@ int vg_count_allreduce(vg_comm* cm, vg_index* ix, uint8_t* c_out, void* dev_out)
     int rc = vg_count_flush(ix);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->copy_stream));
-    CU(vg::launch_extract(ix->view, ix->d_key56, nullptr, n, cm->arena + cm->reduce_off, 1, s));
+    CU(vg::counts_in_key_order(ix, cm->arena + cm->reduce_off, 1, s));
     ix->launches += 1;
     uint8_t* out = dev_out ? (uint8_t*)dev_out : cm->d_reduced;
     rc = combine_from_peers(cm, cm->reduce_off, n, out, s);
@@ -276,14 +276,19 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
                              cudaGetErrorString(e__)));                                                      \
     } while (0)
     // ---- symmetric objects (same order, same sizes on every rank) ----
-    size_t slots_off = 0, keybuf_off = 0, incount_off = 0;
+    size_t slots_off = 0, keybuf_off = 0, incount_off = 0, rank_off = 0, cvec_off = 0;
     const size_t counts_bytes = (size_t)((n + 15) & ~15ull) + 16;
+    // this rank's count vector (slot order) and rank_base: peers reach them for the rare direct probe of a key
+    // whose list is full, so they live in the arena too; no rank owns more keys than min(n, slots of its table)
+    const size_t cvec_bytes = (size_t)((std::min<uint64_t>(n, 4 * nb_local) + 31) & ~15ull);
     PartState& ps = ix->part;
     ix->view.slots = (uint64_t*)arena_alloc(cm, nb_local * 32, &slots_off);
     ix->d_counts = (uint8_t*)arena_alloc(cm, counts_bytes, &ix->counts_off);
     ps.view.keybuf = (uint64_t*)arena_alloc(cm, P * cap * sizeof(uint64_t), &keybuf_off);
     ps.view.incount = (unsigned long long*)arena_alloc(cm, P * sizeof(unsigned long long), &incount_off);
-    if (!ix->view.slots || !ix->d_counts || !ps.view.keybuf || !ps.view.incount) {
+    ix->view.rank_base = (uint32_t*)arena_alloc(cm, nb_local * sizeof(uint32_t), &rank_off);
+    ix->view.cvec = (uint8_t*)arena_alloc(cm, cvec_bytes, &cvec_off);
+    if (!ix->view.slots || !ix->d_counts || !ps.view.keybuf || !ps.view.incount || !ix->view.rank_base || !ix->view.cvec) {
         ix->view.slots = nullptr;
         return bail(fail(VG_E_NOMEM, "arena of %zu bytes too small: table %llu + counts %zu + key lists %llu bytes per rank",
                          cm->arena_bytes, (unsigned long long)(nb_local * 32), counts_bytes, (unsigned long long)(P * cap * 8)));
@@ -298,6 +303,8 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
         ps.view.peer_keybuf[r] = (uint64_t*)(cm->peer_base[r] + keybuf_off);
         ps.view.peer_slots[r] = (uint64_t*)(cm->peer_base[r] + slots_off);
         ps.view.peer_incount[r] = (unsigned long long*)(cm->peer_base[r] + incount_off);
+        ps.view.peer_rank_base[r] = (uint32_t*)(cm->peer_base[r] + rank_off);
+        ps.view.peer_cvec[r] = (uint8_t*)(cm->peer_base[r] + cvec_off);
     }
     ps.round_keys = round_bytes;
     cudaStream_t s = c->compute_stream;
@@ -309,6 +316,7 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     CUB(cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), s));
     CUB(cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), s));
     CUB(cudaMemsetAsync(ps.view.incount, 0, P * sizeof(unsigned long long), s));
+    CUB(cudaMemsetAsync(ix->view.cvec, 0, cvec_bytes, s));
     CUB(vg::launch_table_fill_empty(ix->view.slots, 4ull * nb_local, s));
 
     // ---- presence pre-filter over ALL keys (every rank filters its own reads before the exchange) ----
@@ -386,6 +394,25 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     CUB(cudaStreamSynchronize(s));
     if (misc.report.failed) return bail(fail(VG_E_NOMEM, "index build: %llu keys found no slot", misc.report.failed));
     ix->duplicates = misc.report.duplicates;
+    {   // slot order of this rank's table; from here on its own keys are only needed as positions in it
+        const uint32_t nblocks = (uint32_t)((nb_local + 1023ull) / 1024);
+        uint32_t* d_sums = nullptr;
+        unsigned long long* d_total = nullptr;
+        unsigned long long total = 0;
+        CUB(cudaMalloc((void**)&d_sums, ((size_t)nblocks + 1) * sizeof(uint32_t)));
+        cudaError_t e = cudaMalloc((void**)&d_total, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = vg::launch_rank_scan(ix->view, d_sums, d_total, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_perm, std::max<uint64_t>(ix->n_own, 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = vg::launch_slot_perm(ix->view, ix->d_key56, ix->n_own, ix->d_perm, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_sums);
+        cudaFree(d_total);
+        CUB(e);
+        ix->m_slots = total;
+        cudaFree(ix->d_key56);
+        ix->d_key56 = nullptr;
+    }
     if (nwords) {
         ps.filter.words = ps.d_filter;
         ps.filter.nwords = nwords;
@@ -435,7 +462,7 @@ int vg::sharded_end(vg_index* ix, uint8_t* c_out) {
     cudaStream_t s = c->compute_stream;
     const uint64_t n = ix->n;
     CU(cudaMemsetAsync(ix->d_counts, 0, (size_t)((n + 15) & ~15ull), s));
-    CU(vg::launch_extract(ix->view, ix->d_key56, ix->d_idx, ix->n_own, ix->d_counts, 1, s));
+    CU(vg::launch_gather_counts(ix->view.cvec, ix->d_perm, ix->d_idx, ix->n_own, ix->d_counts, 1, s));
     ix->launches += 1;
     int rc = combine_from_peers(cm, ix->counts_off, n, ix->d_combined, s);
     if (rc) return rc;

@@ -79,6 +79,11 @@ struct PartState {
     bool may_grow = false;     // rounds double (up to 4 G bases) when a sample needs more than one
     vg::PrefilterView filter{nullptr, 0};
     uint32_t* d_filter = nullptr;
+    // diagnostic (vg_index_set_timing): CUDA events around every scatter launch and every sweep, accumulated
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double ms_scatter = 0, ms_sweep = 0;
+    uint64_t n_scatter = 0, n_sweep = 0;
 };
 
 // One rank of a group of GPUs whose processes map each other's memory (CUDA IPC, NVLink).  Everything a
@@ -111,14 +116,18 @@ struct vg_index {
     size_t counts_off = 0;         // sharded: arena offset of d_counts (peers read it in the combine)
     uint8_t* d_combined = nullptr; // sharded: counts of all n keys after the combine
     vg::IndexView view{};
-    uint64_t* d_key56 = nullptr;   // key order given at create: the canonical k-mer of each key (sharded: own keys)
-    uint8_t* d_counts = nullptr;   // scratch for vg_count_end
-    uint8_t* d_flags = nullptr;    // optional per-entry subset for vg_count_histogram
+    uint64_t* d_key56 = nullptr;   // direct probing only: the canonical k-mer of each key, in the order given at create
+    uint8_t* d_counts = nullptr;   // scratch for vg_count_end (counts in key order)
+    uint8_t* d_flags = nullptr;    // optional per-entry subset for vg_count_histogram (slot order when partitioned)
+    // partitioned probing: the counters live in view.cvec, in slot order (see IndexView)
+    uint32_t* d_perm = nullptr;    // slot-order position of each key (sharded: of each own key)
+    uint64_t m_slots = 0;          // occupied slots of this table == entries of view.cvec
     unsigned long long* d_hist = nullptr;
     vg::DeviceMisc* d_misc = nullptr;
     uint64_t duplicates = 0;
     uint64_t launches = 0;
     uint64_t fastq_blocks = 0;     // raw FASTQ blocks parsed, checked and counted on the device so far
+    uint64_t h2d_bytes = 0;        // bytes copied host -> device for this index since the last vg_count_begin
     bool counting = false;
     bool foreign_streams = false;
 };
@@ -133,6 +142,7 @@ struct vg_cbf {
 
 namespace vg {
 void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
+cudaError_t counts_in_key_order(vg_index* ix, void* d_out, int elem_bytes, cudaStream_t s);
 int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier
 int sharded_end(vg_index* ix, uint8_t* c_out);        // vg_comm.cpp: extract own keys, combine over NVLink
 int enqueue_piece(vg_index* ix, int slot, const char* src, uint64_t len, const unsigned int* d_skip = nullptr);

@@ -19,6 +19,14 @@ struct IndexView {
     // table holds global buckets [b_base, b_base + nbuckets).  Unsharded: nb_total == nbuckets, b_base == 0.
     uint32_t nb_total;
     uint32_t b_base;
+    // Partitioned probing keeps the read-coverage counters OUTSIDE the table, densely, in slot order: entry
+    // rank_base[b] + s of cvec belongs to slot s of bucket b (buckets fill front to back, so the occupied slots of
+    // a bucket are 0 .. occ-1 and rank_base is the exclusive prefix sum of the occupancies).  The table is then
+    // read-only while counting, a sample's result is cvec itself (no gather over the keys, no sweep to zero the
+    // counts: one memset), and the sweep writes nothing back into the slices it pulled into L2.
+    // nullptr (direct probing of a tiny table): the count lives in the low byte of each slot.
+    uint32_t* rank_base;
+    uint8_t* cvec;
 };
 
 // Presence pre-filter: a word-blocked Bloom filter over the index keys (both bits of a key sit in
@@ -60,6 +68,8 @@ struct PartView {
     unsigned long long* incount;    // world x P_local: how many keys each source put into each of MY lists
     uint64_t* peer_keybuf[kMaxWorld];
     uint64_t* peer_slots[kMaxWorld];           // for the rare direct probe of a key whose list is full
+    uint32_t* peer_rank_base[kMaxWorld];       //   ... and that table's rank_base / cvec (see IndexView)
+    uint8_t* peer_cvec[kMaxWorld];
     unsigned long long* peer_incount[kMaxWorld];
 };
 constexpr uint32_t kMaxPartitions = 1024;
@@ -101,6 +111,9 @@ int sm_count(int device);
 cudaError_t launch_table_fill_empty(uint64_t* slots, uint64_t nslots, cudaStream_t s);
 // in place: hash (the reference's key >> 8) -> canonical k-mer (hash64 is invertible)
 cudaError_t launch_unhash(uint64_t* d_key56, uint64_t n, uint64_t mask, cudaStream_t s);
+// device-resident caller keys -> canonical k-mers (validated; *d_bad must start at ~0)
+cudaError_t launch_keys_to_key56(const uint64_t* d_keys, uint64_t n, uint32_t k, uint64_t mask, uint64_t* d_key56,
+                                 unsigned long long* d_bad, cudaStream_t s);
 cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
                           cudaStream_t s);
 // Sharded build: of the n canonical k-mers at d_key56 (caller positions first_idx + i), append those whose
@@ -109,6 +122,16 @@ cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t
 cudaError_t launch_select_owned(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint64_t first_idx,
                                 uint64_t* d_own, uint64_t* d_own_idx, unsigned long long* d_n_own, cudaStream_t s);
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s);
+// rank_base[b] = occupied slots in buckets [0, b); *d_total = occupied slots of the whole table.
+// d_block_sums: scratch of (nbuckets + 1023) / 1024 + 1 u32.
+cudaError_t launch_rank_scan(const IndexView& ix, uint32_t* d_block_sums, unsigned long long* d_total, cudaStream_t s);
+// perm[i] = slot-order position of key i (0xffffffff: the key is not in this table)
+cudaError_t launch_slot_perm(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint32_t* d_perm, cudaStream_t s);
+// out[d_idx ? d_idx[i] : i] = cvec[perm[i]] (0 where perm[i] == 0xffffffff): counts in the caller's key order
+cudaError_t launch_gather_counts(const uint8_t* cvec, const uint32_t* d_perm, const uint64_t* d_idx, uint64_t n, void* d_out,
+                                 int out_elem_bytes, cudaStream_t s);
+// out[perm[i]] = in[i]: per-key bytes (the histogram's subset flags) into slot order
+cudaError_t launch_scatter_bytes(const uint8_t* d_in, const uint32_t* d_perm, uint64_t n, uint8_t* d_out, cudaStream_t s);
 // d_skip (optional): device flag, non-zero = count nothing (see Chunk::skip)
 cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t nbytes, CountStats* d_stats,
                          int ctas_per_sm, int nsm, cudaStream_t s, const unsigned int* d_skip = nullptr);

@@ -18,6 +18,29 @@
 
 namespace vg {
 
+// exclusive prefix sum over the CTA's threads (blockDim.x == kCtaThreads); total in `total`
+__device__ __forceinline__ uint32_t cta_exclusive_sum(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kCtaThreads / 32; ++i) {
+        const uint32_t ws = warp_sums[i];
+        if ((uint32_t)i < warp) before += ws;
+        all += ws;
+    }
+    total = all;
+    __syncthreads();
+    return before + inc - v;
+}
+
 // ---------------------------------------------------------------------------
 // index build
 // ---------------------------------------------------------------------------
@@ -30,6 +53,21 @@ __global__ void fill_empty_kernel(uint64_t* slots, uint64_t nslots) {
 __global__ void unhash_kernel(uint64_t* key56, uint64_t n, uint64_t mask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) key56[i] = hash64_inv(key56[i], mask);
+}
+
+// keys as the caller holds them (hash64(canonical k-mer) << 8 | k, src/kmer.cpp:138) -> canonical k-mers; *bad = the
+// lowest position whose key is malformed (low byte != k, or a hash beyond 2k bits), ~0 if none
+__global__ void keys_to_key56_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t k, uint64_t mask, uint64_t* key56,
+                                     unsigned long long* bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i], h = key >> 8;
+    if ((key & 0xffu) != k || h > mask) {
+        atomicMin(bad, (unsigned long long)i);
+        key56[i] = kKey56Max;
+        return;
+    }
+    key56[i] = hash64_inv(h, mask);
 }
 
 // One thread per key.  Claims the first empty slot in probe order with a 64-bit CAS; because
@@ -82,6 +120,108 @@ __global__ void clear_counts_kernel(uint64_t* slots, uint64_t nslots) {
     }
 }
 
+__device__ __forceinline__ int match_slot(const uint64_t (&v)[4], uint64_t key, bool& saw_empty, uint64_t& seen);
+
+// ---- slot order (partitioned path): rank_base, the key -> slot permutation, gathers through it --------------
+constexpr int kScanChunk = kCtaThreads * 4;  // buckets per CTA of the occupancy scan
+__device__ __forceinline__ uint32_t bucket_occupancy(const uint64_t* slots, uint64_t b) {
+    uint64_t v[4];
+    ld_bucket(slots + 4 * b, v);
+    return (v[0] != kSlotEmpty) + (v[1] != kSlotEmpty) + (v[2] != kSlotEmpty) + (v[3] != kSlotEmpty);
+}
+__global__ void __launch_bounds__(kCtaThreads) occ_block_sums_kernel(IndexView ix, uint32_t* block_sums) {
+    __shared__ uint32_t ws[kCtaThreads / 32];
+    const uint64_t b0 = (uint64_t)blockIdx.x * kScanChunk + threadIdx.x * 4;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (b0 + j < ix.nbuckets) v += bucket_occupancy(ix.slots, b0 + j);
+    uint32_t total;
+    cta_exclusive_sum(v, ws, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+// one CTA: exclusive scan of the block sums in place; the grand total goes to *total
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* block_sums, uint32_t nblocks, unsigned long long* total) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (nblocks + 1023) / 1024, t0 = threadIdx.x * per;
+    unsigned long long sum = 0;
+    for (uint32_t i = 0; i < per && t0 + i < nblocks; ++i) sum += block_sums[t0 + i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        *total = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = 0; i < per && t0 + i < nblocks; ++i) {
+        const uint32_t v = block_sums[t0 + i];
+        block_sums[t0 + i] = (uint32_t)run;  // the caller checked that the total fits 32 bits
+        run += v;
+    }
+}
+__global__ void __launch_bounds__(kCtaThreads) rank_base_kernel(IndexView ix, const uint32_t* block_sums) {
+    __shared__ uint32_t ws[kCtaThreads / 32];
+    const uint64_t b0 = (uint64_t)blockIdx.x * kScanChunk + threadIdx.x * 4;
+    uint32_t occ[4], v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        occ[j] = b0 + j < ix.nbuckets ? bucket_occupancy(ix.slots, b0 + j) : 0u;
+        v += occ[j];
+    }
+    uint32_t total;
+    uint32_t run = block_sums[blockIdx.x] + cta_exclusive_sum(v, ws, total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (b0 + j < ix.nbuckets) ix.rank_base[b0 + j] = run;
+        run += occ[j];
+    }
+}
+
+__global__ void slot_perm_kernel(IndexView ix, const uint64_t* __restrict__ key56, uint64_t n, uint32_t* perm) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = key56[i];
+    uint32_t r = 0xffffffffu;  // not a canonical k-mer / not in this table: its count is always 0
+    if (key != kKey56Max) {
+        uint32_t b = bucket_of(key, ix.nb_total) - ix.b_base;
+        if (b < ix.nbuckets) {
+            for (uint32_t tries = 0; tries < ix.nbuckets; ++tries) {
+                uint64_t v[4];
+                ld_bucket(ix.slots + 4ull * b, v);
+                bool saw_empty;
+                uint64_t seen = 0;
+                const int hs = match_slot(v, key, saw_empty, seen);
+                if (hs >= 0) { r = ix.rank_base[b] + (uint32_t)hs; break; }
+                if (saw_empty) break;
+                b = (b + 1 == ix.nbuckets) ? 0 : b + 1;
+            }
+        }
+    }
+    perm[i] = r;
+}
+
+template <typename OutT>
+__global__ void gather_counts_kernel(const uint8_t* __restrict__ cvec, const uint32_t* __restrict__ perm,
+                                     const uint64_t* __restrict__ idx, uint64_t n, OutT* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = perm[i];
+    out[idx ? idx[i] : i] = (OutT)(r == 0xffffffffu ? 0u : (uint32_t)cvec[r]);
+}
+
+__global__ void scatter_bytes_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ perm, uint64_t n, uint8_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = perm[i];
+    if (r != 0xffffffffu && in[i]) out[r] = in[i];  // duplicates of a key share a slot: any non-zero flag marks it
+}
+
 // ---------------------------------------------------------------------------
 // probe + count
 // ---------------------------------------------------------------------------
@@ -93,6 +233,24 @@ __device__ __forceinline__ void slot_sat_add(uint64_t* p, uint64_t seen, uint32_
         if (c == 255u) return;  // saturation is absorbing
         uint32_t add = min(n, 255u - c);
         uint64_t prev = atomicCAS((unsigned long long*)p, old, old + add);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+// The same on the dense count vector of the partitioned path (IndexView::cvec): byte r, by a 32-bit CAS on
+// the word that holds it.  Rare paths only (a key whose list is full, a hit that spilled over a slice edge).
+// kSystem: the vector lives on a peer GPU (mapped over NVLink); .gpu scope is not atomic across devices.
+template <bool kSystem>
+__device__ __forceinline__ void cvec_sat_add(uint8_t* cvec, uint64_t r, uint32_t n) {
+    uint32_t* w = (uint32_t*)(cvec + (r & ~3ULL));
+    const uint32_t sh = (uint32_t)(r & 3u) * 8u;
+    uint32_t old = *(volatile uint32_t*)w;
+    for (;;) {
+        const uint32_t c = (old >> sh) & 0xffu;
+        if (c == 255u) return;
+        const uint32_t nw = old + (min(n, 255u - c) << sh);
+        const uint32_t prev = kSystem ? atomicCAS_system(w, old, nw) : atomicCAS(w, old, nw);
         if (prev == old) return;
         old = prev;
     }
@@ -294,16 +452,23 @@ __constant__ uint32_t c_magic[kMaxBinCap + 1];
 // worst-case overflow buffer has to exist.  Kept out of line: it must not cost the hot path registers.
 // `slots` / `b` are the table that owns the key and its home bucket there: for a sharded index that may be
 // a peer GPU's table (64-bit CAS works over NVLink; no sweep runs while keys are being scattered).
-__device__ __noinline__ void probe_one_direct(uint64_t* slots, uint32_t nbuckets, uint32_t b, uint64_t key,
-                                              CountStats* stats) {
+struct TableRef {  // a table a key may be probed in directly: this GPU's, or (sharded index) a peer's over NVLink
+    uint64_t* slots;
+    uint32_t* rank_base;
+    uint8_t* cvec;
+    bool remote;
+};
+__device__ __noinline__ void probe_one_direct(TableRef t, uint32_t nbuckets, uint32_t b, uint64_t key, CountStats* stats) {
     for (uint32_t tries = 0; tries < nbuckets; ++tries) {
         uint64_t v[4];
-        ld_bucket(slots + 4ull * b, v);
+        ld_bucket(t.slots + 4ull * b, v);
         bool saw_empty;
         uint64_t seen = 0;
         const int hs = match_slot(v, key, saw_empty, seen);
         if (hs >= 0) {
-            slot_sat_add(slots + 4ull * b + hs, seen, 1u);
+            const uint64_t r = (uint64_t)t.rank_base[b] + (uint32_t)hs;
+            if (t.remote) cvec_sat_add<true>(t.cvec, r, 1u);
+            else cvec_sat_add<false>(t.cvec, r, 1u);
             atomicAdd(&stats->hits, 1ull);
             return;
         }
@@ -312,22 +477,21 @@ __device__ __noinline__ void probe_one_direct(uint64_t* slots, uint32_t nbuckets
     }
 }
 // The table that owns `key` and the key's home bucket there.
-__device__ __forceinline__ void owner_table(const IndexView& ix, const PartView& pv, uint64_t key, uint64_t*& slots,
-                                            uint32_t& b) {
+__device__ __forceinline__ void owner_table(const IndexView& ix, const PartView& pv, uint64_t key, TableRef& t, uint32_t& b) {
     const uint32_t bg = bucket_of(key, ix.nb_total);
-    slots = ix.slots;
+    t = TableRef{ix.slots, ix.rank_base, ix.cvec, false};
     b = bg;
     if (pv.world > 1) {
         const uint32_t o = bg / ix.nbuckets;
-        slots = pv.peer_slots[o];
+        t = TableRef{pv.peer_slots[o], pv.peer_rank_base[o], pv.peer_cvec[o], o != pv.rank};
         b = bg - o * ix.nbuckets;
     }
 }
 __device__ __forceinline__ void probe_one_direct(const IndexView& ix, const PartView& pv, uint64_t key, CountStats* stats) {
-    uint64_t* slots;
+    TableRef t;
     uint32_t b;
-    owner_table(ix, pv, key, slots, b);
-    probe_one_direct(slots, ix.nbuckets, b, key, stats);
+    owner_table(ix, pv, key, t, b);
+    probe_one_direct(t, ix.nbuckets, b, key, stats);
 }
 // Where slice p's keys from this GPU go: the slice owner's key list for source `rank`.
 __device__ __forceinline__ uint64_t* list_of(const PartView& pv, uint32_t p) {
@@ -366,11 +530,11 @@ __device__ __forceinline__ uint64_t ld_shared_u64(uint32_t addr) {
 }
 
 // A key that finds its tile bin full: reserve one place in the slice's key list right away.
-__device__ __noinline__ void scatter_one_global(unsigned long long* cursor_p, uint64_t* list, uint64_t cap, uint64_t* slots,
+__device__ __noinline__ void scatter_one_global(unsigned long long* cursor_p, uint64_t* list, uint64_t cap, TableRef t,
                                                 uint32_t nbuckets, uint32_t b, uint64_t key, CountStats* stats) {
     const unsigned long long pos = atomicAdd(cursor_p, 1ull);
     if (pos < cap) list[pos] = key;
-    else probe_one_direct(slots, nbuckets, b, key, stats);
+    else probe_one_direct(t, nbuckets, b, key, stats);
 }
 
 // K1 of the partitioned path.  Per 4 KiB CTA tile, eight positions per lane at a time: encode + hash,
@@ -441,11 +605,11 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if ((over >> j) & 1u) {
-                        uint64_t* slots;
+                        TableRef tr;
                         uint32_t b;
-                        owner_table(ix, pv, keys[j], slots, b);
+                        owner_table(ix, pv, keys[j], tr, b);
                         const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
-                        scatter_one_global(&pv.cursor[p], list_of(pv, p), pv.cap, slots, ix.nbuckets, b, keys[j], stats);
+                        scatter_one_global(&pv.cursor[p], list_of(pv, p), pv.cap, tr, ix.nbuckets, b, keys[j], stats);
                     }
             }
         };
@@ -521,7 +685,7 @@ __device__ __forceinline__ uint64_t ld_key_stream(const uint64_t* p) {
 template <int kBatch>
 __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_t (&keys)[kBatch], uint32_t emit,
                                               uint32_t b0, uint32_t b1, uint32_t* ctr, uint32_t& n_hit) {
-    uint32_t bk[kBatch], st[kBatch];  // st: bit 31 hit, bit 30 counter already saturated, bits 0-1 slot
+    uint32_t bk[kBatch], st[kBatch];  // st: bit 31 hit, bits 0-1 slot
     uint32_t pend = 0;                // positions whose search continues in the next bucket
     // A scattered 256-bit load costs 1.5 L1TEX cycles per lane, a 128-bit one 1.0 (tools/gather_bench.cu), and
     // at load factor 0.3 most keys sit in the first two slots of their bucket (buckets fill front to back):
@@ -529,12 +693,10 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
     uint32_t more = 0;                // positions that need the second half of their bucket
     auto half = [&](const uint64_t (&v)[2], uint64_t key, uint32_t first_slot, bool& second_taken) {
         const uint32_t want_hi = (uint32_t)(key >> 24), want_lo = (uint32_t)(key << 8);
-        const uint32_t d0 = (uint32_t)v[0] ^ want_lo, d1 = (uint32_t)v[1] ^ want_lo;
-        const bool m0 = (uint32_t)(v[0] >> 32) == want_hi && d0 < 256u;
-        const bool m1 = (uint32_t)(v[1] >> 32) == want_hi && d1 < 256u;
-        const uint32_t cnt = m1 ? d1 : d0;  // want_lo's low byte is 0: d == count
+        const bool m0 = (uint32_t)(v[0] >> 32) == want_hi && (uint32_t)v[0] == want_lo;  // slot == key << 8: the low
+        const bool m1 = (uint32_t)(v[1] >> 32) == want_hi && (uint32_t)v[1] == want_lo;  // byte of a slot stays 0 here
         second_taken = v[1] != kSlotEmpty;
-        return (m0 || m1) ? (0x80000000u | (cnt == 255u ? 0x40000000u : 0u) | (first_slot + (m1 ? 1u : 0u))) : 0u;
+        return (m0 || m1) ? (0x80000000u | (first_slot + (m1 ? 1u : 0u))) : 0u;
     };
     {
         uint64_t v[kBatch][2];
@@ -583,7 +745,7 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
             bool saw_empty;
             uint64_t sv = 0;
             const int h2 = match_slot(w, key, saw_empty, sv);
-            const uint32_t ns = h2 >= 0 ? (0x80000000u | (((uint32_t)sv & 0xffu) == 255u ? 0x40000000u : 0u) | (uint32_t)h2) : 0u;
+            const uint32_t ns = h2 >= 0 ? (0x80000000u | (uint32_t)h2) : 0u;
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
                 if (b == (uint32_t)j) {
@@ -598,39 +760,30 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
     for (int b = 0; b < kBatch; ++b) {
         if (st[b] >> 31) {
             n_hit += 1;
-            if (!(st[b] & 0x40000000u)) {  // saturation is absorbing: nothing left to add
-                const uint32_t hs = st[b] & 3u;
-                if (bk[b] >= b0 && bk[b] < b1) {
-                    atomicAdd(ctr + (size_t)(bk[b] - b0) * 4 + hs, 1u);  // result unused: a RED, no round trip
-                } else {
-                    uint64_t* p = ix.slots + 4ull * bk[b] + hs;
-                    slot_sat_add(p, *(volatile uint64_t*)p, 1u);
-                }
-            }
+            const uint32_t hs = st[b] & 3u;
+            if (bk[b] >= b0 && bk[b] < b1) atomicAdd(ctr + (size_t)(bk[b] - b0) * 4 + hs, 1u);  // result unused: a RED, no round trip
+            else cvec_sat_add<false>(ix.cvec, (uint64_t)ix.rank_base[bk[b]] + hs, 1u);           // spilled over the slice edge
         }
     }
 }
 
-// Folds the side counters of slice [b0, b1) into its slots: count = min(255, count + hits).
-// One bucket (32-byte sector of slots + 16 bytes of counters) per thread and step; plain stores are
-// safe because nothing else touches a slice while it is retired (the sweep needs >= 3 slices, so a
-// key spilling over the table's end never lands in the slice being retired).
+// Folds the side counters of slice [b0, b1) into the count vector: c = min(255, c + hits) at rank_base[b] + slot.
+// One bucket (16 bytes of counters) per thread and step; neighbouring buckets own neighbouring bytes of cvec.
+// Plain byte loads / stores are safe: nothing else touches these bytes while the slice is retired (the sweep
+// needs >= 3 slices, so a key spilling over the table's end never lands in the slice being retired, and the
+// 32-bit CAS of such a spill elsewhere never changes a byte it does not own).
 __device__ __forceinline__ void retire_slice(const IndexView& ix, uint32_t b0, uint32_t b1, uint32_t* ctr) {
     const uint64_t nb = b1 - b0;
-    uint64_t* slots = ix.slots + 4ull * b0;
+    const uint32_t* rb = ix.rank_base + b0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) {
         const uint4 c = *reinterpret_cast<const uint4*>(ctr + 4 * i);
         if (c.x | c.y | c.z | c.w) {
-            uint64_t v[4];
-            ld_bucket(slots + 4 * i, v);
+            uint8_t* cv = ix.cvec + rb[i];
             const uint32_t cs[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t cnt = (uint32_t)(v[j] & 0xffu);
-                v[j] = (v[j] & ~0xffULL) | (uint64_t)min(255u, cnt + min(cs[j], 255u));
-            }
-            asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(slots + 4 * i), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+            for (int j = 0; j < 4; ++j)
+                if (cs[j]) cv[j] = (uint8_t)min(255u, (uint32_t)cv[j] + min(cs[j], 255u));
             *reinterpret_cast<uint4*>(ctr + 4 * i) = make_uint4(0, 0, 0, 0);
         }
     }
@@ -931,29 +1084,6 @@ __device__ __forceinline__ uint32_t seg_newlines(const uint8_t* raw, uint32_t of
     return m;
 }
 
-// exclusive prefix sum over the CTA's threads (blockDim.x == kCtaThreads); total in `total`
-__device__ __forceinline__ uint32_t cta_exclusive_sum(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
-        if (lane >= (uint32_t)d) inc += t;
-    }
-    if (lane == 31) warp_sums[warp] = inc;
-    __syncthreads();
-    uint32_t before = 0, all = 0;
-#pragma unroll
-    for (int i = 0; i < kCtaThreads / 32; ++i) {
-        const uint32_t ws = warp_sums[i];
-        if ((uint32_t)i < warp) before += ws;
-        all += ws;
-    }
-    total = all;
-    __syncthreads();
-    return before + inc - v;
-}
-
 __global__ void __launch_bounds__(kCtaThreads) fastq_count_lines_kernel(const uint8_t* raw, uint32_t len, uint32_t* tile_count) {
     __shared__ uint32_t ws[kCtaThreads / 32];
     uint4 w;
@@ -1120,6 +1250,13 @@ cudaError_t launch_unhash(uint64_t* d_key56, uint64_t n, uint64_t mask, cudaStre
     return cudaGetLastError();
 }
 
+cudaError_t launch_keys_to_key56(const uint64_t* d_keys, uint64_t n, uint32_t k, uint64_t mask, uint64_t* d_key56,
+                                 unsigned long long* d_bad, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    keys_to_key56_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_keys, n, k, mask, d_key56, d_bad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_insert(const IndexView& ix, const uint64_t* d_key56, uint64_t n, InsertReport* d_rep,
                           cudaStream_t s) {
     if (n == 0) return cudaSuccess;
@@ -1155,6 +1292,36 @@ cudaError_t launch_combine_counts(const PeerPtrs& counts, int world, uint64_t n,
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s) {
     uint64_t nslots = 4ull * ix.nbuckets;
     clear_counts_kernel<<<grid_1d(nslots, 256, 148 * 16), 256, 0, s>>>(ix.slots, nslots);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rank_scan(const IndexView& ix, uint32_t* d_block_sums, unsigned long long* d_total, cudaStream_t s) {
+    const uint32_t nblocks = (uint32_t)(((uint64_t)ix.nbuckets + kScanChunk - 1) / kScanChunk);
+    occ_block_sums_kernel<<<nblocks, kCtaThreads, 0, s>>>(ix, d_block_sums);
+    scan_block_sums_kernel<<<1, 1024, 0, s>>>(d_block_sums, nblocks, d_total);
+    rank_base_kernel<<<nblocks, kCtaThreads, 0, s>>>(ix, d_block_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slot_perm(const IndexView& ix, const uint64_t* d_key56, uint64_t n, uint32_t* d_perm, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    slot_perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix, d_key56, n, d_perm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_counts(const uint8_t* cvec, const uint32_t* d_perm, const uint64_t* d_idx, uint64_t n, void* d_out,
+                                 int out_elem_bytes, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (out_elem_bytes == 1) gather_counts_kernel<uint8_t><<<g, 256, 0, s>>>(cvec, d_perm, d_idx, n, (uint8_t*)d_out);
+    else if (out_elem_bytes == 4) gather_counts_kernel<uint32_t><<<g, 256, 0, s>>>(cvec, d_perm, d_idx, n, (uint32_t*)d_out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_bytes(const uint8_t* d_in, const uint32_t* d_perm, uint64_t n, uint8_t* d_out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    scatter_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_in, d_perm, n, d_out);
     return cudaGetLastError();
 }
 

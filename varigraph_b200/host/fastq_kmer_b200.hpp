@@ -32,18 +32,21 @@ public:
         return inst;
     }
     vg_index* index() const { return ix_; }
-    // c_out[i] belongs to the i-th entry in the iteration order captured at build time
+    // c[s] belongs to the map entry whose k-mer sits at position s of the device's slot-order count vector
+    // (vg_index_slot_perm, captured once per graph): the per-sample result needs no reordering on the device
     void write_back(const std::vector<uint8_t>& c, uint32_t threads) {
-        const size_t n = cptr_.size();
+        const size_t m = cptr_.size();
         const uint32_t nt = std::max<uint32_t>(1, std::min<uint32_t>(threads, 64));
         std::vector<std::thread> pool;
         for (uint32_t t = 0; t < nt; ++t)
             pool.emplace_back([&, t] {
-                for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) *cptr_[i] = c[i];
+                for (size_t s = m * t / nt, e = m * (t + 1) / nt; s < e; ++s)
+                    if (cptr_[s]) *cptr_[s] = c[s];
             });
         for (auto& th : pool) th.join();
     }
-    size_t size() const { return cptr_.size(); }
+    size_t size() const { return size_; }          // map entries, in the iteration order captured at build time
+    size_t slots() const { return cptr_.size(); }  // entries of the device's count vector
     bool has_flags = false;  // vg_index_set_flags done for this graph (see VarigraphKernel)
     // the map entries in the order the device index knows them
     template <typename Fn>
@@ -66,14 +69,18 @@ private:
                   << map.size() << " k-mers) on GPU " << gpu << " ...\n";
         std::vector<uint64_t> keys;
         keys.reserve(map.size());
-        cptr_.clear();
-        cptr_.reserve(map.size());
-        for (auto& kv : map) {
-            keys.push_back(kv.first);
-            cptr_.push_back(&kv.second.c);
-        }
+        for (auto& kv : map) keys.push_back(kv.first);
         VGB200_CHECK(vg_ctx_create(gpu, buffer_mb, &ctx_));
         VGB200_CHECK(vg_index_create(ctx_, keys.data(), keys.size(), k, 0.0, &ix_));
+        std::vector<uint32_t> perm(keys.size());
+        VGB200_CHECK(vg_index_slot_perm(ix_, perm.data()));
+        std::vector<uint64_t>().swap(keys);
+        cptr_.assign(vg_index_slots(ix_), nullptr);
+        size_t i = 0;
+        for (auto& kv : map) {
+            const uint32_t s = perm[i++];
+            if (s != 0xffffffffu) cptr_[s] = &kv.second.c;  // else: a key no read can produce; its c stays 0
+        }
         map_ = &map;
         size_ = map.size();
         k_ = k;
@@ -124,8 +131,8 @@ public:
         VGB200_CHECK(vg_count_begin(dev.index()));
         uint64_t readBase = 0;
         VGB200_CHECK(vg_count_files(dev.index(), paths.data(), (int)paths.size(), (int)threads_, &readBase));
-        vector<uint8_t> c(dev.size());
-        VGB200_CHECK(vg_count_end(dev.index(), c.data(), nullptr, nullptr));
+        vector<uint8_t> c(dev.slots());
+        VGB200_CHECK(vg_count_end_slots(dev.index(), c.data(), nullptr, nullptr));
         mReadBase += readBase;
         dev.write_back(c, threads_);
         malloc_trim(0);
