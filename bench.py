@@ -733,7 +733,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(w), "index_kmers": nkeys, "index_table_bytes": ix.table_bytes,
-                           "table_partitions": ix.partitions, "index_duplicate_kmers": ix.duplicates,
+                           "table_partitions": ix.partitions, "table_slices": ix.slices, "index_duplicate_kmers": ix.duplicates,
                            "reads_per_gpu": nbytes // rec, "positions_per_gpu": positions,
                            "coverage_per_gpu": cov_rank,
                            "parallelism": (f"reads sharded x{world}, index "

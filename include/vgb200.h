@@ -61,7 +61,8 @@ int vg_index_create_device(vg_ctx* ctx, const uint64_t* dev_keys, uint64_t n, ui
 int vg_index_destroy(vg_index* ix);
 uint64_t vg_index_size(const vg_index* ix);          /* n */
 uint64_t vg_index_table_bytes(const vg_index* ix);   /* bytes of the slot table in HBM */
-uint32_t vg_index_partitions(const vg_index* ix);    /* table slices of the partitioned probe, 0 = direct */
+uint32_t vg_index_partitions(const vg_index* ix);    /* partitions the scatter bins by (table slices, or coarse groups of them), 0 = direct */
+uint32_t vg_index_slices(const vg_index* ix);        /* L2-sized table slices of this GPU's table the sweep probes, 0 = direct */
 uint64_t vg_index_launches(const vg_index* ix);      /* kernels launched for this index so far */
 uint64_t vg_index_duplicates(const vg_index* ix);    /* keys given more than once at create (they share a slot) */
 uint64_t vg_count_h2d_bytes(const vg_index* ix);     /* bytes copied host -> device since the last vg_count_begin */

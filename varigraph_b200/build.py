@@ -30,6 +30,17 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list) -> str:
+    """An A/B build of the same sources with extra -D flags -> varigraph_b200/libvgb200_<name>.so (load it with VG_LIB)."""
+    out = os.path.join(HERE, f"libvgb200_{name}.so")
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-lz"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building {out}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB

@@ -13,7 +13,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_uint8, c_uint32,
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgb200.so")
+LIB_PATH = os.environ.get("VG_LIB") or os.path.join(_HERE, "libvgb200.so")  # VG_LIB: an A/B build of the same sources
 
 VG_OK, VG_E_INVALID, VG_E_CUDA, VG_E_NOMEM, VG_E_IO, VG_E_STATE = 0, -1, -2, -3, -4, -5
 
@@ -46,6 +46,7 @@ def _load() -> ctypes.CDLL:
         "vg_index_size": (c_uint64, [c_void_p]),
         "vg_index_table_bytes": (c_uint64, [c_void_p]),
         "vg_index_partitions": (c_uint32, [c_void_p]),
+        "vg_index_slices": (c_uint32, [c_void_p]),
         "vg_index_launches": (c_uint64, [c_void_p]),
         "vg_index_duplicates": (c_uint64, [c_void_p]),
         "vg_count_h2d_bytes": (c_uint64, [c_void_p]),
@@ -246,6 +247,10 @@ class Index:
     @property
     def partitions(self) -> int:
         return int(lib.vg_index_partitions(self._h))
+
+    @property
+    def slices(self) -> int:
+        return int(lib.vg_index_slices(self._h))
 
     @property
     def launches(self) -> int:

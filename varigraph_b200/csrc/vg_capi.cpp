@@ -60,31 +60,57 @@ void vg::pin_in_l2(vg_ctx* c, void* ptr, size_t bytes) {
     }
 }
 
+// Slices and coarse partitions of a table of `nbuckets` buckets per GPU, `world` GPUs (the same on every rank).
+// false: the table is to be probed directly (no workable partitioning).
+bool vg::part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g) {
+    const uint64_t table_bytes = 32ull * nbuckets;
+    uint64_t slice_bytes = 32ull << 20;
+    const char* sb = getenv("VG_SLICE_BYTES");
+    if (sb && strtoull(sb, nullptr, 10) >= 64) {
+        slice_bytes = strtoull(sb, nullptr, 10);
+    } else {
+        const uint64_t floor_bytes = world > 1 ? 64 : (1ull << 20);
+        while (slice_bytes > floor_bytes && table_bytes / slice_bytes < 3) slice_bytes >>= 1;
+    }
+    uint32_t shift2 = 0;
+    while ((32ull << (shift2 + 1)) <= slice_bytes) ++shift2;  // buckets per slice = 2^shift2
+    const uint64_t nslices = (nbuckets + (1ull << shift2) - 1) >> shift2;
+    uint64_t two_from = 96;
+    if (const char* e = getenv("VG_TWO_LEVEL_FROM")) two_from = strtoull(e, nullptr, 10);
+    uint32_t sub_bits = 0;
+    if (nslices * world > two_from) {
+        const uint64_t coarse_max = std::max<uint64_t>(64 / world, 2);  // per GPU; all GPUs together: a CTA tile's bins
+        while (sub_bits < vg::kMaxSubBits && ((nslices + (1ull << sub_bits) - 1) >> sub_bits) > coarse_max) ++sub_bits;
+        if (sub_bits == 0) sub_bits = 1;
+    }
+    uint64_t P_local = (nslices + (1ull << sub_bits) - 1) >> sub_bits;
+    if (world > 1 && sub_bits == 0 && P_local < 3) P_local = 3;  // a sharded table is sized by its slices: the sweep needs three
+    if (world > 1 && sub_bits && P_local < 2) P_local = 2;
+    if (P_local * world > vg::kMaxPartitions) return false;
+    if (world == 1 && nslices < 3) return false;  // the sweep retires slice p-1 while slice p is probed
+    g.shift2 = shift2;
+    g.sub_bits = sub_bits;
+    g.P_local = (uint32_t)P_local;
+    return true;
+}
+
 static int part_setup(vg_index* ix) {
     vg_ctx* c = ix->ctx;
     const char* env = getenv("VG_PARTITION");
     const int force = env ? atoi(env) : -1;
     if (force == 0) return VG_OK;
     const uint64_t table_bytes = 32ull * ix->view.nbuckets;
-    // Slices of 32 MB (L2-resident with room to spare); 64 MB for very large tables to keep the slice
-    // count down; smaller ones for small tables so that at least three slices exist -- measured on
-    // B200, the scatter + sweep pipeline (pre-filter, fire-and-forget side counters) also beats direct
-    // probing with CAS when the whole table fits L2 (68 vs 52 G k-mers/s on a 96 MB table).
-    uint64_t slice_bytes = 32ull << 20;
-    if (const char* e = getenv("VG_SLICE_BYTES")) {
-        slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
-    } else {
-        while (slice_bytes > (1ull << 20) && table_bytes / slice_bytes < 3) slice_bytes >>= 1;
-    }
-    uint32_t shift = 0;
-    while ((32ull << (shift + 1)) <= slice_bytes) ++shift;  // buckets per slice = 2^shift
-    uint64_t P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
-    if (P > 256 && !getenv("VG_SLICE_BYTES")) {
-        ++shift;
-        P = (ix->view.nbuckets + (1ull << shift) - 1) >> shift;
-    }
     if (force != 1 && table_bytes < (8ull << 20)) return VG_OK;   // tiny table: direct probing
-    if (P > vg::kMaxPartitions || P < 3) return VG_OK;            // direct probing
+    // Slices of 32 MB (L2-resident with room to spare); smaller ones for small tables so that at least three
+    // slices exist -- measured on B200, the scatter + sweep pipeline (pre-filter, fire-and-forget side counters)
+    // also beats direct probing with CAS when the whole table fits L2 (68 vs 52 G k-mers/s on a 96 MB table).
+    // A CTA tile of 4 Ki positions scatters well into a few dozen bins, not into hundreds: beyond
+    // VG_TWO_LEVEL_FROM slices (default 96) the scatter bins by coarse partitions of 2^sub_bits slices (at most 64
+    // of them) and the sweep re-scatters each coarse list into its slices' lists before probing them.
+    vg::PartGeometry geo;
+    if (!vg::part_geometry(ix->view.nbuckets, 1, geo)) return VG_OK;  // direct probing
+    const uint32_t shift2 = geo.shift2, sub_bits = geo.sub_bits, shift = shift2 + sub_bits;
+    const uint64_t P = geo.P_local;
     // A round = the bases scattered before one sweep of the table: 1 G to start with (10 bytes of key list
     // per base); part_grow doubles it when a sample turns out to be longer (VG_ROUND_KEYS pins it).
     uint64_t round_keys = 1024ull << 20, slack = 65536;
@@ -101,7 +127,10 @@ static int part_setup(vg_index* ix) {
     PartState& ps = ix->part;
     ps.view.P = (uint32_t)P;
     ps.view.shift = shift;
+    ps.view.shift2 = shift2;
+    ps.view.sub_bits = sub_bits;
     ps.view.cap = (round_keys / P) * 5 / 4 + slack;
+    ps.view.cap2 = sub_bits ? (ps.view.cap >> sub_bits) * 5 / 4 + slack : 0;
     ps.slack = slack;
     ps.view.world = 1;
     ps.view.rank = 0;
@@ -109,13 +138,17 @@ static int part_setup(vg_index* ix) {
     ps.round_keys = round_keys;
     cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), c->compute_stream);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift2) * sizeof(uint32_t), c->compute_stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), c->compute_stream);
+    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.keybuf2, (ps.view.cap2 << sub_bits) * sizeof(uint64_t));
+    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.cursor2, sizeof(unsigned long long) << sub_bits);
     if (e != cudaSuccess) {  // not enough memory for the key buffers: fall back to direct probing
         cudaFree(ps.view.keybuf);
         cudaFree(ps.view.cursor);
         cudaFree(ps.view.ctr);
+        cudaFree(ps.view.keybuf2);
+        cudaFree(ps.view.cursor2);
         ps = PartState();
         cudaGetLastError();
         return VG_OK;
@@ -142,6 +175,8 @@ static int part_setup(vg_index* ix) {
             cudaFree(ps.view.keybuf);
             cudaFree(ps.view.cursor);
             cudaFree(ps.view.ctr);
+            cudaFree(ps.view.keybuf2);
+            cudaFree(ps.view.cursor2);
             cudaFree(ix->view.rank_base);
             cudaFree(ix->view.cvec);
             cudaFree(ix->d_perm);
@@ -171,7 +206,7 @@ static int part_setup(vg_index* ix) {
                 CU(cudaStreamSynchronize(c->compute_stream));
                 ps.filter.words = ps.d_filter;
                 ps.filter.nwords = nwords;
-                vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
+                if ((size_t)nwords * 4 <= (64ull << 20)) vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
             } else {
                 cudaGetLastError();
             }
@@ -206,7 +241,7 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     phase_begin(ps, s);
     CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
     phase_end(ps, s, ps.ms_sweep, ps.n_sweep);
-    ix->launches += ps.view.P + 1;
+    ix->launches += vg::sweep_launches(ix->view, ps.view);
     ps.pending = 0;
     return VG_OK;
 }
@@ -230,6 +265,19 @@ static void part_grow(vg_index* ix, cudaStream_t s) {
         cudaGetLastError();
         ps.may_grow = false;
         return;
+    }
+    if (ps.view.sub_bits) {  // the slices' own lists grow with the coarse ones
+        const uint64_t sub_cap = (cap2 >> ps.view.sub_bits) * 5 / 4 + ps.slack;
+        uint64_t* bigger2 = nullptr;
+        if (cudaMalloc((void**)&bigger2, (sub_cap << ps.view.sub_bits) * sizeof(uint64_t)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(bigger);
+            ps.may_grow = false;
+            return;
+        }
+        cudaFree(ps.view.keybuf2);
+        ps.view.keybuf2 = bigger2;
+        ps.view.cap2 = sub_cap;
     }
     cudaFree(ps.view.keybuf);
     ps.view.keybuf = bigger;
@@ -591,6 +639,8 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->d_misc);
     cudaFree(ix->part.view.cursor);
     cudaFree(ix->part.view.ctr);
+    cudaFree(ix->part.view.keybuf2);
+    cudaFree(ix->part.view.cursor2);
     cudaFree(ix->part.d_filter);
     if (ix->part.ev0) cudaEventDestroy(ix->part.ev0);
     if (ix->part.ev1) cudaEventDestroy(ix->part.ev1);
@@ -624,6 +674,10 @@ int vg_index_timing(const vg_index* ix, double* scatter_ms, double* sweep_ms, ui
     return VG_OK;
 }
 uint32_t vg_index_partitions(const vg_index* ix) { return ix && ix->part.enabled ? ix->part.view.P : 0; }
+uint32_t vg_index_slices(const vg_index* ix) {
+    if (!ix || !ix->part.enabled) return 0;
+    return (uint32_t)(((uint64_t)ix->view.nbuckets + ((1ull << ix->part.view.shift2) - 1)) >> ix->part.view.shift2);
+}
 uint64_t vg_index_launches(const vg_index* ix) { return ix ? ix->launches : 0; }
 uint64_t vg_index_table_bytes(const vg_index* ix) { return ix ? 32ull * ix->view.nbuckets : 0; }
 

@@ -234,17 +234,11 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     // ---- geometry: the same on every rank (depends on n, world and the tuning variables only) ----
     uint64_t nb_min = (uint64_t)((double)n / W / (4.0 * load_factor)) + 1;
     if (nb_min < 64) nb_min = 64;
-    uint64_t slice_bytes = 32ull << 20;
-    if (const char* e = getenv("VG_SLICE_BYTES")) slice_bytes = strtoull(e, nullptr, 10) >= 64 ? strtoull(e, nullptr, 10) : slice_bytes;
-    while (slice_bytes > 64 && nb_min * 32 / slice_bytes < 3) slice_bytes >>= 1;
-    uint32_t shift = 0;
-    while ((32ull << (shift + 1)) <= slice_bytes) ++shift;
-    uint64_t P_local = (nb_min + (1ull << shift) - 1) >> shift;
-    while (P_local * W > vg::kMaxPartitions) {
-        ++shift;
-        P_local = (nb_min + (1ull << shift) - 1) >> shift;
-    }
-    if (P_local < 3) P_local = 3;  // the sweep retires slice p-1 while slice p is probed: needs three
+    vg::PartGeometry geo;  // a sharded table is sized by its slices; small ones shrink them until every GPU has three
+    if (!vg::part_geometry(nb_min, W, geo))
+        return fail(VG_E_INVALID, "index of %llu keys cannot be partitioned over %u GPUs", (unsigned long long)n, W);
+    const uint32_t shift2 = geo.shift2, sub_bits = geo.sub_bits, shift = shift2 + sub_bits;
+    const uint64_t P_local = geo.P_local;
     const uint64_t nb_local = P_local << shift, nb_total = nb_local * W;
     if (nb_total >= 0xffffffffull) return fail(VG_E_INVALID, "index of %llu keys needs too many buckets", (unsigned long long)n);
     if (round_bytes == 0) round_bytes = 256ull << 20;
@@ -253,6 +247,7 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     if (const char* e = getenv("VG_PART_SLACK")) slack = strtoull(e, nullptr, 10);
     const uint64_t P = P_local * W;
     const uint64_t cap = (round_bytes / P) * 5 / 4 + slack;
+    const uint64_t cap2 = sub_bits ? ((cap * W) >> sub_bits) * 5 / 4 + slack : 0;  // a coarse partition receives from W sources
 
     vg_index* ix = new vg_index();
     ix->ctx = c;
@@ -295,7 +290,10 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     }
     ps.view.P = (uint32_t)P;
     ps.view.shift = shift;
+    ps.view.shift2 = shift2;
+    ps.view.sub_bits = sub_bits;
     ps.view.cap = cap;
+    ps.view.cap2 = cap2;
     ps.view.world = W;
     ps.view.rank = (uint32_t)cm->rank;
     ps.view.P_local = (uint32_t)P_local;
@@ -309,11 +307,15 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     ps.round_keys = round_bytes;
     cudaStream_t s = c->compute_stream;
     CUB(cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long)));
-    CUB(cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift) * sizeof(uint32_t)));
+    CUB(cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift2) * sizeof(uint32_t)));
+    if (sub_bits) {
+        CUB(cudaMalloc((void**)&ps.view.keybuf2, (cap2 << sub_bits) * sizeof(uint64_t)));
+        CUB(cudaMalloc((void**)&ps.view.cursor2, sizeof(unsigned long long) << sub_bits));
+    }
     CUB(cudaMalloc((void**)&ix->d_combined, counts_bytes));
     CUB(cudaMalloc((void**)&ix->d_misc, sizeof(vg::DeviceMisc)));
     CUB(cudaMemsetAsync(ix->d_misc, 0, sizeof(vg::DeviceMisc), s));
-    CUB(cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift) * sizeof(uint32_t), s));
+    CUB(cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift2) * sizeof(uint32_t), s));
     CUB(cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), s));
     CUB(cudaMemsetAsync(ps.view.incount, 0, P * sizeof(unsigned long long), s));
     CUB(cudaMemsetAsync(ix->view.cvec, 0, cvec_bytes, s));
@@ -443,12 +445,12 @@ int vg::sharded_flush(vg_index* ix, cudaStream_t s) {
         int rc = barrier_on(cm, s);
         if (rc) return rc;
         CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
-        ix->launches += (uint64_t)ps.view.P_local + 2;
+        ix->launches += vg::sweep_launches(ix->view, ps.view) + 1;
         rc = barrier_on(cm, s);
         if (rc) return rc;
     } else {  // a group of one: the key lists and cursors are local
         CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
-        ix->launches += ps.view.P_local + 1;
+        ix->launches += vg::sweep_launches(ix->view, ps.view);
     }
     ps.pending = 0;
     return VG_OK;

@@ -141,6 +141,13 @@ struct vg_cbf {
 };
 
 namespace vg {
+struct PartGeometry {
+    uint32_t shift2;    // buckets per slice = 2^shift2
+    uint32_t sub_bits;  // slices per coarse partition = 2^sub_bits (0: the scatter bins by slice)
+    uint32_t P_local;   // partitions of the scatter per GPU
+};
+bool part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g);
+uint64_t sweep_launches(const IndexView& ix, const PartView& pv);  // kernels one sweep launches
 void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
 cudaError_t counts_in_key_order(vg_index* ix, void* d_out, int elem_bytes, cudaStream_t s);
 int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier

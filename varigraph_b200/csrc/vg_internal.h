@@ -59,7 +59,17 @@ struct PartView {
     uint32_t P;                     // slices of the whole (global) table = P_local * world
     uint32_t shift;                 // slice = global bucket >> shift
     uint64_t cap;                   // capacity of one key list; keys beyond it are probed directly
-    uint32_t* ctr;                  // 2 x (4 << shift) u32 side counters: hits of the slice being probed
+    uint32_t* ctr;                  // 2 x (4 << shift2) u32 side counters: hits of the slice being probed
+    // Two-level scatter (tables of many slices).  P / shift / cap / keybuf / cursor above then describe COARSE
+    // partitions of 2^sub_bits slices each, so that a CTA tile's k-mers always fall into a few dozen fat bins whatever
+    // the size of the table; the sweep takes one coarse list at a time and re-scatters it (rescatter_kernel) into the
+    // lists of its slices -- cap2 keys each at keybuf2, fill counts at cursor2 -- right before probing them.
+    // sub_bits == 0: one level, a partition is a slice (shift2 == shift).
+    uint32_t sub_bits;
+    uint32_t shift2;                // slice = bucket >> shift2; shift == shift2 + sub_bits
+    uint64_t cap2;
+    uint64_t* keybuf2;
+    unsigned long long* cursor2;
     // Sharded index (world > 1): slice p belongs to GPU p / P_local, and the scatter stores its keys
     // straight into that GPU's key list for source `rank` over NVLink (peer memory mapped with CUDA
     // IPC) -- the all-to-all of k-mers is the scatter's own copy-out.  Unsharded: world == 1,
@@ -73,6 +83,7 @@ struct PartView {
     unsigned long long* peer_incount[kMaxWorld];
 };
 constexpr uint32_t kMaxPartitions = 1024;
+constexpr uint32_t kMaxSubBits = 6;
 
 // On-device FASTQ parsing: per-file and per-block state (device memory) and the scratch of one context.
 struct FastqFileState {
@@ -144,6 +155,7 @@ cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint6
                                    cudaStream_t s);
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s);
+uint64_t sweep_launches(const IndexView& ix, const PartView& pv);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 // d_idx == nullptr: out[i] = count of d_key56[i]; else out[d_idx[i]] = ... (a sharded index's own keys)
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, const uint64_t* d_idx, uint64_t n, void* d_out,

@@ -677,6 +677,103 @@ __device__ __forceinline__ uint64_t ld_key_stream(const uint64_t* p) {
     return r;
 }
 
+// Second level of the scatter (PartView::sub_bits > 0): one coarse partition's key list(s) -> the key lists of its
+// Q table slices.  The binning of scatter_kernel with keys in place of text: 4096 keys per CTA tile (a thread takes
+// every 256th, so the 8-byte loads coalesce), bins in shared memory, one reservation per slice and tile, copy-out a
+// thread per bin slot.  Q <= 64, so the bins are always fat.  kMulti (sharded index): the coarse partition has `nsub`
+// lists, one per source GPU, pv.cap keys apart, their fill counts `count_stride` apart.
+template <bool kMulti>
+__global__ void __launch_bounds__(kCtaThreads, 4)
+rescatter_kernel(IndexView ix, PartView pv, ScatterCfg cfg, const uint64_t* __restrict__ lists, const unsigned long long* count_ptr,
+                 uint32_t nsub, uint32_t count_stride, uint32_t slice0, uint32_t Q, CountStats* stats) {
+    extern __shared__ __align__(16) uint64_t smem_bins[];
+    const uint32_t cap = cfg.cap;
+    unsigned long long* base_s = reinterpret_cast<unsigned long long*>(smem_bins + (size_t)Q * cfg.stride);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(base_s + Q);
+    uint32_t* cnt_s = hist + Q;
+    uint32_t* fit_s = cnt_s + Q;
+    __shared__ uint32_t max_cnt;
+    if (threadIdx.x == 0) max_cnt = 0;
+    for (uint32_t i = threadIdx.x; i < Q; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(smem_bins);
+    asm volatile("" : "+r"(bins_s));
+    uint32_t stride = cfg.stride;
+    asm volatile("" : "+r"(stride));
+    const uint32_t base_a = bins_s + ((Q * stride) << 3);
+    const TableRef mine{ix.slots, ix.rank_base, ix.cvec, false};
+    constexpr uint32_t kTileKeys = kCtaThreads * 16;
+#pragma unroll 1
+    for (uint32_t sub = 0; sub < (kMulti ? nsub : 1u); ++sub) {
+        const uint64_t* list = kMulti ? lists + (uint64_t)sub * pv.cap : lists;
+        const uint64_t n = min((uint64_t)count_ptr[kMulti ? (size_t)sub * count_stride : 0], pv.cap);
+        const uint64_t ntiles = (n + kTileKeys - 1) / kTileKeys;
+        for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint64_t keys[8];
+                uint32_t emit = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t idx = t * kTileKeys + (uint64_t)(half * 8 + j) * kCtaThreads + threadIdx.x;
+                    keys[j] = 0;
+                    if (idx < n) {
+                        keys[j] = ld_key_stream(list + idx);
+                        emit |= 1u << j;
+                    }
+                }
+                uint32_t over = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if ((emit >> j) & 1u) {
+                        const uint32_t q = ((bucket_of(keys[j], ix.nb_total) - ix.b_base) >> pv.shift2) - slice0;
+                        if (q < Q) {
+                            const uint32_t r = atomicAdd(&hist[q], 1u);
+                            if (r < cap) st_shared_u64(bins_s + ((q * stride + r) << 3), keys[j]);
+                            else over |= 1u << j;
+                        } else {
+                            over |= 1u << j;  // cannot happen with a consistent geometry; still counted exactly
+                        }
+                    }
+                }
+                if (over) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((over >> j) & 1u) {
+                            const uint32_t b = bucket_of(keys[j], ix.nb_total) - ix.b_base;
+                            const uint32_t q = (b >> pv.shift2) - slice0;
+                            if (q < Q) scatter_one_global(&pv.cursor2[q], pv.keybuf2 + (uint64_t)q * pv.cap2, pv.cap2, mine, ix.nbuckets, b, keys[j], stats);
+                            else probe_one_direct(mine, ix.nbuckets, b, keys[j], stats);
+                        }
+                }
+            }
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; q < Q; q += blockDim.x) {
+                const uint32_t m = min(hist[q], cap);
+                hist[q] = 0;
+                unsigned long long b = 0;
+                if (m) b = atomicAdd(&pv.cursor2[q], (unsigned long long)m);
+                cnt_s[q] = m;
+                if (m) atomicMax(&max_cnt, m);
+                fit_s[q] = b >= pv.cap2 ? 0u : (uint32_t)min((unsigned long long)m, pv.cap2 - b);
+                base_s[q] = (unsigned long long)(pv.keybuf2 + (uint64_t)q * pv.cap2 + b);
+            }
+            __syncthreads();
+            const uint32_t row = max_cnt, nslots = Q * row, magic = c_magic[row];
+            for (uint32_t s = threadIdx.x; s < nslots; s += blockDim.x) {
+                const uint32_t q = __umulhi(s, magic), i = s - q * row;
+                if (i < cnt_s[q]) {
+                    const uint64_t key = ld_shared_u64(bins_s + ((q * stride + i) << 3));
+                    if (i < fit_s[q]) reinterpret_cast<uint64_t*>(ld_shared_u64(base_a + (q << 3)))[i] = key;
+                    else probe_one_direct(mine, ix.nbuckets, bucket_of(key, ix.nb_total) - ix.b_base, key, stats);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) max_cnt = 0;
+        }
+    }
+}
+
 // K2 + K3 of the partitioned path.  All probes of a key list fall into one L2-resident slice of the
 // table [b0, b1), so a hit is recorded with a fire-and-forget 32-bit reduction into the slice's
 // side counters (also L2-resident) instead of a CAS round trip; retire_slice folds them into the
@@ -797,14 +894,14 @@ template <int kBatch, bool kMulti>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 4)
 probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ lists, const unsigned long long* count_ptr, uint32_t nsub,
                    uint32_t count_stride, uint64_t cap, uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0,
-                   uint32_t r1, uint32_t* ctr_prev, CountStats* stats) {
+                   uint32_t r1, uint32_t* ctr_prev, uint32_t f0, uint32_t f1, CountStats* stats) {
     __shared__ unsigned long long blk_hit;
     if (threadIdx.x == 0) blk_hit = 0;
-    {
+    {   // buckets [f0, f1) -> L2: this slice, or (prefetch-ahead) the next one, whose probes then never wait for DRAM
         const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const uint64_t gsz = (uint64_t)gridDim.x * blockDim.x;
         const char* tbl = (const char*)ix.slots;
-        for (uint64_t line = (uint64_t)b0 * 32 / 128 + gtid; line * 128 < (uint64_t)b1 * 32; line += gsz)
+        for (uint64_t line = (uint64_t)f0 * 32 / 128 + gtid; line * 128 < (uint64_t)f1 * 32; line += gsz)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + line * 128));
     }
     if (r1 > r0) retire_slice(ix, r0, r1, ctr_prev);
@@ -1355,6 +1452,7 @@ cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint6
     return cudaGetLastError();
 }
 
+static cudaError_t ensure_magic();
 cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
                            uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
                            cudaStream_t s, const unsigned int* d_skip) {
@@ -1371,17 +1469,9 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
     const uint32_t want = (uint32_t)(expect * capx) + 8;
     auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 16; };
-    static bool magic_on[64] = {};  // constant memory is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    bool& magic_ready = magic_on[dev & 63];
-    if (!magic_ready) {
-        uint32_t m[kMaxBinCap + 1];
-        m[0] = 0;
-        for (uint32_t d = 1; d <= kMaxBinCap; ++d) m[d] = (uint32_t)((1ull << 32) / d) + 1u;
-        cudaError_t e = cudaMemcpyToSymbol(c_magic, m, sizeof m);
+    {
+        cudaError_t e = ensure_magic();
         if (e != cudaSuccess) return e;
-        magic_ready = true;
     }
     uint32_t cap = want > kMaxBinCap ? kMaxBinCap : want;
     while (cap > 4 && bytes(cap) > budget) --cap;
@@ -1403,45 +1493,109 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     return cudaGetLastError();
 }
 
+static cudaError_t ensure_magic() {  // c_magic lives in constant memory, which is per device
+    static bool magic_on[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& ready = magic_on[dev & 63];
+    if (ready) return cudaSuccess;
+    static uint32_t m[kMaxBinCap + 1];
+    m[0] = 0;
+    for (uint32_t d = 1; d <= kMaxBinCap; ++d) m[d] = (uint32_t)((1ull << 32) / d) + 1u;
+    cudaError_t e = cudaMemcpyToSymbol(c_magic, m, sizeof m);
+    if (e == cudaSuccess) ready = true;
+    return e;
+}
+
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
                                     cudaStream_t s) {
     const bool b4 = count_variant() == 4;
     int occ = 0;
     auto slice = [&](uint32_t p, uint32_t& b0, uint32_t& b1) {  // local slice p of THIS table
-        b0 = p << pv.shift;
-        const uint64_t e = ((uint64_t)(p + 1)) << pv.shift;
+        b0 = p << pv.shift2;
+        const uint64_t e = ((uint64_t)(p + 1)) << pv.shift2;
         b1 = (uint32_t)(e > ix.nbuckets ? ix.nbuckets : e);
     };
-    const size_t ctr_elems = (size_t)4 << pv.shift;
+    const size_t ctr_elems = (size_t)4 << pv.shift2;
     const bool sharded = pv.world > 1;
     const uint32_t nsub = sharded ? pv.world : 1u;
     // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice.
     // A sharded index has one key list per source GPU and slice: the kMulti kernel walks them all.
-    auto launch = [&](auto kern, const uint64_t* lists, const unsigned long long* cnt, uint32_t b0, uint32_t b1,
-                      uint32_t* cur, uint32_t r0, uint32_t r1, uint32_t* prv) {
+    auto launch = [&](auto kern, const uint64_t* lists, const unsigned long long* cnt, uint32_t nlists, uint64_t cap, uint32_t b0,
+                      uint32_t b1, uint32_t* cur, uint32_t r0, uint32_t r1, uint32_t* prv, uint32_t f0, uint32_t f1) {
         if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-        kern<<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, lists, cnt, nsub, pv.P_local, pv.cap, b0, b1, cur, r0, r1, prv, d_stats);
+        kern<<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, lists, cnt, nlists, pv.P_local, cap, b0, b1, cur, r0, r1, prv, f0, f1, d_stats);
     };
-    for (uint32_t p = 0; p <= pv.P_local; ++p) {
-        uint32_t b0 = 0, b1 = 0, r0 = 0, r1 = 0;
-        if (p < pv.P_local) slice(p, b0, b1);
+    const uint32_t nslices = (uint32_t)(((uint64_t)ix.nbuckets + ((1ull << pv.shift2) - 1)) >> pv.shift2);
+    // VG_PREFETCH_AHEAD=1: launch p pulls slice p+1 into L2 while it probes slice p (the first launch of a group
+    // pulls its own slice as well); default: every launch pulls the slice it probes.
+    const char* ahead_env = getenv("VG_PREFETCH_AHEAD");
+    const bool ahead = ahead_env && atoi(ahead_env) != 0;
+    auto probe_step = [&](uint32_t p, const uint64_t* lists, const unsigned long long* cnt, bool multi, uint64_t cap, bool first_of_group) {
+        uint32_t b0 = 0, b1 = 0, r0 = 0, r1 = 0, f0 = 0, f1 = 0;
+        if (p < nslices) slice(p, b0, b1);
         if (p > 0) slice(p - 1, r0, r1);
+        if (!ahead) {
+            f0 = b0, f1 = b1;
+        } else if (p < nslices) {
+            uint32_t n0 = b1, n1 = b1;
+            if (p + 1 < nslices) slice(p + 1, n0, n1);
+            f0 = first_of_group ? b0 : n0;
+            f1 = n1;
+        }
         uint32_t* cur = pv.ctr + (size_t)(p & 1) * ctr_elems;
         uint32_t* prv = pv.ctr + (size_t)((p + 1) & 1) * ctr_elems;
-        const uint32_t q = p < pv.P_local ? p : 0;
-        const uint64_t* lists = pv.keybuf + (uint64_t)q * nsub * pv.cap;
-        const unsigned long long* cnt = (sharded ? pv.incount : pv.cursor) + q;
-        if (sharded) {
-            if (b4) launch(probe_slice_kernel<4, true>, lists, cnt, b0, b1, cur, r0, r1, prv);
-            else launch(probe_slice_kernel<8, true>, lists, cnt, b0, b1, cur, r0, r1, prv);
+        if (multi) {
+            if (b4) launch(probe_slice_kernel<4, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1);
+            else launch(probe_slice_kernel<8, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1);
         } else {
-            if (b4) launch(probe_slice_kernel<4, false>, lists, cnt, b0, b1, cur, r0, r1, prv);
-            else launch(probe_slice_kernel<8, false>, lists, cnt, b0, b1, cur, r0, r1, prv);
+            if (b4) launch(probe_slice_kernel<4, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1);
+            else launch(probe_slice_kernel<8, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1);
         }
+    };
+    if (pv.sub_bits == 0) {
+        for (uint32_t p = 0; p <= pv.P_local; ++p) {
+            const uint32_t q = p < pv.P_local ? p : 0;
+            probe_step(p, pv.keybuf + (uint64_t)q * nsub * pv.cap, (sharded ? pv.incount : pv.cursor) + q, sharded, pv.cap, p == 0);
+        }
+    } else {
+        // two levels: coarse list c -> the lists of its Q slices (rescatter), then those slices are probed
+        cudaError_t e = ensure_magic();
+        if (e != cudaSuccess) return e;
+        const uint32_t Q = 1u << pv.sub_bits;
+        const uint32_t want = (uint32_t)(1.6 * (kCtaThreads * 16) / Q) + 8;
+        auto bytes = [&](uint32_t cp) { return (size_t)Q * ((size_t)(cp | 1u) * 8 + 20) + 16; };
+        uint32_t cap = want > kMaxBinCap ? kMaxBinCap : want;
+        while (cap > 4 && bytes(cap) > (size_t)52 * 1024) --cap;
+        const ScatterCfg cfg{cap, cap | 1u};
+        const size_t smem = bytes(cap);
+        using RK = void (*)(IndexView, PartView, ScatterCfg, const uint64_t*, const unsigned long long*, uint32_t, uint32_t, uint32_t,
+                            uint32_t, CountStats*);
+        RK rk = sharded ? (RK)rescatter_kernel<true> : (RK)rescatter_kernel<false>;
+        e = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int rocc = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, rk, kCtaThreads, smem) != cudaSuccess || rocc < 1) rocc = 1;
+        uint32_t p = 0;
+        for (uint32_t c = 0; c < pv.P_local && p < nslices; ++c) {
+            e = cudaMemsetAsync(pv.cursor2, 0, Q * sizeof(unsigned long long), s);
+            if (e != cudaSuccess) return e;
+            rk<<<(unsigned)(nsm * rocc), kCtaThreads, smem, s>>>(ix, pv, cfg, pv.keybuf + (uint64_t)c * nsub * pv.cap,
+                                                               (sharded ? pv.incount : pv.cursor) + c, nsub, pv.P_local, c << pv.sub_bits, Q,
+                                                               d_stats);
+            for (uint32_t q = 0; q < Q && p < nslices; ++q, ++p)
+                probe_step(p, pv.keybuf2 + (uint64_t)q * pv.cap2, pv.cursor2 + q, false, pv.cap2, q == 0);
+        }
+        probe_step(nslices, pv.keybuf2, pv.cursor2, false, pv.cap2, false);  // retires the last slice, probes nothing
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || sharded) return e;  // sharded: publish_counts re-armed the cursors already
     return cudaMemsetAsync(pv.cursor, 0, pv.P * sizeof(unsigned long long), s);
+}
+
+uint64_t sweep_launches(const IndexView& ix, const PartView& pv) {
+    const uint64_t nslices = ((uint64_t)ix.nbuckets + ((1ull << pv.shift2) - 1)) >> pv.shift2;
+    return nslices + 1 + (pv.sub_bits ? pv.P_local : 0);
 }
 
 cudaError_t launch_extract(const IndexView& ix, const uint64_t* d_key56, const uint64_t* d_idx, uint64_t n, void* d_out,
