@@ -94,6 +94,17 @@ bool vg::part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g) {
     return true;
 }
 
+int vg::fetch_slice_ranks(vg_index* ix) {
+    PartState& ps = ix->part;
+    const uint64_t per = 1ull << ps.view.shift2;
+    const uint64_t nslices = (ix->view.nbuckets + per - 1) / per;
+    ps.slice_rank.assign((size_t)nslices + 1, 0);
+    CU(cudaMemcpy2D(ps.slice_rank.data(), sizeof(uint32_t), ix->view.rank_base, per * sizeof(uint32_t), sizeof(uint32_t), (size_t)nslices,
+                    cudaMemcpyDeviceToHost));
+    ps.slice_rank[(size_t)nslices] = (uint32_t)ix->m_slots;
+    return VG_OK;
+}
+
 static int part_setup(vg_index* ix) {
     vg_ctx* c = ix->ctx;
     const char* env = getenv("VG_PARTITION");
@@ -190,6 +201,10 @@ static int part_setup(vg_index* ix) {
         }
     }
     ps.enabled = true;
+    {
+        int rc = vg::fetch_slice_ranks(ix);
+        if (rc) return rc;
+    }
     // Presence pre-filter: 4 bits per key (measured best on B200: 30 MB for the chr20 index beats both
     // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
     // the streaming traffic; larger indexes go without.  VG_PREFILTER=0 disables it.
@@ -239,7 +254,8 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     if (ix->sharded) return VG_OK;  // a sharded round ends only in the collective calls (vg_count_flush / _end)
     if (!ps.enabled || ps.pending == 0) return VG_OK;
     phase_begin(ps, s);
-    CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+    CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
+                                   ix->ctx->nsm, s));
     phase_end(ps, s, ps.ms_sweep, ps.n_sweep);
     ix->launches += vg::sweep_launches(ix->view, ps.view);
     ps.pending = 0;
@@ -417,8 +433,13 @@ int vg_ctx_create(int device, int buffer_mb, vg_ctx** out) {
     if (const char* e = getenv("VG_CTAS_PER_SM")) c->ctas_per_sm = atoi(e);
     c->nsm = vg::sm_count(device);
     c->chunk_bytes = (size_t)buffer_mb << 20;
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+    cudaError_t se = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        delete c;
+        return fail(VG_E_CUDA, "vg_ctx_create: %s", cudaGetErrorString(se));
+    }
     c->own_compute_stream = c->compute_stream;
     *out = c;
     return VG_OK;
@@ -710,7 +731,9 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
     vg_ctx* c = ix->ctx;
     DeviceGuard g(c->device);
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
-    if (cuda_stream) {  // order after vg_count_begin's clears on the context stream
+    if (ix->part.enabled && s != c->compute_stream)
+        return fail(VG_E_INVALID, "a partitioned index counts on the context stream only: use vg_ctx_set_stream");
+    if (cuda_stream && s != c->compute_stream) {  // order after vg_count_begin's clears on the context stream
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, c->compute_stream));
@@ -718,8 +741,6 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
         CU(cudaEventDestroy(ev));
         ix->foreign_streams = true;
     }
-    if (ix->part.enabled && s != c->compute_stream)
-        return fail(VG_E_INVALID, "a partitioned index counts on the context stream only: use vg_ctx_set_stream");
     return count_device_chunk(ix, (const uint8_t*)dev_bases, nbytes, s);
 }
 
@@ -736,6 +757,7 @@ int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
     int rc = ctx_ensure_ring(c, std::max<int>(want, (int)c->ring.size()), !pinned);
     if (rc) return rc;
     uint64_t off = 0;
+    int last = -1;
     while (off < nbytes) {
         uint64_t len = std::min<uint64_t>(c->chunk_bytes, nbytes - off);
         if (off + len < nbytes) {  // cut at a read boundary
@@ -758,7 +780,12 @@ int vg_count_submit(vg_index* ix, const char* host_bases, uint64_t nbytes) {
         rc = vg::enqueue_piece(ix, si, src, len);
         if (rc) return rc;
         off += len;
+        last = si;
     }
+    // "returns once the bytes are consumed from host_bases": a pinned source is DMA-ed from where it lies, so the
+    // last copy must have left the caller's buffer before the caller may refill it (pageable sources were copied
+    // into the ring's own pinned twins already)
+    if (pinned && last >= 0) CU(cudaEventSynchronize(c->ring[(size_t)last].copied));
     return VG_OK;
 }
 
@@ -957,6 +984,7 @@ int vg_encode_positions_device(vg_ctx* c, const void* dev_bases, uint64_t nbytes
 
 int vg_encode_positions(vg_ctx* c, const char* host_bases, uint64_t nbytes, uint32_t k, uint64_t* host_keys_out) {
     if (!c || (!host_bases && nbytes) || (!host_keys_out && nbytes)) return fail(VG_E_INVALID, "NULL argument");
+    if (k < 1 || k > 28) return fail(VG_E_INVALID, "k=%u outside 1..28", k);
     if (nbytes == 0) return VG_OK;
     DeviceGuard g(c->device);
     uint8_t* d_b = nullptr;
@@ -976,7 +1004,6 @@ int vg_encode_positions(vg_ctx* c, const char* host_bases, uint64_t nbytes, uint
         rc = fail(VG_E_CUDA, "vg_encode_positions: %s", cudaGetErrorString(e));
     cudaFree(d_b);
     cudaFree(d_k);
-    if (rc == VG_OK && (k < 1 || k > 28)) rc = fail(VG_E_INVALID, "k=%u outside 1..28", k);
     return rc;
 }
 

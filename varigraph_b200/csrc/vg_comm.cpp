@@ -414,6 +414,8 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
         ix->m_slots = total;
         cudaFree(ix->d_key56);
         ix->d_key56 = nullptr;
+        int frc = vg::fetch_slice_ranks(ix);
+        if (frc) return bail(frc);
     }
     if (nwords) {
         ps.filter.words = ps.d_filter;
@@ -444,12 +446,14 @@ int vg::sharded_flush(vg_index* ix, cudaStream_t s) {
         CU(vg::launch_publish_counts(ps.view, s));
         int rc = barrier_on(cm, s);
         if (rc) return rc;
-        CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+        CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
+                                       ix->ctx->nsm, s));
         ix->launches += vg::sweep_launches(ix->view, ps.view) + 1;
         rc = barrier_on(cm, s);
         if (rc) return rc;
     } else {  // a group of one: the key lists and cursors are local
-        CU(vg::launch_probe_partitions(ix->view, ps.view, &ix->d_misc->stats, ix->ctx->nsm, s));
+        CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
+                                       ix->ctx->nsm, s));
         ix->launches += vg::sweep_launches(ix->view, ps.view);
     }
     ps.pending = 0;

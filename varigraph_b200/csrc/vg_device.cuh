@@ -219,14 +219,59 @@ struct KmerParams {
     uint64_t mask;
 };
 
+// Where a kernel reads the chunk's text from: global memory as it lies (streaming 128-bit loads), or a copy of the
+// CTA's tile that a bulk async copy (TMA) staged in shared memory (byte `off0` of the chunk sits at shared address saddr).
+struct GlobalText {
+    const uint8_t* al;
+    __device__ __forceinline__ uint4 ld16(int64_t off) const { return ld_stream16(al + off); }
+    __device__ __forceinline__ uint32_t ld4(int64_t off) const {
+        uint32_t r;
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(al + off));
+        return r;
+    }
+};
+struct SharedText {
+    uint32_t saddr;
+    int64_t off0;
+    __device__ __forceinline__ uint4 ld16(int64_t off) const {
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr + (uint32_t)(off - off0)));
+        return r;
+    }
+    __device__ __forceinline__ uint32_t ld4(int64_t off) const {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr + (uint32_t)(off - off0)));
+        return r;
+    }
+};
+
+// One 32-bit word of text -> bits 0-7: its four 2-bit codes (first base highest), bits 8-11: their validity
+// (first base in bit 11).  Out-of-range bytes are invalid.
+template <class Src>
+__device__ __forceinline__ uint32_t encode_word(const Chunk& c, const Src& src, int64_t off, const uint8_t* lut) {
+    if (off + 4 <= c.lo || off >= c.hi || off < 0) return 0;
+    const uint32_t t = src.ld4(off);
+    const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
+    uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] | w4[768 + (t >> 24)];
+    if (off < c.lo || off + 4 > c.hi) {
+        uint32_t keep = 0xffu;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (off + j >= c.lo && off + j < c.hi) keep |= 1u << (11 - j);
+        v &= keep;
+    }
+    return v;
+}
+
 // Encode one 16-byte segment to (2-bit packed, first base in the top bits; validity mask, first
 // base in bit 15).  Out-of-range bytes are invalid.
-__device__ __forceinline__ void encode_seg(const Chunk& c, int64_t off, const uint8_t* lut,
+template <class Src>
+__device__ __forceinline__ void encode_seg(const Chunk& c, const Src& src, int64_t off, const uint8_t* lut,
                                            uint32_t& packed, uint32_t& vmask) {
     packed = 0;
     vmask = 0;
     if (off + kSegBytes <= c.lo || off >= c.hi || off < 0) return;
-    uint4 w = ld_stream16(c.al + off);
+    uint4 w = src.ld16(off);
     uint32_t ws[4] = {w.x, w.y, w.z, w.w};
     const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
 #pragma unroll
@@ -258,14 +303,26 @@ struct OddEncoder {
     uint32_t all_k;  // bit (15 - j): the k bytes ending at own position j are all valid
 
     __device__ __forceinline__ void init(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        init(c, GlobalText{c.al}, off, kp, lut);
+    }
+    template <class Src>
+    __device__ __forceinline__ void init(const Chunk& c, const Src& src, int64_t off, const KmerParams& kp, const uint8_t* lut) {
         const int lane = threadIdx.x & 31;
         uint32_t v0;
-        encode_seg(c, off, lut, p0, v0);
-        uint32_t ex = 0, exv = 0;
-        if (lane < 2) encode_seg(c, off - 32, lut, ex, exv);
-        // lane 0 holds segment (warp_off - 32), lane 1 holds segment (warp_off - 16)
-        uint32_t ex0 = __shfl_sync(kFullMask, ex, 0), exv0 = __shfl_sync(kFullMask, exv, 0);
-        uint32_t ex1 = __shfl_sync(kFullMask, ex, 1), exv1 = __shfl_sync(kFullMask, exv, 1);
+        encode_seg(c, src, off, lut, p0, v0);
+        // The 32 bases in front of the warp's text (what lanes 0 and 1 lack a left neighbour for): lanes 0-7 encode one
+        // 32-bit word each and everybody collects the eight results -- a few dozen instructions, where two lanes
+        // running the whole 16-byte encoder would cost every warp two full segments' worth of issue slots.
+        uint32_t wv = 0;
+        if (lane < 8) wv = encode_word(c, src, off - 16 * lane - 32 + 4 * lane, lut);
+        uint32_t x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = __shfl_sync(kFullMask, wv, q);
+        // segment (warp_off - 32) from words 0-3, segment (warp_off - 16) from words 4-7
+        const uint32_t ex0 = ((x[0] & 0xffu) << 24) | ((x[1] & 0xffu) << 16) | ((x[2] & 0xffu) << 8) | (x[3] & 0xffu);
+        const uint32_t exv0 = ((x[0] >> 8) << 12) | ((x[1] >> 8) << 8) | ((x[2] >> 8) << 4) | (x[3] >> 8);
+        const uint32_t ex1 = ((x[4] & 0xffu) << 24) | ((x[5] & 0xffu) << 16) | ((x[6] & 0xffu) << 8) | (x[7] & 0xffu);
+        const uint32_t exv1 = ((x[4] >> 8) << 12) | ((x[5] >> 8) << 8) | ((x[6] >> 8) << 4) | (x[7] >> 8);
         uint32_t p1 = __shfl_up_sync(kFullMask, p0, 1), v1 = __shfl_up_sync(kFullMask, v0, 1);
         uint32_t p2 = __shfl_up_sync(kFullMask, p0, 2), v2 = __shfl_up_sync(kFullMask, v0, 2);
         if (lane == 0) { p1 = ex1; v1 = exv1; p2 = ex0; v2 = exv0; }

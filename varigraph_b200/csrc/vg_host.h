@@ -79,6 +79,7 @@ struct PartState {
     bool may_grow = false;     // rounds double (up to 4 G bases) when a sample needs more than one
     vg::PrefilterView filter{nullptr, 0};
     uint32_t* d_filter = nullptr;
+    std::vector<uint32_t> slice_rank;  // cvec position of the first slot of every table slice (+ the total): what to prefetch
     // diagnostic (vg_index_set_timing): CUDA events around every scatter launch and every sweep, accumulated
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -148,6 +149,7 @@ struct PartGeometry {
 };
 bool part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g);
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv);  // kernels one sweep launches
+int fetch_slice_ranks(vg_index* ix);  // fills part.slice_rank from rank_base (after the rank scan)
 void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
 cudaError_t counts_in_key_order(vg_index* ix, void* d_out, int elem_bytes, cudaStream_t s);
 int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier

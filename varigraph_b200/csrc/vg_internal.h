@@ -153,8 +153,9 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
                            cudaStream_t s, const unsigned int* d_skip = nullptr);
 cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k,
                                    cudaStream_t s);
-cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
-                                    cudaStream_t s);
+// h_slice_rank (host, slices + 1 entries, may be NULL): cvec position of the first slot of each slice of this table
+cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, const uint32_t* h_slice_rank, CountStats* d_stats,
+                                    int nsm, cudaStream_t s);
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 // d_idx == nullptr: out[i] = count of d_key56[i]; else out[d_idx[i]] = ... (a sharded index's own keys)

@@ -537,13 +537,41 @@ __device__ __noinline__ void scatter_one_global(unsigned long long* cursor_p, ui
     else probe_one_direct(t, nbuckets, b, key, stats);
 }
 
+// ---- bulk async copies (TMA, cp.async.bulk) with mbarrier completion: the tile load of scatter_kernel<.., kTma> ----
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on mbar
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar) : "memory");
+}
+
 // K1 of the partitioned path.  Per 4 KiB CTA tile, eight positions per lane at a time: encode + hash,
 // drop what the presence pre-filter rules out, and append each survivor to its table slice's bin in
 // shared memory (rank = shared-memory atomic).  After a barrier the bins are copied out: one global
 // reservation per slice and tile (a thread per slice), a second barrier, then a thread per bin slot
 // -- a tile's run for a slice is contiguous in the slice's key list, so the 8-byte stores coalesce
 // run by run whatever the number of slices (a warp per bin wastes lanes once bins get short).
-template <bool kOdd>
+// kTma: the tile's text (plus the 32 bytes in front of it) is staged in shared memory by a bulk async copy that one
+// thread issues a whole tile ahead (two buffers, one mbarrier each): the load latency never sits in front of the
+// encoder and the LSU only sees shared-memory loads.
+template <bool kOdd, bool kTma>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
@@ -571,8 +599,39 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     asm volatile("" : "+r"(stride));
     const uint32_t base_a = bins_s + ((P * stride) << 3);  // base_s[], same address space, same reason
     uint32_t n_pos = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    constexpr int kStage = kTileBytes + 32;
+    __shared__ __align__(16) uint8_t tile_s[kTma ? 2 * kStage : 16];
+    __shared__ __align__(8) uint64_t tile_bar[2];
+    const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(tile_s), bar_a = (uint32_t)__cvta_generic_to_shared(tile_bar);
+    // stage tile `t` (grid-stride numbering) into buffer `b`: bytes [start, start + kStage) of the chunk, clipped to the
+    // 16-byte aligned extent of the caller's buffer
+    auto stage = [&](int64_t t, uint32_t b) {
+        const int64_t start = (first_tile + t) * kTileBytes - 32;
+        const int64_t s0 = start < 0 ? 0 : start, e0 = min(start + kStage, (c.hi + 15) & ~(int64_t)15);
+        if (e0 > s0) {
+            mbar_expect_tx(bar_a + 8 * b, (uint32_t)(e0 - s0));
+            bulk_g2s(tile_a + b * kStage + (uint32_t)(s0 - start), c.al + s0, (uint32_t)(e0 - s0), bar_a + 8 * b);
+        } else {
+            mbar_arrive(bar_a + 8 * b);
+        }
+    };
+    if (kTma && kOdd) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar_a, 1);
+            mbar_init(bar_a + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if ((int64_t)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+        }
+        __syncthreads();
+    }
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
+        if (kTma && kOdd) {
+            // every thread is past the previous tile's barriers, so nobody still reads the other buffer
+            if (threadIdx.x == 0 && t + gridDim.x < ntiles) stage(t + gridDim.x, (it + 1) & 1);
+            mbar_wait(bar_a + 8 * (it & 1), (it >> 1) & 1);
+        }
         // ---- encode, filter, bin -----------------------------------------------------------------
         constexpr int kGroups = 8 / kFilterSpan;
         constexpr uint32_t kGroupMask = (1u << kFilterSpan) - 1u;
@@ -615,7 +674,8 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
         };
         if (kOdd) {
             OddEncoder enc;
-            enc.init(c, off, kp, lut);
+            if (kTma) enc.init(c, SharedText{tile_a + (it & 1) * kStage, (first_tile + t) * kTileBytes - 32}, off, kp, lut);
+            else enc.init(c, off, kp, lut);
             uint64_t keys[8], pairs[kGroups];
             uint32_t emit = enc.next<8, false, true>(kp, keys, pairs);
             n_pos += __popc(emit);
@@ -865,23 +925,47 @@ __device__ __forceinline__ void probe_and_red(const IndexView& ix, const uint64_
 }
 
 // Folds the side counters of slice [b0, b1) into the count vector: c = min(255, c + hits) at rank_base[b] + slot.
-// One bucket (16 bytes of counters) per thread and step; neighbouring buckets own neighbouring bytes of cvec.
-// Plain byte loads / stores are safe: nothing else touches these bytes while the slice is retired (the sweep
-// needs >= 3 slices, so a key spilling over the table's end never lands in the slice being retired, and the
+// One bucket (16 bytes of counters) per thread and step, kRetireBatch buckets in flight per thread: the three
+// dependent accesses (counters -> rank_base -> counts) are what this pass costs, so they are issued batch-wise and
+// the launch that probed the slice has already pulled its rank_base and cvec lines into L2.  Neighbouring buckets own
+// neighbouring bytes of cvec.  Plain byte stores are safe: nothing else touches these bytes while the slice is retired
+// (the sweep needs >= 3 slices, so a key spilling over the table's end never lands in the slice being retired, and the
 // 32-bit CAS of such a spill elsewhere never changes a byte it does not own).
+constexpr int kRetireBatch = 4;
 __device__ __forceinline__ void retire_slice(const IndexView& ix, uint32_t b0, uint32_t b1, uint32_t* ctr) {
     const uint64_t nb = b1 - b0;
     const uint32_t* rb = ix.rank_base + b0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) {
-        const uint4 c = *reinterpret_cast<const uint4*>(ctr + 4 * i);
-        if (c.x | c.y | c.z | c.w) {
-            uint8_t* cv = ix.cvec + rb[i];
-            const uint32_t cs[4] = {c.x, c.y, c.z, c.w};
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nb; i0 += kRetireBatch * stride) {
+        uint4 c[kRetireBatch];
+        uint32_t base[kRetireBatch], w0[kRetireBatch], w1[kRetireBatch];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (cs[j]) cv[j] = (uint8_t)min(255u, (uint32_t)cv[j] + min(cs[j], 255u));
-            *reinterpret_cast<uint4*>(ctr + 4 * i) = make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < kRetireBatch; ++u) {
+            const uint64_t i = i0 + u * stride;
+            c[u] = i < nb ? *reinterpret_cast<const uint4*>(ctr + 4 * i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kRetireBatch; ++u) base[u] = (c[u].x | c[u].y | c[u].z | c[u].w) ? rb[i0 + u * stride] : 0u;
+#pragma unroll
+        for (int u = 0; u < kRetireBatch; ++u) {  // the bucket's four counts: two aligned words (cvec is padded)
+            w0[u] = w1[u] = 0;
+            if (c[u].x | c[u].y | c[u].z | c[u].w) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ix.cvec + (base[u] & ~3u));
+                w0[u] = wp[0];
+                w1[u] = wp[1];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRetireBatch; ++u) {
+            if (c[u].x | c[u].y | c[u].z | c[u].w) {
+                const uint32_t old4 = __funnelshift_r(w0[u], w1[u], (base[u] & 3u) * 8u);
+                uint8_t* cv = ix.cvec + base[u];
+                const uint32_t cs[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cs[j]) cv[j] = (uint8_t)min(255u, ((old4 >> (8 * j)) & 0xffu) + min(cs[j], 255u));
+                *reinterpret_cast<uint4*>(ctr + 4 * (i0 + u * stride)) = make_uint4(0, 0, 0, 0);
+            }
         }
     }
 }
@@ -894,18 +978,25 @@ template <int kBatch, bool kMulti>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 4)
 probe_slice_kernel(IndexView ix, const uint64_t* __restrict__ lists, const unsigned long long* count_ptr, uint32_t nsub,
                    uint32_t count_stride, uint64_t cap, uint32_t b0, uint32_t b1, uint32_t* ctr_cur, uint32_t r0,
-                   uint32_t r1, uint32_t* ctr_prev, uint32_t f0, uint32_t f1, CountStats* stats) {
+                   uint32_t r1, uint32_t* ctr_prev, uint32_t f0, uint32_t f1, uint32_t c0, uint32_t c1, CountStats* stats) {
     __shared__ unsigned long long blk_hit;
     if (threadIdx.x == 0) blk_hit = 0;
-    {   // buckets [f0, f1) -> L2: this slice, or (prefetch-ahead) the next one, whose probes then never wait for DRAM
+    __syncthreads();
+    {   // buckets [f0, f1) -> L2: this slice, or (prefetch-ahead) the next one, whose probes then never wait for DRAM;
+        // and what the NEXT launch needs to retire the slice probed here: its rank_base entries and its counts [c0, c1)
         const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const uint64_t gsz = (uint64_t)gridDim.x * blockDim.x;
         const char* tbl = (const char*)ix.slots;
         for (uint64_t line = (uint64_t)f0 * 32 / 128 + gtid; line * 128 < (uint64_t)f1 * 32; line += gsz)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + line * 128));
+        const char* rbp = (const char*)ix.rank_base;
+        for (uint64_t line = (uint64_t)b0 * 4 / 128 + gtid; line * 128 < (uint64_t)b1 * 4; line += gsz)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + line * 128));
+        const char* cvp = (const char*)ix.cvec;
+        for (uint64_t line = (uint64_t)c0 / 128 + gtid; line * 128 < (uint64_t)c1; line += gsz)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cvp + line * 128));
     }
-    if (r1 > r0) retire_slice(ix, r0, r1, ctr_prev);
-    __syncthreads();
+    if (r1 > r0) retire_slice(ix, r0, r1, ctr_prev);  // independent of the probes below: no barrier in between
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp_gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1459,13 +1550,18 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     if (ntiles <= 0) return cudaSuccess;
     Chunk c = make_chunk(d_bases, nbytes, d_skip);
     using KernelT = void (*)(IndexView, PartView, PrefilterView, ScatterCfg, Chunk, int64_t, int64_t, CountStats*);
-    KernelT kern = (ix.k & 1) ? (KernelT)scatter_kernel<true> : (KernelT)scatter_kernel<false>;
+    // VG_SCATTER_TMA=1: the tile load as a bulk async copy into shared memory, a tile ahead (A/B knob; odd k)
+    const char* tma_env = getenv("VG_SCATTER_TMA");
+    const bool tma = tma_env && atoi(tma_env) != 0 && (ix.k & 1);
+    KernelT kern = (ix.k & 1) ? (tma ? (KernelT)scatter_kernel<true, true> : (KernelT)scatter_kernel<true, false>)
+                              : (KernelT)scatter_kernel<false, false>;
     // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
     // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
     // path, so this only tunes speed.
     static const double capx = [] { const char* e = getenv("VG_SCATTER_CAPX"); return e ? atof(e) : 1.8; }();
-    static const size_t budget = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52) * 1024; }();
+    static const size_t budget_kb = [] { const char* e = getenv("VG_SCATTER_SMEM_KB"); return (size_t)(e ? atoi(e) : 52); }();
+    const size_t budget = (budget_kb - (tma ? 9 : 0)) * 1024;  // the staged tiles take 8.3 KB of a CTA's share
     const double expect = (pf.words ? 0.6 : 1.0) * kTileBytes / (double)pv.P;
     const uint32_t want = (uint32_t)(expect * capx) + 8;
     auto bytes = [&](uint32_t cp) { return (size_t)pv.P * ((size_t)(cp | 1u) * 8 + 20) + 16; };
@@ -1507,8 +1603,8 @@ static cudaError_t ensure_magic() {  // c_magic lives in constant memory, which 
     return e;
 }
 
-cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, CountStats* d_stats, int nsm,
-                                    cudaStream_t s) {
+cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, const uint32_t* h_slice_rank, CountStats* d_stats,
+                                    int nsm, cudaStream_t s) {
     const bool b4 = count_variant() == 4;
     int occ = 0;
     auto slice = [&](uint32_t p, uint32_t& b0, uint32_t& b1) {  // local slice p of THIS table
@@ -1522,9 +1618,11 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
     // sweep: launch p probes slice p and retires slice p-1; one extra launch retires the last slice.
     // A sharded index has one key list per source GPU and slice: the kMulti kernel walks them all.
     auto launch = [&](auto kern, const uint64_t* lists, const unsigned long long* cnt, uint32_t nlists, uint64_t cap, uint32_t b0,
-                      uint32_t b1, uint32_t* cur, uint32_t r0, uint32_t r1, uint32_t* prv, uint32_t f0, uint32_t f1) {
+                      uint32_t b1, uint32_t* cur, uint32_t r0, uint32_t r1, uint32_t* prv, uint32_t f0, uint32_t f1, uint32_t c0,
+                      uint32_t c1) {
         if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1)) occ = 2;
-        kern<<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, lists, cnt, nlists, pv.P_local, cap, b0, b1, cur, r0, r1, prv, f0, f1, d_stats);
+        kern<<<(unsigned)(nsm * occ), kCtaThreads, 0, s>>>(ix, lists, cnt, nlists, pv.P_local, cap, b0, b1, cur, r0, r1, prv, f0, f1, c0, c1,
+                                                           d_stats);
     };
     const uint32_t nslices = (uint32_t)(((uint64_t)ix.nbuckets + ((1ull << pv.shift2) - 1)) >> pv.shift2);
     // VG_PREFETCH_AHEAD=1: launch p pulls slice p+1 into L2 while it probes slice p (the first launch of a group
@@ -1545,12 +1643,13 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, Cou
         }
         uint32_t* cur = pv.ctr + (size_t)(p & 1) * ctr_elems;
         uint32_t* prv = pv.ctr + (size_t)((p + 1) & 1) * ctr_elems;
+        const uint32_t c0 = (h_slice_rank && p < nslices) ? h_slice_rank[p] : 0u, c1 = (h_slice_rank && p < nslices) ? h_slice_rank[p + 1] : 0u;
         if (multi) {
-            if (b4) launch(probe_slice_kernel<4, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1);
-            else launch(probe_slice_kernel<8, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1);
+            if (b4) launch(probe_slice_kernel<4, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1, c0, c1);
+            else launch(probe_slice_kernel<8, true>, lists, cnt, nsub, cap, b0, b1, cur, r0, r1, prv, f0, f1, c0, c1);
         } else {
-            if (b4) launch(probe_slice_kernel<4, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1);
-            else launch(probe_slice_kernel<8, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1);
+            if (b4) launch(probe_slice_kernel<4, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1, c0, c1);
+            else launch(probe_slice_kernel<8, false>, lists, cnt, 1u, cap, b0, b1, cur, r0, r1, prv, f0, f1, c0, c1);
         }
     };
     if (pv.sub_bits == 0) {

@@ -30,9 +30,26 @@ public:
         uint64_t added = 0;
         for (const auto& [chromosome, sequence] : mFastaSeqMap) added += mbfD->add_sequence_kernel(sequence, mKmerLen);
         mbfD->copyFilterDToHost();
+        mbfD->release_device();  // index() only needs the host copy (inherited count / find)
         cerr << "[" << __func__ << "::" << getTime() << "] " << added << " k-mers added; filter usage rate "
              << fixed << setprecision(2) << mbf->get_cap() << defaultfloat << setprecision(6) << "\n\n";
         malloc_trim(0);
+    }
+
+    // ConstructIndex::clear_mbf (src/construct_index.cpp:53-60) deletes `mbf` through BloomFilter*, whose destructor
+    // is not virtual: delete the filter as what it is, then let the base class do the rest.
+    void clear_mbf_kernel() {
+        delete mbfD;
+        mbfD = nullptr;
+        mbf = nullptr;
+        clear_mbf();
+    }
+    ~ConstructIndexKernel() {
+        if (mbfD) {
+            delete mbfD;
+            mbfD = nullptr;
+            mbf = nullptr;
+        }
     }
 
     void index_kernel() { index(); }

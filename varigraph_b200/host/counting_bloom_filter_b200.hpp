@@ -18,9 +18,14 @@ public:
         VGB200_CHECK(vg_ctx_create(gpu, buffer_mb, &ctx_));
         VGB200_CHECK(vg_cbf_create(ctx_, _size, _numHashes, _seeds.data(), &cbf_));
     }
-    ~BloomFilterKernel() {
+    ~BloomFilterKernel() { release_device(); }
+
+    // The device twin (about 9.6 bytes per genome base) is only needed until the filter has been downloaded.
+    void release_device() {
         if (cbf_) vg_cbf_destroy(cbf_);
         if (ctx_) vg_ctx_destroy(ctx_);
+        cbf_ = nullptr;
+        ctx_ = nullptr;
     }
 
     // kmer_sketch_bf (src/kmer.cpp:20-52) for one chromosome, fused with the filter update on the

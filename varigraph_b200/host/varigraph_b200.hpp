@@ -41,7 +41,7 @@ public:
         ci->make_QRmap();
         ci->index_kernel();
         ci->save_index();
-        ci->clear_mbf();
+        ci->clear_mbf_kernel();
         cerr << "[" << __func__ << "::" << getTime() << "] " << "graph: " << ci->mGraphBaseNum << " bases, "
              << ci->mGraphKmerHashHapStrMap.size() << " k-mers, " << ci->mHapMap.size() << " haplotypes\n\n";
     }
