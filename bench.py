@@ -105,13 +105,15 @@ def make_variants(dev, L: int, nvar: int, g: torch.Generator, ref: torch.Tensor)
     return alt, pos, vlen
 
 
-def make_graph(dev, genome_len: int, nvar: int, seed: int):
+def make_graph(dev, genome_len: int, nvar: int, seed: int, want_keys: bool = True):
     """-> (ref codes u8[L], alt codes u8[L], var_pos int64[nvar], var_len int64[nvar], keys int64 unique)"""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     L = genome_len
     ref = torch.randint(0, 4, (L,), generator=g, device=dev, dtype=torch.uint8)
     alt, pos, vlen = make_variants(dev, L, nvar, g, ref)
+    if not want_keys:
+        return ref, alt, pos, vlen, None
     nv = pos.numel()
     n = L - K + 1
     d = torch.zeros(L + 2, dtype=torch.int32, device=dev)
@@ -126,7 +128,7 @@ def make_graph(dev, genome_len: int, nvar: int, seed: int):
     return ref, alt, pos, vlen, keys
 
 
-def make_graph_windows(dev, genome_len: int, nvar: int, seed: int, window: int = 128_000_000):
+def make_graph_windows(dev, genome_len: int, nvar: int, seed: int, window: int = 128_000_000, want_keys: bool = True):
     """The same graph shape for genomes of any length, built in windows so that no temporary exceeds a few GB.
     The keys stay where they are made (device).  Not de-duplicated: a random genome repeats a 27-mer a few dozen times
     in 1.4e9 windows; the device index reports and tolerates duplicates (they share a slot)."""
@@ -138,6 +140,8 @@ def make_graph_windows(dev, genome_len: int, nvar: int, seed: int, window: int =
         e = min(L, s + (1 << 30))
         ref[s:e] = torch.randint(0, 4, (e - s,), generator=g, device=dev, dtype=torch.uint8)
     alt, pos, vlen = make_variants(dev, L, nvar, g, ref)
+    if not want_keys:
+        return ref, alt, pos, vlen, None
     lo_all = (pos - K + 1).clamp(min=0)          # first window start that overlaps each variant
     hi_all = pos + vlen                          # one past the last
     est = int((hi_all - lo_all).sum().item()) * 2 + 1024
@@ -388,11 +392,17 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     strong = a.scaling == "strong" or w.get("strong", False)
     cov_rank = w["coverage"] / world if strong else w["coverage"]
     t_gen0 = time.perf_counter()
+    sharded = world > 1 and a.index == "sharded"
+    # replicated index on several GPUs: rank 0 alone makes the keys and builds the index, the others receive a replica
+    builder = rank == 0 or sharded or a.reduce == "nccl"
     if big:
-        ref, alt, pos, vlen, keys = make_graph_windows(dev, L, w["variants"], seed=20261017)
+        ref, alt, pos, vlen, keys = make_graph_windows(dev, L, w["variants"], seed=20261017, want_keys=builder)
     else:
-        ref, alt, pos, vlen, keys = make_graph(dev, L, w["variants"], seed=20261017)
-    nkeys = int(keys.numel())
+        ref, alt, pos, vlen, keys = make_graph(dev, L, w["variants"], seed=20261017, want_keys=builder)
+    nk = torch.tensor([int(keys.numel()) if keys is not None else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(nk, op=dist.ReduceOp.MAX)
+    nkeys = int(nk.item())
     torch.cuda.synchronize()
 
     ctx = capi.Context(local, buffer_mb=a.buffer_mb)
@@ -400,7 +410,6 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     # ---- N > 1: map the peers' memory (handles travel through torch.distributed, data never does) ----
-    sharded = world > 1 and a.index == "sharded"
     comm, reduce_how = None, ("nccl" if world > 1 else None)
     if world > 1 and (sharded or a.reduce == "p2p"):
         def exchange(mine: bytes):
@@ -409,7 +418,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             return got
         round_bytes = a.round_mb << 20
         table_est = int(nkeys / world / (4 * (a.load_factor or 0.3)) * 32 * 1.1) + (64 << 20)
-        arena = (nkeys + (1 << 20)) + ((table_est + table_est // 8 + nkeys + round_bytes * 10 + (128 << 20)) if sharded else 0)
+        arena = (2 * nkeys + (2 << 20)) + ((table_est + table_est // 8 + nkeys + round_bytes * 10 + (128 << 20)) if sharded else 0)
         ok = torch.ones(1, device=dev)
         try:
             comm = capi.Comm(ctx, rank, world, arena, exchange)
@@ -423,26 +432,38 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             comm = None
         else:
             reduce_how = "p2p"
+    replica = comm is not None and not sharded
+    if world > 1 and not sharded and not replica and keys is None:
+        raise SystemExit("bench.py: peer mapping failed and this rank has no keys; rerun with --reduce nccl")
     # a sample of the index for the in-run parity check against the reference (every key when the index is small)
-    keys_np = None
-    if big:
-        sel = (((keys >> 8) * -7046029254386353131) >> 58) == 0  # 1/64 of the keys, by hash (0x9E3779B97F4A7C15 as int64)
-        sample_keys_np = keys[sel].cpu().numpy().view(np.uint64)
-        sample_idx = torch.nonzero(sel).reshape(-1)
-        del sel
-    else:
-        keys_np = keys.cpu().numpy().view(np.uint64)
-        sample_keys_np, sample_idx = keys_np, None
+    keys_np = sample_keys_np = sample_idx = None
+    if keys is not None:
+        if big:
+            sel = (((keys >> 8) * -7046029254386353131) >> 58) == 0  # 1/64 of the keys, by hash (0x9E3779B97F4A7C15 as int64)
+            sample_keys_np = keys[sel].cpu().numpy().view(np.uint64)
+            sample_idx = torch.nonzero(sel).reshape(-1)
+            del sel
+        else:
+            keys_np = keys.cpu().numpy().view(np.uint64)
+            sample_keys_np = keys_np
     t_build0 = time.perf_counter()
     if sharded:
         if keys_np is None:
             keys_np = keys.cpu().numpy().view(np.uint64)
         ix = capi.Index(ctx, keys_np, K, a.load_factor, comm=comm, round_bytes=(a.round_mb << 20))
+    elif keys is None:
+        ix = None
     elif big:
         ix = capi.Index(ctx, (keys.data_ptr(), nkeys), K, a.load_factor)
     else:
         ix = capi.Index(ctx, keys_np, K, a.load_factor)
+    torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
+    t_repl0 = time.perf_counter()
+    if replica:
+        ix = comm.replicate(0, ix)  # table, slot order and pre-filter travel over NVLink; one slot order for all ranks
+        torch.cuda.synchronize()
+    t_repl = time.perf_counter() - t_repl0
     del keys
     torch.cuda.empty_cache()
     lines_dev = make_reads(dev, ref, alt, pos, vlen, cov_rank, seed=1000 + rank)
@@ -459,8 +480,8 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     torch.cuda.synchronize()
 
     nslots = ix.slots if not sharded else 0
-    out32 = torch.empty(max(nkeys, 1), dtype=torch.int32, device=dev) if (world > 1 and comm is None) else None
-    out8 = torch.empty(max(nkeys, 1) + 32, dtype=torch.uint8, device=dev) if world > 1 else None
+    out32 = torch.empty(max(nkeys, 1), dtype=torch.int32, device=dev) if (world > 1 and not replica and not sharded) else None
+    out8 = None
     counts_host = torch.empty(max(nkeys, nslots, 1), dtype=torch.uint8, pin_memory=True)
     per_round = max(1, ((a.round_mb << 20) - (1 << 20)) // rec) * rec
     round_cuts = [(o, min(per_round, nbytes - o)) for o in range(0, nbytes, per_round)] if sharded else []
@@ -480,9 +501,8 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         ix.flush()
         if kev:
             kev[1].record(stream)
-        if comm is not None:  # every rank sums its peers' u8 vectors over NVLink
-            comm.allreduce_counts(ix, want_host=False, dev_out=out8.data_ptr())
-            return out8[:max(nkeys, 1)]
+        if replica:  # reduce-scatter + all-gather over peer memory, in place, in slot order
+            return comm.allreduce_slots(ix, want_host=False)[1]
         if world > 1:  # --reduce nccl: all-reduce of u32, clamp to 255
             ix.extract_device(out32.data_ptr(), 4)
             return vdist.reduce_counts(out32)
@@ -537,6 +557,15 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     # ---- counts of the device path, key order, for the checks below ---------------------------------------
     if sharded:
         device_counts = device_step(want=True)
+    elif replica:
+        ix.begin()
+        ix.submit_device(lines_dev.data_ptr(), nbytes)
+        if big:
+            device_counts = None
+            comm.allreduce_slots(ix, want_host=False)
+        else:
+            device_counts = comm.allreduce_slots(ix)[0][ix.slot_perm()]
+        ix.end(want_counts=False)
     elif world > 1:
         device_counts = device_step().cpu().numpy()
     else:
@@ -561,8 +590,8 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             capi._chk(capi.lib.vg_count_end(ix._h, counts_host.data_ptr(), None, None))
             return
         ix.submit_ptr(lines_host.data_ptr(), host_bytes)
-        if comm is not None:
-            capi._chk(capi.lib.vg_count_allreduce(comm._h, ix._h, counts_host.data_ptr(), None))
+        if replica:
+            capi._chk(capi.lib.vg_count_allreduce_slots(comm._h, ix._h, counts_host.data_ptr(), None))
             capi._chk(capi.lib.vg_count_end(ix._h, None, None, None))
         elif world > 1:
             ix.extract_device(out32.data_ptr(), 4, stream.cuda_stream)  # syncs the context streams first
@@ -592,11 +621,11 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         staged_ok = None
         if device_counts is not None and host_bytes == nbytes:
             got = counts_host.numpy()
-            if world == 1:
+            if world == 1 or replica:
                 got = got[:nslots][ix.slot_perm()]
             staged_ok = bool(np.array_equal(got[:nkeys], device_counts[:nkeys]))
         e2e_staged = {"value": float(hp.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(host_bytes),
-                      "d2h_bytes_per_step": int(nslots if world == 1 else nkeys), "counts_equal_device_path": staged_ok,
+                      "d2h_bytes_per_step": int(nslots if (world == 1 or replica) else nkeys), "counts_equal_device_path": staged_ok,
                       "input": "parsed 'read\\n' records in pinned host memory"
                                + ("" if host_bytes == nbytes else f" (first {host_bytes} bytes of each rank's reads)")}
 
@@ -617,8 +646,8 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             def files_step():
                 ix.begin()
                 rb = ix.count_files(fqs, threads=threads)
-                if comm is not None:
-                    capi._chk(capi.lib.vg_count_allreduce(comm._h, ix._h, counts_host.data_ptr(), None))
+                if replica:
+                    capi._chk(capi.lib.vg_count_allreduce_slots(comm._h, ix._h, counts_host.data_ptr(), None))
                     capi._chk(capi.lib.vg_count_end(ix._h, None, None, None))
                 elif world > 1:
                     ix.extract_device(out32.data_ptr(), 4, stream.cuda_stream)
@@ -645,11 +674,11 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             files_ok = None
             if device_counts is not None and host_bytes == nbytes:
                 got = counts_host.numpy()
-                if world == 1:
+                if world == 1 or replica:
                     got = got[:nslots][ix.slot_perm()]
                 files_ok = bool(np.array_equal(got[:nkeys], device_counts[:nkeys])) and rb == nreads * READ_LEN
             e2e = {"value": float(hp.item()) / float(te.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": int(ix.h2d_bytes_last), "d2h_bytes_per_step": int(nslots if world == 1 else nkeys),
+                   "h2d_bytes_per_step": int(ix.h2d_bytes_last), "d2h_bytes_per_step": int(nslots if (world == 1 or replica) else nkeys),
                    "counts_equal_device_path": files_ok, "file_bytes_per_step": int(file_bytes), "host_threads": threads,
                    "input": "two plain four-line FASTQ files per rank on tmpfs through vg_count_files "
                             "(the same kind of file the reference arm reads)"}
@@ -711,7 +740,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         ix.begin()
         if rank == 0:
             ix.submit_ptr(lines_host.data_ptr(), nr * rec)
-        if comm is not None:
+        if replica:
             mine = comm.allreduce_counts(ix, want_host=True)
             mp = ix.end(want_counts=False)[1]
         elif world > 1:
@@ -738,10 +767,12 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                            "coverage_per_gpu": cov_rank,
                            "parallelism": (f"reads sharded x{world}, index "
                                            + (f"sharded x{world} (k-mer all-to-all fused into the scatter over NVLink, "
-                                              f"{len(round_cuts)} rounds)" if sharded else f"replicated, counts reduced by {reduce_how}")
+                                              f"{len(round_cuts)} rounds)" if sharded else
+                                              ("built on rank 0 and replicated over NVLink, counts combined in slot order by a "
+                                               "reduce-scatter + all-gather over peer memory" if replica else f"replicated, counts reduced by {reduce_how}"))
                                            if world > 1 else "1 GPU"),
                            "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush",
-                           "generate_s": t_gen, "index_build_s": t_build},
+                           "generate_s": t_gen, "index_build_s": t_build, "index_replicate_s": t_repl if replica else None},
                 "e2e": e2e if e2e is not None else e2e_staged, "e2e_staged": e2e_staged,
                 "gpu_launches": int(launches_timed), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "parity": parity}

@@ -195,6 +195,18 @@ int vg_comm_check(vg_comm* comm);   /* waits for the context stream; VG_E_STATE 
  * returns when they are there, otherwise it is asynchronous on the context stream. */
 int vg_count_allreduce(vg_comm* comm, vg_index* ix, uint8_t* c_out, void* dev_out);
 
+/* Replica group: the index is built ONCE and copied, bit for bit, to the other ranks over NVLink (COLLECTIVE).  Rank
+ * `root` passes an index it built with vg_index_create / _device (8 MB or more, i.e. partitioned) and gets the same handle
+ * back in *out; every other rank passes NULL and gets a replica.  No rank but the root ever holds the key array, all ranks
+ * share one slot order, and the count vectors move into the group's arena (arena_bytes >= n + 1 MB), so that
+ * vg_count_allreduce_slots can combine them where they lie: a reduce-scatter and an all-gather over peer memory,
+ * 2 (world-1)/world bytes per k-mer and rank on the wire, result = every rank's vector in slot order
+ * (vg_index_slot_perm maps it to the keys; identical on all ranks).  vg_count_allreduce on such an index does the same
+ * and then gathers into key order.  c_slots_out (host, vg_index_slots bytes) and dev_counts may each be NULL; with
+ * c_slots_out the call returns when the counts are there, otherwise it is asynchronous on the context stream. */
+int vg_index_replicate(vg_comm* comm, int root, vg_index* root_ix, vg_index** out);
+int vg_count_allreduce_slots(vg_comm* comm, vg_index* ix, uint8_t* c_slots_out, const uint8_t** dev_counts);
+
 /* Sharded index (the index does not fit one GPU): ONE open-addressing table cut into `world` runs of
  * buckets, one per rank.  COLLECTIVE; every rank passes the same keys in the same order and keeps those
  * whose home bucket it owns.  Each rank then submits ITS reads with vg_count_submit / _submit_device /

@@ -70,6 +70,21 @@ def worker(rank: int, world: int, port: int, scenario: str, path: str, env: dict
                 pos, hits = ix.stats()
                 ix.end(want_counts=False)
             out = dict(counts=counts, pos=pos, hits=hits)
+        elif scenario == "replica":
+            # rank 0 alone builds the index; the other rank receives table, slot order and pre-filter over peer memory
+            ix = comm.replicate(0, capi.Index(ctx, keys, k) if rank == 0 else None)
+            perm = ix.slot_perm()
+            for rep in range(2):
+                ix.begin()
+                ix.submit(mine)
+                slots, _ = comm.allreduce_slots(ix)
+                pos, hits = ix.stats()
+                ix.end(want_counts=False)
+            ix.begin()
+            ix.submit(mine)
+            counts = comm.allreduce_counts(ix)  # the key-order call on a replica: slot-order reduce + one gather
+            ix.end(want_counts=False)
+            out = dict(counts=counts, slot_counts=slots[perm], perm=perm, pos=pos, hits=hits, parts=ix.partitions, n=ix.n)
         elif scenario == "sharded":
             ix = capi.Index(ctx, keys, k, comm=comm, round_bytes=int(z["round_bytes"]))
             for rep in range(2):
@@ -80,6 +95,7 @@ def worker(rank: int, world: int, port: int, scenario: str, path: str, env: dict
         else:
             raise ValueError(scenario)
         comm.check()
+        out["device"] = dev
         np.savez(f"{path}.out{rank}.npz", **out)
         dist.barrier()  # nobody unmaps a peer's arena while it is still in use
         ix.close()

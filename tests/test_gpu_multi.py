@@ -63,7 +63,11 @@ def _run_two_ranks(tmp_path, scenario, keys, lines, k, env=None, round_bytes=0, 
     path = str(tmp_path / scenario)
     np.savez(path + ".in.npz", keys=keys, lines=lines, k=k, arena=arena, round_bytes=round_bytes)
     mp.spawn(multi_worker.worker, args=(2, _free_port(), scenario, path, env or {}), nprocs=2, join=True)
-    return [np.load(f"{path}.out{r}.npz") for r in range(2)]
+    res = [np.load(f"{path}.out{r}.npz") for r in range(2)]
+    import torch
+    if torch.cuda.device_count() >= 2:  # a real pair of GPUs: the peer memory the ranks read is across NVLink
+        assert int(res[0]["device"]) != int(res[1]["device"])
+    return res
 
 
 def test_two_ranks_replicated_allreduce_over_peer_memory(tmp_path, oracle):
@@ -74,6 +78,26 @@ def test_two_ranks_replicated_allreduce_over_peer_memory(tmp_path, oracle):
     r0, r1 = _run_two_ranks(tmp_path, "replicated", keys, lines, 27)
     want, wpos, whits = oracle.count_lines(keys, lines, 27)
     assert np.array_equal(r0["counts"], want) and np.array_equal(r1["counts"], want)
+    assert int(r0["pos"]) + int(r1["pos"]) == wpos and int(r0["hits"]) + int(r1["hits"]) == whits
+    assert want.max() == 255
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+def test_two_ranks_replica_group_slot_order_reduce(tmp_path, oracle, two_level):
+    """The index is built by rank 0 only and copied to rank 1 over peer memory (vg_index_replicate); the counts are
+    combined in slot order by a reduce-scatter + all-gather in place (vg_count_allreduce_slots)."""
+    keys, lines, g = _workload(oracle, seed=5)
+    hot = np.tile(_read_of(g, 1000), 300)
+    lines = np.concatenate([hot[: 150 * 151], lines, hot[150 * 151:]])
+    env = {"VG_PARTITION": "1", "VG_SLICE_BYTES": "16384", "VG_ROUND_KEYS": "65536", "VG_PART_SLACK": "64"}
+    if two_level:
+        env.update({"VG_SLICE_BYTES": "2048", "VG_TWO_LEVEL_FROM": "8"})
+    r0, r1 = _run_two_ranks(tmp_path, "replica", keys, lines, 27, env=env)
+    want, wpos, whits = oracle.count_lines(keys, lines, 27)
+    for r in (r0, r1):
+        assert int(r["n"]) == keys.size and int(r["parts"]) >= 2
+        assert np.array_equal(r["slot_counts"], want) and np.array_equal(r["counts"], want)
+    assert np.array_equal(r0["perm"], r1["perm"])
     assert int(r0["pos"]) + int(r1["pos"]) == wpos and int(r0["hits"]) + int(r1["hits"]) == whits
     assert want.max() == 255
 

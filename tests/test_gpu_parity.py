@@ -420,8 +420,15 @@ def _fastq_text(rng, g, nreads, crlf=False):
     return out
 
 
+@pytest.fixture(params=["strip", "device"])
+def road(request, monkeypatch):
+    """Both roads of plain FASTQ: sequences stripped by the host workers / raw text parsed on the device."""
+    monkeypatch.setenv("VG_FASTQ_ROAD", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("crlf", [False, True])
-def test_count_files_raw_fastq_parsed_on_device(ctx, vglib, oracle, tmp_path, monkeypatch, crlf):
+def test_count_files_raw_fastq_parsed_on_device(ctx, vglib, oracle, tmp_path, monkeypatch, road, crlf):
     """Plain four-line FASTQ goes to the GPU as raw text in many record-aligned blocks; same counts and
     mReadBase as the kseq road and as the oracle's kseq restatement."""
     t = helpers.tiny()
@@ -451,7 +458,7 @@ def test_count_files_raw_fastq_parsed_on_device(ctx, vglib, oracle, tmp_path, mo
 
 
 @pytest.mark.parametrize("flaw", ["multiline", "short_qual", "truncated_tail", "fasta_inside", "nul"])
-def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, tmp_path, flaw):
+def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, tmp_path, road, flaw):
     """An irregular record deep inside a plain FASTQ file: the blocks before it are counted on the device,
     everything from its block on by the kseq reader -- together exactly what kseq makes of the file."""
     t = helpers.tiny()
@@ -481,7 +488,7 @@ def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, t
     ix.close()
 
 
-def test_count_files_raw_fastq_random_damage(ctx, vglib, oracle, tmp_path):
+def test_count_files_raw_fastq_random_damage(ctx, vglib, oracle, tmp_path, road):
     """Random damage anywhere in a multi-block plain FASTQ file (lost / extra newlines, stray marker bytes,
     NUL, CR, a cut tail): device parsing plus kseq fallback must give exactly what kseq makes of the file."""
     t = helpers.tiny()
@@ -523,7 +530,7 @@ def test_count_files_raw_fastq_random_damage(ctx, vglib, oracle, tmp_path):
     ix.close()
 
 
-def test_count_files_raw_fastq_long_records_go_to_kseq(ctx, vglib, oracle, tmp_path):
+def test_count_files_raw_fastq_long_records_go_to_kseq(ctx, vglib, oracle, tmp_path, road):
     """Records longer than the boundary-search window cannot be cut into raw blocks: the first block goes to
     the device, the rest of the file to the kseq reader from the last boundary on; same result."""
     t = helpers.tiny()
@@ -549,7 +556,7 @@ def test_count_files_raw_fastq_long_records_go_to_kseq(ctx, vglib, oracle, tmp_p
     ix.close()
 
 
-def test_count_files_vs_reference_live(ctx, vglib, reference, tmp_path):
+def test_count_files_vs_reference_live(ctx, vglib, reference, tmp_path, road):
     """Same graph.bin, same FASTQ files: reference CPU path vs CUDA path, per k-mer."""
     t = helpers.tiny()
     graph = tmp_path / "graph.bin"

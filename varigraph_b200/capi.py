@@ -85,6 +85,8 @@ def _load() -> ctypes.CDLL:
         "vg_comm_barrier": (c_int, [c_void_p]),
         "vg_comm_check": (c_int, [c_void_p]),
         "vg_count_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+        "vg_index_replicate": (c_int, [c_void_p, c_int, c_void_p, P(c_void_p)]),
+        "vg_count_allreduce_slots": (c_int, [c_void_p, c_void_p, c_void_p, P(c_void_p)]),
         "vg_index_create_sharded": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, c_uint64, P(c_void_p)]),
         "vg_index_own_keys": (c_uint64, [c_void_p]),
         "vg_count_room": (c_uint64, [c_void_p]),
@@ -196,6 +198,24 @@ class Comm:
         out = np.empty(index.n, dtype=np.uint8) if want_host else None
         _chk(lib.vg_count_allreduce(self._h, index._h, _ptr(out) if want_host else None, c_void_p(dev_out)))
         return out
+
+    def replicate(self, root: int, index: "Index" = None) -> "Index":
+        """COLLECTIVE: the root passes the index it built, the others None; everybody gets a member of the replica group."""
+        h = c_void_p()
+        _chk(lib.vg_index_replicate(self._h, root, index._h if index is not None else None, byref(h)))
+        if index is not None:
+            return index
+        ix = Index.__new__(Index)
+        ix._h, ix.ctx, ix.comm = h, self.ctx, None
+        ix.n, ix.k = int(lib.vg_index_size(h)), None
+        return ix
+
+    def allreduce_slots(self, index: "Index", want_host: bool = True):
+        """COLLECTIVE: slot-order count reduce of a replica group -> (u8[slots] host or None, device pointer)."""
+        out = np.empty(index.slots, dtype=np.uint8) if want_host else None
+        p = c_void_p()
+        _chk(lib.vg_count_allreduce_slots(self._h, index._h, _ptr(out) if want_host else None, byref(p)))
+        return out, int(p.value or 0)
 
     def close(self) -> None:
         if self._h:

@@ -94,6 +94,27 @@ bool vg::part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g) {
     return true;
 }
 
+// Presence pre-filter.  Up to 128 M keys: 4 bits per key (measured best on B200: 30 MB for the chr20 index beats both
+// 8 bits per key and none), at most 64 MB, pinned in L2, one lookup per 4 read positions.  Larger indexes: 8 bits per key
+// in plain HBM, one lookup per 8 positions -- a random DRAM sector per lookup, but at human variant density it keeps
+// 70 % of the k-mers out of the key lists, the re-scatter and the sweep (42 -> 64 G k-mers/s on the 1.2e9-key index).
+// VG_PREFILTER=0 disables it, VG_PREFILTER_BYTES / VG_PREFILTER_SPAN (4 | 8) override.  Keyed by sub-words of the k-mers.
+void vg::prefilter_plan(uint64_t n, uint32_t k, uint64_t& bytes, uint32_t& span) {
+    bytes = 0;
+    span = 4;
+    const char* pe = getenv("VG_PREFILTER");
+    if ((pe && atoi(pe) == 0) || n == 0 || k < 8) return;
+    if (n / 2 <= (64ull << 20)) {
+        bytes = n / 2;
+    } else {
+        bytes = std::min<uint64_t>(n, 0x7fffffffull * 4);
+        span = 8;
+    }
+    if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
+    if (const char* fs = getenv("VG_PREFILTER_SPAN")) span = atoi(fs) == 8 ? 8 : 4;
+    if (k < 12) span = 4;  // the filter's words are (k - span + 1)-mers
+}
+
 int vg::fetch_slice_ranks(vg_index* ix) {
     PartState& ps = ix->part;
     const uint64_t per = 1ull << ps.view.shift2;
@@ -103,6 +124,42 @@ int vg::fetch_slice_ranks(vg_index* ix) {
                     cudaMemcpyDeviceToHost));
     ps.slice_rank[(size_t)nslices] = (uint32_t)ix->m_slots;
     return VG_OK;
+}
+
+// The buffers of the partitioned path whose sizes follow from ps.view (P, shift2, sub_bits, cap, cap2): key lists, fill
+// counts, side counters, and the feedback on how full a round's lists get.
+cudaError_t vg::part_alloc_lists(vg_index* ix) {
+    PartState& ps = ix->part;
+    cudaStream_t s = ix->ctx->compute_stream;
+    const uint64_t P = ps.view.P;
+    const uint32_t shift2 = ps.view.shift2, sub_bits = ps.view.sub_bits;
+    cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift2) * sizeof(uint32_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), s);
+    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.keybuf2, (ps.view.cap2 << sub_bits) * sizeof(uint64_t));
+    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.cursor2, sizeof(unsigned long long) << sub_bits);
+    if (e != cudaSuccess) return e;
+    if (cudaMalloc((void**)&ps.d_round_keys, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ps.h_round_keys, sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ps.ev_round, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();  // no feedback on the rounds' fill: they stay as long as the lists are
+        cudaFree(ps.d_round_keys);
+        ps.d_round_keys = nullptr;
+    }
+    return cudaSuccess;
+}
+void vg::part_free_lists(vg_index* ix) {
+    PartState& ps = ix->part;
+    cudaFree(ps.view.keybuf);
+    cudaFree(ps.view.cursor);
+    cudaFree(ps.view.ctr);
+    cudaFree(ps.view.keybuf2);
+    cudaFree(ps.view.cursor2);
+    ps.view.keybuf = ps.view.keybuf2 = nullptr;
+    ps.view.cursor = ps.view.cursor2 = nullptr;
+    ps.view.ctr = nullptr;
 }
 
 static int part_setup(vg_index* ix) {
@@ -147,19 +204,9 @@ static int part_setup(vg_index* ix) {
     ps.view.rank = 0;
     ps.view.P_local = (uint32_t)P;
     ps.round_keys = round_keys;
-    cudaError_t e = cudaMalloc((void**)&ps.view.keybuf, P * ps.view.cap * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.cursor, P * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ps.view.ctr, ((size_t)8 << shift2) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.ctr, 0, ((size_t)8 << shift2) * sizeof(uint32_t), c->compute_stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ps.view.cursor, 0, P * sizeof(unsigned long long), c->compute_stream);
-    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.keybuf2, (ps.view.cap2 << sub_bits) * sizeof(uint64_t));
-    if (e == cudaSuccess && sub_bits) e = cudaMalloc((void**)&ps.view.cursor2, sizeof(unsigned long long) << sub_bits);
+    cudaError_t e = vg::part_alloc_lists(ix);
     if (e != cudaSuccess) {  // not enough memory for the key buffers: fall back to direct probing
-        cudaFree(ps.view.keybuf);
-        cudaFree(ps.view.cursor);
-        cudaFree(ps.view.ctr);
-        cudaFree(ps.view.keybuf2);
-        cudaFree(ps.view.cursor2);
+        vg::part_free_lists(ix);
         ps = PartState();
         cudaGetLastError();
         return VG_OK;
@@ -183,11 +230,7 @@ static int part_setup(vg_index* ix) {
         if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_perm, std::max<uint64_t>(ix->n, 1) * sizeof(uint32_t));
         if (e == cudaSuccess) e = vg::launch_slot_perm(ix->view, ix->d_key56, ix->n, ix->d_perm, c->compute_stream);
         if (e != cudaSuccess) {
-            cudaFree(ps.view.keybuf);
-            cudaFree(ps.view.cursor);
-            cudaFree(ps.view.ctr);
-            cudaFree(ps.view.keybuf2);
-            cudaFree(ps.view.cursor2);
+            vg::part_free_lists(ix);
             cudaFree(ix->view.rank_base);
             cudaFree(ix->view.cvec);
             cudaFree(ix->d_perm);
@@ -205,22 +248,19 @@ static int part_setup(vg_index* ix) {
         int rc = vg::fetch_slice_ranks(ix);
         if (rc) return rc;
     }
-    // Presence pre-filter: 4 bits per key (measured best on B200: 30 MB for the chr20 index beats both
-    // 8 bits per key and none) as long as that stays within 64 MB, i.e. comfortably L2-resident next to
-    // the streaming traffic; larger indexes go without.  VG_PREFILTER=0 disables it.
-    const char* pe = getenv("VG_PREFILTER");
-    if (!(pe && atoi(pe) == 0) && ix->n > 0 && ix->view.k >= 8) {  // keyed by sub-words of the k-mers
+    {
         uint64_t bytes = 0;
-        if (ix->n / 2 <= (64ull << 20)) bytes = ix->n / 2;
-        if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
+        uint32_t span = 4;
+        vg::prefilter_plan(ix->n, ix->view.k, bytes, span);
         if (bytes >= 64) {
             const uint32_t nwords = (uint32_t)std::min<uint64_t>(bytes / 4, 0x7fffffffull);
             if (cudaMalloc((void**)&ps.d_filter, (size_t)nwords * 4) == cudaSuccess) {
                 CU(cudaMemsetAsync(ps.d_filter, 0, (size_t)nwords * 4, c->compute_stream));
-                CU(vg::launch_prefilter_build(ps.d_filter, nwords, ix->d_key56, ix->n, ix->view.k, c->compute_stream));
+                CU(vg::launch_prefilter_build(ps.d_filter, nwords, ix->d_key56, ix->n, ix->view.k, span, c->compute_stream));
                 CU(cudaStreamSynchronize(c->compute_stream));
                 ps.filter.words = ps.d_filter;
                 ps.filter.nwords = nwords;
+                ps.filter.span = span;
                 if ((size_t)nwords * 4 <= (64ull << 20)) vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
             } else {
                 cudaGetLastError();
@@ -253,6 +293,13 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     PartState& ps = ix->part;
     if (ix->sharded) return VG_OK;  // a sharded round ends only in the collective calls (vg_count_flush / _end)
     if (!ps.enabled || ps.pending == 0) return VG_OK;
+    if (ps.d_round_keys && ps.round_pending == 0) {  // how many keys did this much text leave? (read back later, without waiting)
+        CU(vg::launch_sum_cursors(ps.view.cursor, ps.view.P, ps.view.cap, ps.d_round_keys, s));
+        CU(cudaMemcpyAsync(ps.h_round_keys, ps.d_round_keys, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(ps.ev_round, s));
+        ps.round_pending = ps.pending;
+        ix->launches += 1;
+    }
     phase_begin(ps, s);
     CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
                                    ix->ctx->nsm, s));
@@ -301,6 +348,20 @@ static void part_grow(vg_index* ix, cudaStream_t s) {
     ps.round_keys = round2;
 }
 
+// Text a round may take (see PartState::key_share).
+static uint64_t round_limit(PartState& ps) {
+    if (ps.round_pending && cudaEventQuery(ps.ev_round) == cudaSuccess) {
+        if (ps.round_pending >= (64u << 20))  // short rounds say little
+            ps.key_share = std::min(1.0, std::max(0.05, (double)*ps.h_round_keys / (double)ps.round_pending));
+        ps.round_pending = 0;
+    }
+    cudaGetLastError();
+    static const bool adapt = [] { const char* e = getenv("VG_ADAPTIVE_ROUNDS"); return !(e && atoi(e) == 0); }();
+    if (!adapt || !ps.may_grow) return ps.round_keys;
+    const double lim = (double)ps.round_keys / std::min(1.0, ps.key_share * 1.25);
+    return (uint64_t)std::min(lim, 16.0 * 1073741824.0) & ~4095ull;
+}
+
 // Count every k-mer of a device-resident chunk on stream s (direct or partitioned).
 static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nbytes, cudaStream_t s,
                               const unsigned int* d_skip = nullptr) {
@@ -315,7 +376,8 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
     const int64_t T = vg::chunk_tiles(d_bases, nbytes);
     int64_t t = 0;
     while (t < T) {
-        int64_t room = (int64_t)((ps.round_keys - ps.pending) / tile_bytes);
+        const uint64_t limit = ix->sharded ? ps.round_keys : round_limit(ps);
+        int64_t room = limit > ps.pending ? (int64_t)((limit - ps.pending) / tile_bytes) : 0;
         if (ix->sharded && room < T - t)
             return fail(VG_E_STATE, "sharded index: the round is full (%llu of %llu bytes); call vg_count_flush on every rank",
                         (unsigned long long)ps.pending, (unsigned long long)ps.round_keys);
@@ -323,7 +385,7 @@ static int count_device_chunk(vg_index* ix, const uint8_t* d_bases, uint64_t nby
             int rc = part_flush(ix, s);
             if (rc) return rc;
             part_grow(ix, s);
-            room = (int64_t)(ps.round_keys / tile_bytes);
+            room = (int64_t)(round_limit(ps) / tile_bytes);
         }
         const int64_t nt = std::min<int64_t>(T - t, room);
         phase_begin(ps, s);
@@ -385,7 +447,7 @@ int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len, const
         const uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
         return v >= 4096 ? v : (384ull << 20);  // measured flat between 256 M and 1 G, worse below
     }();
-    if (ix->part.enabled && !ix->sharded && ix->part.pending >= std::min<uint64_t>(ix->part.round_keys, staged_round)) {
+    if (ix->part.enabled && !ix->sharded && ix->part.pending >= std::min<uint64_t>(round_limit(ix->part), staged_round)) {
         rc = part_flush(ix, c->compute_stream);
         if (rc) return rc;
     }
@@ -649,7 +711,7 @@ int vg_index_destroy(vg_index* ix) {
         cudaFree(ix->d_counts);
         cudaFree(ix->part.view.keybuf);
         cudaFree(ix->view.rank_base);
-        cudaFree(ix->view.cvec);
+        if (!ix->replica_of) cudaFree(ix->view.cvec);  // a replica group keeps the count vectors in its arena
     }
     cudaFree(ix->d_perm);
     cudaFree(ix->d_key56);
@@ -663,6 +725,9 @@ int vg_index_destroy(vg_index* ix) {
     cudaFree(ix->part.view.keybuf2);
     cudaFree(ix->part.view.cursor2);
     cudaFree(ix->part.d_filter);
+    cudaFree(ix->part.d_round_keys);
+    if (ix->part.h_round_keys) cudaFreeHost(ix->part.h_round_keys);
+    if (ix->part.ev_round) cudaEventDestroy(ix->part.ev_round);
     if (ix->part.ev0) cudaEventDestroy(ix->part.ev0);
     if (ix->part.ev1) cudaEventDestroy(ix->part.ev1);
     delete ix;

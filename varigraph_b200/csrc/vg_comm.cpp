@@ -78,6 +78,8 @@ int combine_from_peers(vg_comm* cm, size_t counts_off, uint64_t n, uint8_t* d_ou
 }  // namespace
 
 extern "C" {
+static int allreduce_slots(vg_comm* cm, vg_index* ix, cudaStream_t s);
+
 
 int vg_comm_create(vg_ctx* c, int rank, int world, uint64_t arena_bytes, vg_comm** out) {
     if (!c || !out) return fail(VG_E_INVALID, "vg_comm_create: NULL argument");
@@ -186,23 +188,224 @@ int vg_count_allreduce(vg_comm* cm, vg_index* ix, uint8_t* c_out, void* dev_out)
     DeviceGuard g(c->device);
     const uint64_t n = ix->n;
     const size_t need = (size_t)((n + 15) & ~15ull) + 16;
-    if (cm->reduce_bytes < need) {
+    const bool replica = ix->replica_of == cm;
+    if (!replica && cm->reduce_bytes < need) {  // every rank's key-order vector goes through the arena
         if (cm->reduce_bytes) return fail(VG_E_STATE, "vg_count_allreduce: one index size per comm (arena scratch is %zu bytes)", cm->reduce_bytes);
         if (!arena_alloc(cm, need, &cm->reduce_off)) return fail(VG_E_NOMEM, "arena too small for a %zu-byte count vector", need);
         cm->reduce_bytes = need;
+    }
+    if (!dev_out && cm->reduced_bytes < need) {
+        cudaFree(cm->d_reduced);
+        cm->d_reduced = nullptr;
+        cm->reduced_bytes = 0;
         CU(cudaMalloc((void**)&cm->d_reduced, need));
+        cm->reduced_bytes = need;
     }
     cudaStream_t s = c->compute_stream;
     int rc = vg_count_flush(ix);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->copy_stream));
-    CU(vg::counts_in_key_order(ix, cm->arena + cm->reduce_off, 1, s));
-    ix->launches += 1;
     uint8_t* out = dev_out ? (uint8_t*)dev_out : cm->d_reduced;
-    rc = combine_from_peers(cm, cm->reduce_off, n, out, s);
-    if (rc) return rc;
+    if (replica) {  // same slot order everywhere: reduce where the counts lie, then one gather into key order
+        if (cm->world > 1 && (rc = allreduce_slots(cm, ix, s)) != VG_OK) return rc;
+        CU(vg::counts_in_key_order(ix, out, 1, s));
+        ix->launches += 1;
+    } else {
+        CU(vg::counts_in_key_order(ix, cm->arena + cm->reduce_off, 1, s));
+        ix->launches += 1;
+        rc = combine_from_peers(cm, cm->reduce_off, n, out, s);
+        if (rc) return rc;
+    }
     if (c_out) {
         CU(cudaMemcpyAsync(c_out, out, n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return check_peers(cm);
+    }
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// replica group: one rank builds the index, the others receive it over NVLink
+// ---------------------------------------------------------------------------
+namespace {
+struct ReplicaMail {  // what the root tells the others, through its arena
+    uint64_t magic, n, m_slots, duplicates, cap, cap2, round_keys, slack;
+    uint32_t k, nbuckets, P, shift, shift2, sub_bits, filter_nwords, filter_span, may_grow, pad;
+    cudaIpcMemHandle_t h_slots, h_rank_base, h_perm, h_filter;
+};
+constexpr uint64_t kMailMagic = 0x76676232303072ULL;
+
+// one buffer of the root's index -> this rank's copy of it (peer-to-peer over NVLink through a CUDA IPC mapping)
+int pull_buffer(const cudaIpcMemHandle_t& h, void* dst, size_t bytes, cudaStream_t s) {
+    void* src = nullptr;
+    CU(cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaIpcCloseMemHandle(src);
+    if (e != cudaSuccess) return fail(VG_E_CUDA, "replica copy of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    return VG_OK;
+}
+}  // namespace
+
+int vg_index_replicate(vg_comm* cm, int root, vg_index* root_ix, vg_index** out) {
+    if (!cm || !out) return fail(VG_E_INVALID, "vg_index_replicate: NULL argument");
+    *out = nullptr;
+    if (!cm->connected) return fail(VG_E_STATE, "vg_index_replicate: vg_comm_connect first");
+    if (root < 0 || root >= cm->world) return fail(VG_E_INVALID, "root %d outside [0,%d)", root, cm->world);
+    const bool is_root = cm->rank == root;
+    if (is_root && (!root_ix || root_ix->ctx != cm->ctx || root_ix->sharded || !root_ix->part.enabled || root_ix->replica_of))
+        return fail(VG_E_INVALID, "vg_index_replicate: the root passes a partitioned, unsharded index of the comm's context");
+    vg_ctx* c = cm->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t s = c->compute_stream;
+    size_t mail_off = 0;
+    uint8_t* d_mail = (uint8_t*)arena_alloc(cm, sizeof(ReplicaMail), &mail_off);
+    if (!d_mail) return fail(VG_E_NOMEM, "arena too small for the replica mailbox");
+    ReplicaMail mail{};
+    if (is_root) {
+        const PartState& ps = root_ix->part;
+        mail.magic = kMailMagic;
+        mail.n = root_ix->n;
+        mail.m_slots = root_ix->m_slots;
+        mail.duplicates = root_ix->duplicates;
+        mail.cap = ps.view.cap;
+        mail.cap2 = ps.view.cap2;
+        mail.round_keys = ps.round_keys;
+        mail.slack = ps.slack;
+        mail.k = root_ix->view.k;
+        mail.nbuckets = root_ix->view.nbuckets;
+        mail.P = ps.view.P;
+        mail.shift = ps.view.shift;
+        mail.shift2 = ps.view.shift2;
+        mail.sub_bits = ps.view.sub_bits;
+        mail.filter_nwords = ps.filter.words ? ps.filter.nwords : 0;
+        mail.filter_span = ps.filter.span;
+        mail.may_grow = ps.may_grow ? 1 : 0;
+        CU(cudaIpcGetMemHandle(&mail.h_slots, root_ix->view.slots));
+        CU(cudaIpcGetMemHandle(&mail.h_rank_base, root_ix->view.rank_base));
+        CU(cudaIpcGetMemHandle(&mail.h_perm, root_ix->d_perm));
+        if (mail.filter_nwords) CU(cudaIpcGetMemHandle(&mail.h_filter, ps.d_filter));
+        CU(cudaMemcpyAsync(d_mail, &mail, sizeof mail, cudaMemcpyHostToDevice, s));
+    }
+    int rc = barrier_on(cm, s);  // the mail is in the root's arena
+    if (rc) return rc;
+    if (!is_root) {
+        CU(cudaMemcpyAsync(&mail, cm->peer_base[root] + mail_off, sizeof mail, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        rc = check_peers(cm);
+        if (rc) return rc;
+        if (mail.magic != kMailMagic) return fail(VG_E_STATE, "rank %d: no replica mail from rank %d", cm->rank, root);
+    }
+    // the count vectors of a replica group live in the arena, at the same offset on every rank: the reduce reads them
+    const size_t cvec_bytes = (size_t)((mail.m_slots + 31) & ~15ull);
+    size_t cvec_off = 0;
+    uint8_t* cvec = (uint8_t*)arena_alloc(cm, cvec_bytes, &cvec_off);
+    if (!cvec) return fail(VG_E_NOMEM, "arena of %zu bytes too small for a %zu-byte count vector", cm->arena_bytes, cvec_bytes);
+    CU(cudaMemsetAsync(cvec, 0, cvec_bytes, s));
+    vg_index* ix = root_ix;
+    if (is_root) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(ix->view.cvec);
+    } else {
+        ix = new vg_index();
+        ix->ctx = c;
+        ix->n = mail.n;
+        ix->m_slots = mail.m_slots;
+        ix->duplicates = mail.duplicates;
+        ix->view.k = mail.k;
+        ix->view.mask = (1ULL << (2 * mail.k)) - 1;
+        ix->view.nbuckets = ix->view.nb_total = mail.nbuckets;
+        ix->view.b_base = 0;
+        PartState& ps = ix->part;
+        ps.view.P = ps.view.P_local = mail.P;
+        ps.view.shift = mail.shift;
+        ps.view.shift2 = mail.shift2;
+        ps.view.sub_bits = mail.sub_bits;
+        ps.view.cap = mail.cap;
+        ps.view.cap2 = mail.cap2;
+        ps.view.world = 1;
+        ps.view.rank = 0;
+        ps.round_keys = mail.round_keys;
+        ps.slack = mail.slack;
+        ps.may_grow = mail.may_grow != 0;
+        auto bail = [&](int code) {
+            ix->view.cvec = nullptr;
+            vg_index_destroy(ix);
+            return code;
+        };
+        cudaError_t e = cudaMalloc((void**)&ix->view.slots, (size_t)mail.nbuckets * 32);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->view.rank_base, (size_t)mail.nbuckets * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_perm, std::max<uint64_t>(mail.n, 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_counts, std::max<uint64_t>(mail.n, 4));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->d_misc, sizeof(vg::DeviceMisc));
+        if (e == cudaSuccess) e = cudaMemsetAsync(ix->d_misc, 0, sizeof(vg::DeviceMisc), s);
+        if (e == cudaSuccess && mail.filter_nwords) e = cudaMalloc((void**)&ps.d_filter, (size_t)mail.filter_nwords * 4);
+        if (e == cudaSuccess) e = vg::part_alloc_lists(ix);
+        if (e != cudaSuccess)
+            return bail(fail(e == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "replica of %llu k-mers: %s",
+                             (unsigned long long)mail.n, cudaGetErrorString(e)));
+        if ((rc = pull_buffer(mail.h_slots, ix->view.slots, (size_t)mail.nbuckets * 32, s)) != VG_OK) return bail(rc);
+        if ((rc = pull_buffer(mail.h_rank_base, ix->view.rank_base, (size_t)mail.nbuckets * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
+        if ((rc = pull_buffer(mail.h_perm, ix->d_perm, (size_t)mail.n * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
+        if (mail.filter_nwords) {
+            if ((rc = pull_buffer(mail.h_filter, ps.d_filter, (size_t)mail.filter_nwords * 4, s)) != VG_OK) return bail(rc);
+            ps.filter.words = ps.d_filter;
+            ps.filter.nwords = mail.filter_nwords;
+            ps.filter.span = mail.filter_span;
+            if ((size_t)mail.filter_nwords * 4 <= (64ull << 20)) vg::pin_in_l2(c, ps.d_filter, (size_t)mail.filter_nwords * 4);
+        }
+        ps.enabled = true;
+        ix->view.cvec = cvec;  // fetch_slice_ranks reads rank_base only
+        if ((rc = vg::fetch_slice_ranks(ix)) != VG_OK) return bail(rc);
+    }
+    ix->view.cvec = cvec;
+    ix->cvec_off = cvec_off;
+    ix->replica_of = cm;
+    rc = barrier_on(cm, s);  // the root keeps its buffers untouched until everybody has its copy
+    if (rc == VG_OK) {
+        CU(cudaStreamSynchronize(s));
+        rc = check_peers(cm);
+    }
+    if (rc) {
+        if (!is_root) {
+            ix->view.cvec = nullptr;
+            vg_index_destroy(ix);
+        }
+        return rc;
+    }
+    *out = ix;
+    return VG_OK;
+}
+
+// Slot-order count reduce of a replica group (COLLECTIVE): reduce-scatter + all-gather over peer memory, in place in
+// the ranks' count vectors; afterwards every rank's vector holds min(255, sum over ranks).
+static int allreduce_slots(vg_comm* cm, vg_index* ix, cudaStream_t s) {
+    const uint64_t nbytes = (ix->m_slots + 15) & ~15ull;
+    const uint64_t seg = ((nbytes / cm->world + 15) & ~15ull) ? ((nbytes / cm->world + 15) & ~15ull) : 16;
+    const vg::PeerPtrs vecs = peers_at(cm, ix->cvec_off);
+    int rc = barrier_on(cm, s);  // every rank has finished counting
+    if (rc) return rc;
+    CU(vg::launch_reduce_segment(vecs, cm->world, cm->rank, seg, nbytes, cm->ctx->nsm, s));
+    rc = barrier_on(cm, s);      // every segment is reduced
+    if (rc) return rc;
+    CU(vg::launch_gather_segments(vecs, cm->world, cm->rank, seg, nbytes, cm->ctx->nsm, s));
+    cm->launches += 2;
+    return barrier_on(cm, s);    // nobody zeroes its vector for the next sample while a peer still reads it
+}
+
+int vg_count_allreduce_slots(vg_comm* cm, vg_index* ix, uint8_t* c_slots_out, const uint8_t** dev_counts) {
+    if (!cm || !ix) return fail(VG_E_INVALID, "vg_count_allreduce_slots: NULL argument");
+    if (ix->replica_of != cm) return fail(VG_E_STATE, "vg_count_allreduce_slots: the index is not a replica of this comm's group (vg_index_replicate)");
+    vg_ctx* c = cm->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t s = c->compute_stream;
+    int rc = vg_count_flush(ix);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->copy_stream));
+    if (cm->world > 1 && (rc = allreduce_slots(cm, ix, s)) != VG_OK) return rc;
+    if (dev_counts) *dev_counts = ix->view.cvec;
+    if (c_slots_out) {
+        CU(cudaMemcpyAsync(c_slots_out, ix->view.cvec, ix->m_slots, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         return check_peers(cm);
     }
@@ -322,11 +525,10 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
     CUB(vg::launch_table_fill_empty(ix->view.slots, 4ull * nb_local, s));
 
     // ---- presence pre-filter over ALL keys (every rank filters its own reads before the exchange) ----
-    const char* pe = getenv("VG_PREFILTER");
-    uint32_t nwords = 0;
-    if (!(pe && atoi(pe) == 0) && n > 0 && k >= 8) {
-        uint64_t bytes = n / 2 <= (64ull << 20) ? n / 2 : 0;
-        if (const char* fb = getenv("VG_PREFILTER_BYTES")) bytes = strtoull(fb, nullptr, 10);
+    uint32_t nwords = 0, fspan = 4;
+    {
+        uint64_t bytes = 0;
+        vg::prefilter_plan(n, k, bytes, fspan);
         if (bytes >= 64) {
             nwords = (uint32_t)std::min<uint64_t>(bytes / 4, 0x7fffffffull);
             CUB(cudaMalloc((void**)&ps.d_filter, (size_t)nwords * 4));
@@ -372,7 +574,7 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
             CUB2(vg::launch_unhash(d_piece, m, ix->view.mask, s));
             CUB2(vg::launch_select_owned(ix->view, d_piece, m, off, pass ? ix->d_key56 : nullptr, pass ? ix->d_idx : nullptr,
                                          d_n_own, s));
-            if (pass == 1 && nwords) CUB2(vg::launch_prefilter_build(ps.d_filter, nwords, d_piece, m, k, s));
+            if (pass == 1 && nwords) CUB2(vg::launch_prefilter_build(ps.d_filter, nwords, d_piece, m, k, fspan, s));
             CUB2(cudaStreamSynchronize(s));  // tmp is reused
         }
         if (pass == 0) {

@@ -194,13 +194,12 @@ __device__ __forceinline__ uint32_t prefilter_mask(uint32_t bits) {
 // gathers (one L1TEX wavefront each).  With fwd / rev the encoder's registers at position i: that word is the
 // low 2(k-d) bits of fwd, and its reverse complement is rev without its d lowest bases.  Only the k-d most
 // recent bases enter, so the value is right whenever any of the d+1 k-mers is emitted.
-#ifndef VG_FILTER_SPAN
-#define VG_FILTER_SPAN 4
-#endif
-constexpr int kFilterSpan = VG_FILTER_SPAN;  // read positions one filter lookup speaks for (a power of two <= 8)
-constexpr int kFilterDrop = kFilterSpan - 1;  // the filter's words are (k - kFilterDrop)-mers
+// kSpan = d + 1, the read positions one filter lookup speaks for (4 or 8): 4 where the filter is L2-resident (a lookup
+// is then one L1TEX wavefront), 8 for the filter of a huge index, which lives in DRAM, where every lookup saved is a random
+// sector not fetched (measured on the human-scale index: 58.9 vs 53.1 G k-mers/s).
+template <int kSpan>
 __device__ __forceinline__ uint64_t shared_smer(uint64_t fwd, uint64_t rev, uint64_t kmask) {
-    const uint64_t a = fwd & (kmask >> (2 * kFilterDrop)), b = rev >> (2 * kFilterDrop);
+    const uint64_t a = fwd & (kmask >> (2 * (kSpan - 1))), b = rev >> (2 * (kSpan - 1));
     return a < b ? a : b;
 }
 
@@ -349,8 +348,8 @@ struct OddEncoder {
     // Consumes the next N own positions: keys[j] = the canonical k-mer ending there (kHashed: its
     // hash64, i.e. the reference's key >> 8); returns the N-bit emit mask (bit j: the reference encoder
     // emits; keys[j] is meaningless where it does not).  With kPairs, pairs[q] = the pre-filter entry that
-    // speaks for positions q * kFilterSpan ... (q + 1) * kFilterSpan - 1 (see shared_smer).
-    template <int N, bool kHashed = true, bool kPairs = false>
+    // speaks for positions q * kSpan ... (q + 1) * kSpan - 1 (see shared_smer).
+    template <int N, bool kHashed = true, bool kPairs = false, int kSpan = 4>
     __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N], uint64_t* pairs = nullptr) {
         const uint32_t top = 2 * (kp.k - 1);
         uint32_t emit = 0;
@@ -365,7 +364,7 @@ struct OddEncoder {
                 rev = ((uint64_t)((rhi >> 2) | ((3u ^ cb) << tsh)) << 32) | __funnelshift_r(rlo, rhi, 2);
                 const uint64_t canon = fwd < rev ? fwd : rev;
                 keys[j] = kHashed ? hash64_wide(canon, mask_hi) : canon;
-                if (kPairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(fwd, rev, kp.mask);
+                if (kPairs && j % kSpan == 0) pairs[j / kSpan] = shared_smer<kSpan>(fwd, rev, kp.mask);
                 emit |= ((all_k >> 15) & 1u) << j;
                 all_k <<= 1;
             }
@@ -379,7 +378,7 @@ struct OddEncoder {
             rev = (rev >> 2) | ((3ULL ^ cb) << top);
             const uint64_t canon = fwd < rev ? fwd : rev;
             keys[j] = kHashed ? hash64(canon, kp.mask) : canon;
-            if (kPairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(fwd, rev, kp.mask);
+            if (kPairs && j % kSpan == 0) pairs[j / kSpan] = shared_smer<kSpan>(fwd, rev, kp.mask);
             emit |= ((all_k >> 15) & 1u) << j;
             all_k <<= 1;
         }
@@ -429,10 +428,10 @@ __device__ __forceinline__ uint32_t chunk_entry(const Chunk& c, int64_t pos, con
     return lut[c.al[pos]];
 }
 
-// pairs (optional, 16 / kFilterSpan entries): pairs[q] = shared_smer of the registers after byte q * kFilterSpan
-// of the segment -- right whenever one of the kFilterSpan k-mers ending from there on is emitted (then the
-// k - kFilterDrop most recent valid bases are the bytes ending there).
-template <bool kHashed = true>
+// pairs (optional, 16 / kSpan entries): pairs[q] = shared_smer of the registers after byte q * kSpan
+// of the segment -- right whenever one of the kSpan k-mers ending from there on is emitted (then the
+// k - kSpan + 1 most recent valid bases are the bytes ending there).
+template <bool kHashed = true, int kSpan = 4>
 __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const KmerParams& kp,
                                            const uint8_t* lut, uint64_t (&keys)[16], uint64_t* pairs = nullptr) {
 #pragma unroll
@@ -491,7 +490,7 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
                 emit |= 1u << j;
             }
         }
-        if (pairs && j % kFilterSpan == 0) pairs[j / kFilterSpan] = shared_smer(st.fwd, st.rev, kp.mask);
+        if (pairs && j % kSpan == 0) pairs[j / kSpan] = shared_smer<kSpan>(st.fwd, st.rev, kp.mask);
     }
     return emit;
 }

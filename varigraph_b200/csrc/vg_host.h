@@ -77,8 +77,17 @@ struct PartState {
     uint64_t pending = 0;      // upper bound of keys scattered since the last probe pass
     uint64_t slack = 0;        // extra keys per list on top of 1.25 x the even share
     bool may_grow = false;     // rounds double (up to 4 G bases) when a sample needs more than one
-    vg::PrefilterView filter{nullptr, 0};
+    vg::PrefilterView filter{nullptr, 0, 4};
     uint32_t* d_filter = nullptr;
+    // How long a round may get.  The lists are sized for round_keys KEYS, but `pending` counts scattered text, and the
+    // pre-filter keeps only part of it: every sweep reports the keys its round really held (a device sum of the fill
+    // counts, copied back asynchronously), and later rounds take pending up to round_keys / (that share x 1.25).
+    // An underestimate is harmless: keys that find their list full are probed at once, exactly.
+    double key_share = 1.0;              // keys per byte of scattered text, last observed
+    unsigned long long* d_round_keys = nullptr;
+    unsigned long long* h_round_keys = nullptr;  // pinned
+    cudaEvent_t ev_round = nullptr;
+    uint64_t round_pending = 0;          // the `pending` that h_round_keys belongs to (0: nothing in flight)
     std::vector<uint32_t> slice_rank;  // cvec position of the first slot of every table slice (+ the total): what to prefetch
     // diagnostic (vg_index_set_timing): CUDA events around every scatter launch and every sweep, accumulated
     bool timing = false;
@@ -103,6 +112,7 @@ struct vg_comm {
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
     size_t reduce_off = 0, reduce_bytes = 0;  // symmetric scratch of vg_count_allreduce
     uint8_t* d_reduced = nullptr;
+    size_t reduced_bytes = 0;
     uint64_t launches = 0;
 };
 
@@ -123,6 +133,8 @@ struct vg_index {
     // partitioned probing: the counters live in view.cvec, in slot order (see IndexView)
     uint32_t* d_perm = nullptr;    // slot-order position of each key (sharded: of each own key)
     uint64_t m_slots = 0;          // occupied slots of this table == entries of view.cvec
+    vg_comm* replica_of = nullptr; // member of a replica group (vg_index_replicate): same table on every rank, cvec in the arena
+    size_t cvec_off = 0;           //   arena offset of view.cvec
     unsigned long long* d_hist = nullptr;
     vg::DeviceMisc* d_misc = nullptr;
     uint64_t duplicates = 0;
@@ -149,7 +161,11 @@ struct PartGeometry {
 };
 bool part_geometry(uint64_t nbuckets, uint32_t world, PartGeometry& g);
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv);  // kernels one sweep launches
+cudaError_t part_alloc_lists(vg_index* ix);
+void part_free_lists(vg_index* ix);
 int fetch_slice_ranks(vg_index* ix);  // fills part.slice_rank from rank_base (after the rank scan)
+// size and span of the presence pre-filter of an index of n keys (bytes == 0: none)
+void prefilter_plan(uint64_t n, uint32_t k, uint64_t& bytes, uint32_t& span);
 void pin_in_l2(vg_ctx* c, void* ptr, size_t bytes);   // L2 persisting window over the presence pre-filter
 cudaError_t counts_in_key_order(vg_index* ix, void* d_out, int elem_bytes, cudaStream_t s);
 int sharded_flush(vg_index* ix, cudaStream_t s);      // vg_comm.cpp: publish, barrier, sweep, barrier

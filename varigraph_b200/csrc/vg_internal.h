@@ -37,6 +37,7 @@ struct IndexView {
 struct PrefilterView {
     const uint32_t* words;          // nullptr: disabled
     uint32_t nwords;
+    uint32_t span;                  // read positions one lookup speaks for: 4 (L2-resident filter) or 8 (filter in DRAM)
 };
 
 struct CountStats {                 // lives in device memory
@@ -151,11 +152,13 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
 cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const PrefilterView& pf, const uint8_t* d_bases,
                            uint64_t nbytes, int64_t first_tile, int64_t ntiles, CountStats* d_stats, int nsm,
                            cudaStream_t s, const unsigned int* d_skip = nullptr);
-cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k,
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k, uint32_t span,
                                    cudaStream_t s);
 // h_slice_rank (host, slices + 1 entries, may be NULL): cvec position of the first slot of each slice of this table
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, const uint32_t* h_slice_rank, CountStats* d_stats,
                                     int nsm, cudaStream_t s);
+// *d_total = sum of the P fill counts at `cursor` (each clipped to cap): the keys of the round about to be swept
+cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, cudaStream_t s);
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 // d_idx == nullptr: out[i] = count of d_key56[i]; else out[d_idx[i]] = ... (a sharded index's own keys)
@@ -172,6 +175,11 @@ cudaError_t launch_publish_counts(const PartView& pv, cudaStream_t s);
 // out[i] = min(255, sum over ranks of peer_counts[r][i]) for i in [0, n): the count reduce over NVLink.
 cudaError_t launch_combine_counts(const PeerPtrs& peer_counts, int world, uint64_t n, uint8_t* d_out, int nsm,
                                   cudaStream_t s);
+// Replica group (same slot order on every rank): vecs.p[r] = rank r's count vector, nbytes long (padded to 16), cut into
+// `world` segments of seg_bytes (a multiple of 16).  reduce: this rank's segment = min(255, sum over ranks), in place;
+// gather: every other segment from its owner.  A barrier belongs before, between and after.
+cudaError_t launch_reduce_segment(const PeerPtrs& vecs, int world, int rank, uint64_t seg_bytes, uint64_t nbytes, int nsm, cudaStream_t s);
+cudaError_t launch_gather_segments(const PeerPtrs& vecs, int world, int rank, uint64_t seg_bytes, uint64_t nbytes, int nsm, cudaStream_t s);
 cudaError_t launch_histogram(const uint8_t* d_counts, const uint8_t* d_flags, uint64_t n, unsigned long long* d_hist,
                              cudaStream_t s);
 cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes, uint64_t* d_out,

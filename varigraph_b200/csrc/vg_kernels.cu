@@ -502,17 +502,16 @@ __device__ __forceinline__ uint64_t* list_of(const PartView& pv, uint32_t p) {
     return pv.keybuf + (uint64_t)p * pv.cap;
 }
 
-// Every (k - kFilterDrop)-mer of every index k-mer, canonical (see shared_smer).
+// Every (k - span + 1)-mer of every index k-mer, canonical (see shared_smer).
 __global__ void prefilter_build_kernel(uint32_t* words, uint32_t nwords, const uint64_t* __restrict__ key56, uint64_t n,
-                                       uint32_t k) {
+                                       uint32_t k, uint32_t span) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t key = key56[i];
     if (key == kKey56Max) return;
-    const uint32_t ks = k - kFilterDrop;
+    const uint32_t ks = k - (span - 1);
     const uint64_t smask = (1ULL << (2 * ks)) - 1;
-#pragma unroll
-    for (int h = 0; h <= kFilterDrop; ++h) {
+    for (uint32_t h = 0; h < span; ++h) {
         const uint64_t sub = (key >> (2 * h)) & smask, rc = revcomp2k(sub, ks);
         uint32_t w, bits;
         prefilter_slot(sub < rc ? sub : rc, nwords, w, bits);
@@ -571,7 +570,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // kTma: the tile's text (plus the 32 bytes in front of it) is staged in shared memory by a bulk async copy that one
 // thread issues a whole tile ahead (two buffers, one mbarrier each): the load latency never sits in front of the
 // encoder and the LSU only sees shared-memory loads.
-template <bool kOdd, bool kTma>
+template <bool kOdd, bool kTma, int kSpan>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
@@ -633,21 +632,21 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             mbar_wait(bar_a + 8 * (it & 1), (it >> 1) & 1);
         }
         // ---- encode, filter, bin -----------------------------------------------------------------
-        constexpr int kGroups = 8 / kFilterSpan;
-        constexpr uint32_t kGroupMask = (1u << kFilterSpan) - 1u;
+        constexpr int kGroups = 8 / kSpan;
+        constexpr uint32_t kGroupMask = (1u << kSpan) - 1u;
         auto bin8 = [&](const uint64_t (&keys)[8], const uint64_t (&pairs)[kGroups], uint32_t emit) {
-            if (pf.words) {  // L2-resident presence pre-filter, one lookup per kFilterSpan positions: never a false negative
+            if (pf.words) {  // presence pre-filter, one lookup per kSpan positions: never a false negative
                 uint32_t fw[kGroups], fb[kGroups];
 #pragma unroll
                 for (int q = 0; q < kGroups; ++q) {
                     uint32_t w;
                     prefilter_slot(pairs[q], pf.nwords, w, fb[q]);
-                    fw[q] = ((emit >> (kFilterSpan * q)) & kGroupMask) ? __ldg(pf.words + w) : 0u;
+                    fw[q] = ((emit >> (kSpan * q)) & kGroupMask) ? __ldg(pf.words + w) : 0u;
                 }
 #pragma unroll
                 for (int q = 0; q < kGroups; ++q) {
                     const uint32_t m = prefilter_mask(fb[q]);
-                    if ((fw[q] & m) != m) emit &= ~(kGroupMask << (kFilterSpan * q));
+                    if ((fw[q] & m) != m) emit &= ~(kGroupMask << (kSpan * q));
                 }
             }
             uint32_t over = 0;   // keys whose bin is full (rare): handled after the hot loop
@@ -677,15 +676,15 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             if (kTma) enc.init(c, SharedText{tile_a + (it & 1) * kStage, (first_tile + t) * kTileBytes - 32}, off, kp, lut);
             else enc.init(c, off, kp, lut);
             uint64_t keys[8], pairs[kGroups];
-            uint32_t emit = enc.next<8, false, true>(kp, keys, pairs);
+            uint32_t emit = enc.next<8, false, true, kSpan>(kp, keys, pairs);
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
-            emit = enc.next<8, false, true>(kp, keys, pairs);
+            emit = enc.next<8, false, true, kSpan>(kp, keys, pairs);
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
         } else {
             uint64_t k16[16], p8[2 * kGroups], keys[8], pairs[kGroups];
-            const uint32_t emit = encode_keys_any<false>(c, off, kp, lut, k16, p8);
+            const uint32_t emit = encode_keys_any<false, kSpan>(c, off, kp, lut, k16, p8);
             n_pos += __popc(emit);
 #pragma unroll
             for (int j = 0; j < 8; ++j) keys[j] = k16[j];
@@ -1135,6 +1134,41 @@ __global__ void combine_counts_kernel(PeerPtrs src, int world, uint64_t n, uint8
     }
 }
 
+// Count reduce of a replica group, in place and in slot order.  Phase 1 (reduce-scatter): this rank owns bytes
+// [seg0, seg1) of the vector; it sums every rank's copy of them (its own included), clamps at 255 and writes the
+// result back into its own copy -- peers only ever read the OTHER segments of this copy meanwhile.  Phase 2
+// (all-gather, after a barrier): it fetches every other segment from the rank that owns it.  Per rank 2 (W-1)/W bytes
+// per entry cross NVLink, against W bytes per entry when every rank reads all vectors.
+__global__ void reduce_segment_kernel(PeerPtrs src, int world, int rank, uint64_t seg0, uint64_t seg1) {
+    const uint64_t v0 = seg0 / 16, v1 = (seg1 + 15) / 16;  // segments are cut at multiples of 16 bytes (the vectors are padded)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) {
+        uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
+        for (int r = 0; r < world; ++r) {
+            const uint4 v = reinterpret_cast<const uint4*>(src.p[r])[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ev[j] += w[j] & 0x00ff00ffu;
+                od[j] += (w[j] >> 8) & 0x00ff00ffu;
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __vminu2(ev[j], 0x00ff00ffu) | (__vminu2(od[j], 0x00ff00ffu) << 8);
+        reinterpret_cast<uint4*>(src.p[rank])[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void gather_segments_kernel(PeerPtrs src, int world, int rank, uint64_t seg_bytes, uint64_t nbytes) {
+    const uint64_t nvec = (nbytes + 15) / 16, seg_vec = seg_bytes / 16;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint4* mine = reinterpret_cast<uint4*>(src.p[rank]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int owner = (int)min((uint64_t)(world - 1), i / seg_vec);
+        if (owner != rank) mine[i] = reinterpret_cast<const uint4*>(src.p[owner])[i];
+    }
+}
+
 // ---------------------------------------------------------------------------
 // count consumers: 256-bin histogram of c over a (static, per-graph) subset of the index entries --
 // the device half of Varigraph::get_hom_kmer (src/varigraph.cpp:253-296), SURVEY 8f N1.
@@ -1477,6 +1511,19 @@ cudaError_t launch_combine_counts(const PeerPtrs& counts, int world, uint64_t n,
     return cudaGetLastError();
 }
 
+cudaError_t launch_reduce_segment(const PeerPtrs& vecs, int world, int rank, uint64_t seg_bytes, uint64_t nbytes, int nsm, cudaStream_t s) {
+    const uint64_t seg0 = std::min<uint64_t>(nbytes, seg_bytes * rank);
+    const uint64_t seg1 = rank == world - 1 ? nbytes : std::min<uint64_t>(nbytes, seg_bytes * (rank + 1));
+    if (seg1 <= seg0) return cudaSuccess;
+    reduce_segment_kernel<<<grid_1d((seg1 - seg0) / 16 + 1, 256, (unsigned)nsm * 8), 256, 0, s>>>(vecs, world, rank, seg0, seg1);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_segments(const PeerPtrs& vecs, int world, int rank, uint64_t seg_bytes, uint64_t nbytes, int nsm, cudaStream_t s) {
+    if (nbytes == 0) return cudaSuccess;
+    gather_segments_kernel<<<grid_1d(nbytes / 16 + 1, 256, (unsigned)nsm * 8), 256, 0, s>>>(vecs, world, rank, seg_bytes, nbytes);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_clear_counts(const IndexView& ix, cudaStream_t s) {
     uint64_t nslots = 4ull * ix.nbuckets;
     clear_counts_kernel<<<grid_1d(nslots, 256, 148 * 16), 256, 0, s>>>(ix.slots, nslots);
@@ -1536,10 +1583,10 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
 
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes) { return tiles_for(make_chunk(d_bases, nbytes)); }
 
-cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k,
+cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint64_t* d_key56, uint64_t n, uint32_t k, uint32_t span,
                                    cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    prefilter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(words, nwords, d_key56, n, k);
+    prefilter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(words, nwords, d_key56, n, k, span);
     return cudaGetLastError();
 }
 
@@ -1553,8 +1600,10 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     // VG_SCATTER_TMA=1: the tile load as a bulk async copy into shared memory, a tile ahead (A/B knob; odd k)
     const char* tma_env = getenv("VG_SCATTER_TMA");
     const bool tma = tma_env && atoi(tma_env) != 0 && (ix.k & 1);
-    KernelT kern = (ix.k & 1) ? (tma ? (KernelT)scatter_kernel<true, true> : (KernelT)scatter_kernel<true, false>)
-                              : (KernelT)scatter_kernel<false, false>;
+    const bool s8 = pf.words && pf.span == 8;
+    KernelT kern = (ix.k & 1) ? (tma ? (s8 ? (KernelT)scatter_kernel<true, true, 8> : (KernelT)scatter_kernel<true, true, 4>)
+                                     : (s8 ? (KernelT)scatter_kernel<true, false, 8> : (KernelT)scatter_kernel<true, false, 4>))
+                              : (s8 ? (KernelT)scatter_kernel<false, false, 8> : (KernelT)scatter_kernel<false, false, 4>);
     // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
     // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
@@ -1690,6 +1739,25 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, con
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || sharded) return e;  // sharded: publish_counts re-armed the cursors already
     return cudaMemsetAsync(pv.cursor, 0, pv.P * sizeof(unsigned long long), s);
+}
+
+__global__ void sum_cursors_kernel(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* total) {
+    __shared__ unsigned long long sh[32];
+    unsigned long long v = 0;
+    for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) v += min((unsigned long long)cap, cursor[p]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += sh[w];
+        *total = t;
+    }
+}
+cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, cudaStream_t s) {
+    sum_cursors_kernel<<<1, 256, 0, s>>>(cursor, P, cap, d_total);
+    return cudaGetLastError();
 }
 
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv) {
