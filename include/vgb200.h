@@ -107,6 +107,13 @@ uint64_t vg_index_fastq_blocks(const vg_index* ix);
  * `window` bytes; -1 if there is none, -2 if the file cannot be read. */
 int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint64_t window);
 
+/* Host-only diagnostic (no GPU needed): what the host workers make of one block of plain four-line FASTQ text that
+ * starts at a record boundary -- "sequence\n" records at out (room for nbytes / 2 + 256 bytes), the number of bytes
+ * written as the result, *bases = their seq.l sum, *bad_at = offset of the first record that is not what kseq reads as a
+ * four-line record (-1: none; nothing from there on is written; the caller re-reads from there with the kseq reader).
+ * last != 0: the block ends at the end of the file, where the final newline may be missing. */
+int64_t vg_fastq_strip_block(const char* text, uint64_t nbytes, int last, uint8_t* out, uint64_t* bases, int64_t* bad_at);
+
 /* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
  * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */
 int vg_count_flush(vg_index* ix);
@@ -181,6 +188,10 @@ int vg_cbf_query(vg_cbf* cbf, const uint64_t* host_keys, uint64_t n, uint8_t* co
 int vg_comm_create(vg_ctx* ctx, int rank, int world, uint64_t arena_bytes, vg_comm** out);
 int vg_comm_handle(const vg_comm* comm, void* handle_out /* VG_COMM_HANDLE_BYTES */);
 int vg_comm_connect(vg_comm* comm, const void* handles /* world x VG_COMM_HANDLE_BYTES, rank order */);
+/* The same group with all ranks in ONE process (a host program that drives several GPUs itself, as the drop-in binary
+ * does for --gpu 0,1,...): out[r] becomes rank r on ctxs[r]'s GPU, the arenas are reached by ordinary peer access, no
+ * handles travel.  COLLECTIVE calls on such a group are made by every rank concurrently, one host thread per rank. */
+int vg_comm_create_local(vg_ctx* const* ctxs, int world, uint64_t arena_bytes, vg_comm** out /* world entries */);
 int vg_comm_destroy(vg_comm* comm);
 int vg_comm_rank(const vg_comm* comm);
 int vg_comm_world(const vg_comm* comm);

@@ -99,3 +99,73 @@ def test_fastq_record_boundary_heuristic(vglib, tmp_path):
     q.write_bytes(b"@not fastq\n" * 50)
     assert f(str(q).encode(), 5, 4096) == -1
     assert f(str(tmp_path / "missing").encode(), 5, 4096) == -2
+
+
+def _strip(vglib, data: bytes, last=True):
+    import ctypes
+    out = np.empty(len(data) // 2 + 512, dtype=np.uint8)
+    bases, bad = ctypes.c_uint64(0), ctypes.c_int64(0)
+    w = vglib.lib.vg_fastq_strip_block(data, len(data), 1 if last else 0, out.ctypes.data, ctypes.byref(bases), ctypes.byref(bad))
+    return out[:w].tobytes(), int(bases.value), int(bad.value)
+
+
+def _no_empty(lines: bytes) -> bytes:
+    """The staged form without empty reads (they emit no k-mer; the feeder does not stage them)."""
+    return b"".join(x + b"\n" for x in lines.split(b"\n") if x)
+
+
+def test_fastq_strip_block_vs_kseq_restatement(vglib, oracle):
+    """Host half of the strip road: the vectorised four-line scanner accepts exactly the records kseq reads as four-line
+    records.  On randomly damaged FASTQ, (what it wrote) + (kseq on the rest, from the record it stopped at) must equal
+    kseq on the whole text -- sequences and seq.l sum -- and a clean text must pass untouched."""
+    import random
+    rng = random.Random(2026)
+    recs = []
+    for i in range(3000):
+        n = rng.choice([0, 1, 1, 30, 75, 100, 150, 151, 191, 192, 193, 250, 400]) if i % 9 == 0 else 150
+        seq = bytes(rng.choice(b"ACGTNacgt") for _ in range(n))
+        qual = bytes(rng.choice(b"@+>IJ#") for _ in range(n))
+        eol = b"\r\n" if i % 7 == 0 else b"\n"
+        recs.append(b"@r%d some text" % i + eol + seq + eol + b"+" + (b"r%d" % i if i % 5 == 0 else b"") + eol + qual + eol)
+    clean = b"".join(recs)
+    lines, nreads, bases, status = oracle.fastq_to_lines(clean)
+    lines = _no_empty(lines)
+    w, b, bad = _strip(vglib, clean)
+    assert bad == -1 and b == bases and w == lines
+    w, b, bad = _strip(vglib, clean[:-1])  # no final newline at EOF
+    assert bad == -1 and b == bases and w == lines
+    w, b, bad = _strip(vglib, clean[:-1], last=False)  # ... which a block in the middle of a file may not have
+    assert bad >= 0 and clean[bad - 1: bad] == b"\n"
+    for trial in range(300):
+        data = bytearray(clean[: rng.randrange(2000, len(clean))] if trial % 4 == 0 else clean)
+        for _ in range(rng.randint(1, 3)):
+            at = rng.randrange(len(data))
+            kind = rng.randrange(7)
+            if kind == 0:
+                nl = data.find(b"\n", at)
+                if nl >= 0:
+                    del data[nl]
+            elif kind == 1:
+                data.insert(at, 10)
+            elif kind == 2:
+                data.insert(at, rng.choice(b"@+>\r\x00 "))
+            elif kind == 3:
+                data[at] = rng.choice(b"@+>\rN\x00")
+            elif kind == 4:
+                del data[max(at, len(data) // 2):]
+            elif kind == 5:
+                nl = data.find(b"\n", at)
+                if nl >= 0:
+                    data.insert(nl, 13)
+            else:
+                data[at:at] = b">fasta\nACGTACGT\n"
+        data = bytes(data)
+        want_lines, _, want_bases, _ = oracle.fastq_to_lines(data)
+        want_lines = _no_empty(want_lines)
+        w, b, bad = _strip(vglib, data)
+        if bad < 0:
+            assert (w, b) == (want_lines, want_bases), trial
+            continue
+        assert bad == 0 or data[bad - 1: bad] == b"\n", trial
+        rest_lines, _, rest_bases, _ = oracle.fastq_to_lines(data[bad:])
+        assert w + _no_empty(rest_lines) == want_lines and b + rest_bases == want_bases, (trial, bad)

@@ -116,6 +116,53 @@ int vg_comm_create(vg_ctx* c, int rank, int world, uint64_t arena_bytes, vg_comm
     return VG_OK;
 }
 
+// All ranks in one process (the C++ host driving several GPUs): the arenas are reached through ordinary peer access.
+// Collective calls on such a group must still be made by every rank, CONCURRENTLY (one host thread per rank): they
+// wait for each other on the device.
+int vg_comm_create_local(vg_ctx* const* ctxs, int world, uint64_t arena_bytes, vg_comm** out) {
+    if (!ctxs || !out) return fail(VG_E_INVALID, "vg_comm_create_local: NULL argument");
+    if (world < 1 || world > vg::kMaxWorld) return fail(VG_E_INVALID, "world %d outside 1..%d", world, vg::kMaxWorld);
+    for (int r = 0; r < world; ++r) {
+        out[r] = nullptr;
+        if (!ctxs[r]) return fail(VG_E_INVALID, "vg_comm_create_local: ctxs[%d] is NULL", r);
+        for (int q = 0; q < r; ++q)
+            if (ctxs[q]->device == ctxs[r]->device) return fail(VG_E_INVALID, "vg_comm_create_local: device %d listed twice", ctxs[r]->device);
+    }
+    int rc = VG_OK;
+    for (int r = 0; r < world && rc == VG_OK; ++r) rc = vg_comm_create(ctxs[r], r, world, arena_bytes, &out[r]);
+    for (int r = 0; r < world && rc == VG_OK; ++r) {
+        DeviceGuard g(ctxs[r]->device);
+        for (int q = 0; q < world && rc == VG_OK; ++q) {
+            if (q == r) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
+            if (!can) {
+                rc = fail(VG_E_CUDA, "GPU %d cannot reach GPU %d's memory", ctxs[r]->device, ctxs[q]->device);
+                break;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail(VG_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            out[r]->peer_base[q] = out[q]->arena;
+        }
+        if (rc == VG_OK) {
+            out[r]->connected = true;
+            out[r]->local = true;
+        }
+    }
+    if (rc != VG_OK)
+        for (int r = 0; r < world; ++r) {
+            if (out[r]) {
+                for (int q = 0; q < world; ++q)
+                    if (q != r) out[r]->peer_base[q] = nullptr;
+                out[r]->local = true;  // nothing to unmap
+                vg_comm_destroy(out[r]);
+                out[r] = nullptr;
+            }
+        }
+    return rc;
+}
+
 int vg_comm_handle(const vg_comm* cm, void* handle_out) {
     if (!cm || !handle_out) return fail(VG_E_INVALID, "vg_comm_handle: NULL argument");
     DeviceGuard g(cm->ctx->device);
@@ -165,8 +212,9 @@ int vg_comm_destroy(vg_comm* cm) {
     if (!cm) return VG_OK;
     DeviceGuard g(cm->ctx->device);
     cudaDeviceSynchronize();
-    for (int r = 0; r < cm->world; ++r)
-        if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);
+    if (!cm->local)
+        for (int r = 0; r < cm->world; ++r)
+            if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);
     cudaFree(cm->arena);
     cudaFree(cm->d_timeout);
     cudaFree(cm->d_reduced);
@@ -232,16 +280,17 @@ struct ReplicaMail {  // what the root tells the others, through its arena
     uint64_t magic, n, m_slots, duplicates, cap, cap2, round_keys, slack;
     uint32_t k, nbuckets, P, shift, shift2, sub_bits, filter_nwords, filter_span, may_grow, pad;
     cudaIpcMemHandle_t h_slots, h_rank_base, h_perm, h_filter;
+    const void *p_slots, *p_rank_base, *p_perm, *p_filter;  // the same buffers as plain pointers (ranks of one process)
 };
 constexpr uint64_t kMailMagic = 0x76676232303072ULL;
 
 // one buffer of the root's index -> this rank's copy of it (peer-to-peer over NVLink through a CUDA IPC mapping)
-int pull_buffer(const cudaIpcMemHandle_t& h, void* dst, size_t bytes, cudaStream_t s) {
-    void* src = nullptr;
-    CU(cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess));
-    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+int pull_buffer(const cudaIpcMemHandle_t& h, const void* local_src, void* dst, size_t bytes, cudaStream_t s) {
+    void* src = const_cast<void*>(local_src);
+    if (!local_src) CU(cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaIpcCloseMemHandle(src);
+    if (!local_src) cudaIpcCloseMemHandle(src);
     if (e != cudaSuccess) return fail(VG_E_CUDA, "replica copy of %zu bytes: %s", bytes, cudaGetErrorString(e));
     return VG_OK;
 }
@@ -281,10 +330,17 @@ int vg_index_replicate(vg_comm* cm, int root, vg_index* root_ix, vg_index** out)
         mail.filter_nwords = ps.filter.words ? ps.filter.nwords : 0;
         mail.filter_span = ps.filter.span;
         mail.may_grow = ps.may_grow ? 1 : 0;
-        CU(cudaIpcGetMemHandle(&mail.h_slots, root_ix->view.slots));
-        CU(cudaIpcGetMemHandle(&mail.h_rank_base, root_ix->view.rank_base));
-        CU(cudaIpcGetMemHandle(&mail.h_perm, root_ix->d_perm));
-        if (mail.filter_nwords) CU(cudaIpcGetMemHandle(&mail.h_filter, ps.d_filter));
+        if (cm->local) {
+            mail.p_slots = root_ix->view.slots;
+            mail.p_rank_base = root_ix->view.rank_base;
+            mail.p_perm = root_ix->d_perm;
+            mail.p_filter = ps.d_filter;
+        } else {
+            CU(cudaIpcGetMemHandle(&mail.h_slots, root_ix->view.slots));
+            CU(cudaIpcGetMemHandle(&mail.h_rank_base, root_ix->view.rank_base));
+            CU(cudaIpcGetMemHandle(&mail.h_perm, root_ix->d_perm));
+            if (mail.filter_nwords) CU(cudaIpcGetMemHandle(&mail.h_filter, ps.d_filter));
+        }
         CU(cudaMemcpyAsync(d_mail, &mail, sizeof mail, cudaMemcpyHostToDevice, s));
     }
     int rc = barrier_on(cm, s);  // the mail is in the root's arena
@@ -344,11 +400,11 @@ int vg_index_replicate(vg_comm* cm, int root, vg_index* root_ix, vg_index** out)
         if (e != cudaSuccess)
             return bail(fail(e == cudaErrorMemoryAllocation ? VG_E_NOMEM : VG_E_CUDA, "replica of %llu k-mers: %s",
                              (unsigned long long)mail.n, cudaGetErrorString(e)));
-        if ((rc = pull_buffer(mail.h_slots, ix->view.slots, (size_t)mail.nbuckets * 32, s)) != VG_OK) return bail(rc);
-        if ((rc = pull_buffer(mail.h_rank_base, ix->view.rank_base, (size_t)mail.nbuckets * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
-        if ((rc = pull_buffer(mail.h_perm, ix->d_perm, (size_t)mail.n * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
+        if ((rc = pull_buffer(mail.h_slots, cm->local ? mail.p_slots : nullptr, ix->view.slots, (size_t)mail.nbuckets * 32, s)) != VG_OK) return bail(rc);
+        if ((rc = pull_buffer(mail.h_rank_base, cm->local ? mail.p_rank_base : nullptr, ix->view.rank_base, (size_t)mail.nbuckets * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
+        if ((rc = pull_buffer(mail.h_perm, cm->local ? mail.p_perm : nullptr, ix->d_perm, (size_t)mail.n * sizeof(uint32_t), s)) != VG_OK) return bail(rc);
         if (mail.filter_nwords) {
-            if ((rc = pull_buffer(mail.h_filter, ps.d_filter, (size_t)mail.filter_nwords * 4, s)) != VG_OK) return bail(rc);
+            if ((rc = pull_buffer(mail.h_filter, cm->local ? mail.p_filter : nullptr, ps.d_filter, (size_t)mail.filter_nwords * 4, s)) != VG_OK) return bail(rc);
             ps.filter.words = ps.d_filter;
             ps.filter.nwords = mail.filter_nwords;
             ps.filter.span = mail.filter_span;

@@ -36,6 +36,7 @@
 #include <cctype>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -176,6 +177,7 @@ struct Feeder {
     std::atomic<int> next_file{0};
     std::atomic<size_t> next_raw{0};
     std::atomic<uint64_t> read_bases{0};
+    std::atomic<uint64_t> busy_ns{0};   // time the block workers spent working (VG_FEEDER_DEBUG)
 
     int take_free() {
         std::unique_lock<std::mutex> lk(mu);
@@ -277,7 +279,7 @@ struct StripState {
     const char* rec;      // start of the current record
     const char* nl[4];    // the newlines that end its lines
     int li = 0;
-    uint64_t nul_seen = 0;
+    const char* nul_hi = nullptr;  // the last NUL byte seen so far (the scan runs ahead of the records by up to a vector)
     uint8_t* o;
     uint64_t bases = 0;
     const char* end;
@@ -296,10 +298,7 @@ static inline __attribute__((always_inline)) bool strip_record(StripState& st) {
     const char s0 = sraw ? seq[0] : 'A';
     const bool ok = (st.rec[0] == '@') & (st.nl[0] != st.rec) & (st.nl[2] != plus) & (sl == ql) & (s0 != '@') & (s0 != '+') & (s0 != '>');
     if (!ok || plus[0] != '+') return false;
-    if (st.nul_seen) {
-        if (memchr(seq, 0, sl)) return false;
-        st.nul_seen = 0;
-    }
+    if (st.nul_hi >= seq && memchr(seq, 0, sl)) return false;
     if (sl) {
         if (sl <= 192 && seq + 192 <= st.end) memcpy(st.o, seq, 192);  // three whole vectors (the chunk has slack behind it)
         else memcpy(st.o, seq, sl);
@@ -313,7 +312,8 @@ static inline __attribute__((always_inline)) bool strip_record(StripState& st) {
 #define VG_STRIP_STEP(mask_nl, mask_zero, width)                      \
     while (p + (width) <= end) {                                      \
         uint64_t m = (mask_nl);                                       \
-        st.nul_seen |= (mask_zero);                                   \
+        const uint64_t mz = (mask_zero);                              \
+        if (mz) st.nul_hi = p + (63 - __builtin_clzll(mz));           \
         while (m) {                                                   \
             st.nl[st.li] = p + __builtin_ctzll(m);                    \
             m &= m - 1;                                               \
@@ -351,7 +351,7 @@ static uint64_t strip_block(const char* p0, const char* end, bool last, uint8_t*
     if (isa == 2) ok = strip_scan_avx512(st, p, end);
     else if (isa == 1) ok = strip_scan_avx2(st, p, end);
     for (; ok && p < end; ++p) {
-        if (*p == 0) st.nul_seen = 1;
+        if (*p == 0) st.nul_hi = p;
         if (*p == '\n') {
             st.nl[st.li] = p;
             if (++st.li == 4) {
@@ -387,8 +387,15 @@ void strip_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, co
         const RawFile& f = (*files)[(size_t)it.file];
         Filled out{slot, 0, (int64_t)idx};
         const char* bad = nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         out.len = strip_block(f.map + it.start, f.map + it.end, it.last, ctx->ring[(size_t)slot].h_pin, out.bases, bad);
         if (bad) out.bad_at = (uint64_t)(bad - f.map);
+        {   // give the block's pages back right away, here, in parallel: tearing down the whole mapping at the end costs
+            // the calling thread ~20 ms per GB (the kseq fallback re-opens the file, it does not need the mapping)
+            const uint64_t page = 4096, a = (it.start + page - 1) & ~(page - 1), b = it.end & ~(page - 1);
+            if (b > a) munmap((void*)(f.map + a), (size_t)(b - a));
+        }
+        fd->busy_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
         {
             std::lock_guard<std::mutex> lk(fd->mu);
             fd->ready_q.push_back(out);
@@ -413,6 +420,7 @@ void raw_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, cons
         const RawFile& f = (*files)[(size_t)it.file];
         uint8_t* dst = ctx->ring[(size_t)slot].h_pin;
         uint64_t len = it.end - it.start, got = 0;
+        const auto t0 = std::chrono::steady_clock::now();
         while (got < len) {
             ssize_t r = pread(f.fd, dst + got, (size_t)(len - got), (off_t)(it.start + got));
             if (r <= 0) break;
@@ -423,6 +431,7 @@ void raw_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, cons
             break;
         }
         if (it.last && len && dst[len - 1] != '\n') dst[len++] = '\n';
+        fd->busy_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
         fd->push_ready(slot, len, (int64_t)idx);
     }
     fd->worker_done();
@@ -557,6 +566,7 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
         if (rc) return rc;
     }
     Feeder fd;
+    const auto t_start = std::chrono::steady_clock::now();
     for (int i = 0; i < (int)ctx->ring.size(); ++i) fd.free_q.push_back(i);
     fd.workers_left = nworkers;
     std::vector<std::thread> pool;
@@ -634,6 +644,10 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
         if (finished) break;
     }
     for (auto& t : pool) t.join();
+    if (getenv("VG_FEEDER_DEBUG"))
+        fprintf(stderr, "[vg_feeder] %d kseq + %d block workers (%s road), %zu blocks, workers busy %.1f ms in total, wall %.1f ms\n", nk, nr,
+                strip ? "strip" : "device", items.size(), fd.busy_ns.load() * 1e-6,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (read_bases) *read_bases += fd.read_bases.load() + strip_bases;
     if (fd.err != VG_OK) return vg::fail(fd.err, "%s", fd.err_msg.c_str());
     return VG_OK;
@@ -720,6 +734,17 @@ extern "C" int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint6
     }
     close(fd);
     return r;
+}
+
+// Host-only test hook (needs no GPU): the strip road's scanner over one block of text that starts at a record boundary.
+extern "C" int64_t vg_fastq_strip_block(const char* text, uint64_t nbytes, int last, uint8_t* out, uint64_t* bases, int64_t* bad_at) {
+    if ((!text && nbytes) || !out) return -1;
+    uint64_t b = 0;
+    const char* bad = nullptr;
+    const uint64_t w = strip_block(text, text + nbytes, last != 0, out, b, bad);
+    if (bases) *bases = b;
+    if (bad_at) *bad_at = bad ? (int64_t)(bad - text) : -1;
+    return (int64_t)w;
 }
 
 extern "C" int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {

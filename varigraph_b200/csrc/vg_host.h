@@ -107,6 +107,7 @@ struct vg_comm {
     size_t arena_bytes = 0, arena_used = 0;
     uint8_t* peer_base[vg::kMaxWorld] = {};
     bool connected = false;
+    bool local = false;                  // all ranks live in this process (vg_comm_create_local): plain peer pointers, no CUDA IPC
     unsigned long long epoch = 0;        // barriers enqueued so far (same on every rank)
     unsigned int* d_timeout = nullptr;   // raised by a barrier that gave up on a peer
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
