@@ -97,10 +97,17 @@ int vg_count_submit_device(vg_index* ix, const void* dev_bases, uint64_t nbytes,
  * FastqKmer::fastq_file_open for each path.  threads = inflate/parse workers (files are
  * processed concurrently).  *read_bases accumulates mReadBase (src/fastq_kmer.cpp:105). */
 int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
-/* Plain (not gzip) four-line FASTQ is shipped as raw text and parsed on the GPU, every record checked
- * against kseq's rules; anything else -- and a file from its first irregular record on -- goes through
- * the host kseq reader, so results never depend on the road taken.  This counts the raw blocks the
- * device accepted so far (diagnostic; VG_RAW_FASTQ=0 disables the raw road). */
+/* The same for ONE sample counted on several GPUs of this process: ixs[g] = a replica of the index on GPU g
+ * (vg_index_replicate over a vg_comm_create_local group), each begun with vg_count_begin.  One set of workers reads
+ * the files; the staged chunks are dealt to the GPUs as they come, so the reads are sharded over the GPUs whatever the
+ * number of files.  Afterwards every rank calls vg_count_allreduce_slots (concurrently). */
+int vg_count_files_multi(vg_index* const* ixs, int nix, const char* const* paths, int npaths, int threads,
+                         uint64_t* read_bases);
+/* Plain (not gzip) four-line FASTQ is cut into record-aligned blocks that many workers handle at once: by default they
+ * strip it to its sequences on the host (vector scan of the memory-mapped file, every record checked against kseq's
+ * rules; VG_FASTQ_ROAD=device ships the raw text and does the same on the GPU).  Anything else -- and a file from its
+ * first irregular record on -- goes through the host kseq reader, so results never depend on the road taken.  This
+ * counts the blocks accepted without a flaw so far (diagnostic; VG_FASTQ_ROAD=kseq disables the block roads). */
 uint64_t vg_index_fastq_blocks(const vg_index* ix);
 /* Host-only diagnostic (no GPU needed): the byte offset at which the raw road would cut `path` at or after
  * `at` -- the first line start whose line begins with '@' and whose next-but-one line begins with '+' within

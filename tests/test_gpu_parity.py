@@ -732,6 +732,50 @@ def test_genotype_two_samples_in_one_run(tmp_path):
     assert out["gpu", "S1"] == out["cpu", "S1"] and out["gpu", "S1"] != out["gpu", "S0"]
 
 
+def _gpu_list():
+    """Two GPU ids for the drop-in's --gpu: distinct devices where the box has them, else the same one twice (the
+    in-process group then runs both ranks on it -- every code path but the NVLink hop)."""
+    import torch
+    return ("0,1", {}) if torch.cuda.device_count() >= 2 else ("0,0", {"VG_ALLOW_SAME_DEVICE": "1"})
+
+
+@pytest.mark.parametrize("nsamples", [1, 3])
+def test_genotype_on_two_gpus_from_the_host_binary(tmp_path, monkeypatch, nsamples):
+    """`varigraph_b200 genotype --gpu a,b`: the C++ host builds the index once, replicates it, and either deals ONE
+    sample's reads over both GPUs and combines the counts in slot order (1 sample), or deals the samples over the GPUs
+    and genotypes them in list order (3 samples >= 2 GPUs).  VCFs byte-identical to the reference's either way."""
+    ref_bin, b200 = _integrated()
+    t = helpers.tiny()
+    (tmp_path / "graph.bin").write_bytes(t["graph_bin"])
+    f1, f2 = helpers.write_tiny_fastqs(str(tmp_path), t, gz=False)
+    cfg = [f"S0 {f1} {f2}"]
+    n = len(t["m1"])
+    for i in range(1, nsamples):
+        a, b = str(tmp_path / f"T{i}_1.fq"), str(tmp_path / f"T{i}_2.fq.gz")
+        synth.write_fastq(a, t["m1"][: n * (3 - i) // 4], "c")
+        synth.write_fastq(b, t["m2"][: n * (3 - i) // 4], "d")
+        cfg.append(f"S{i} {a} {b}")
+    (tmp_path / "samples.cfg").write_text("\n".join(cfg) + "\n")
+    gpus, env = _gpu_list()
+    for k, v in {"VG_PARTITION": "1", "VG_SLICE_BYTES": "262144", **env}.items():  # a 2.8 MB table, driven through the sweep
+        monkeypatch.setenv(k, v)
+    out = {}
+    for name, exe, extra in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", gpus, "--buffer", "1"])):
+        d = tmp_path / name
+        d.mkdir()
+        log = _run([exe, "genotype", "--load-graph", str(tmp_path / "graph.bin"), "-s", str(tmp_path / "samples.cfg"), "-t", "4"] + extra,
+                   cwd=str(d))
+        if name == "gpu":
+            assert "replicas on 1 more" in log
+            assert ("counted on GPU" in log) == (nsamples >= 2)
+        for i in range(nsamples):
+            with gzip.open(d / f"S{i}.varigraph.vcf.gz", "rb") as f:
+                out[name, i] = f.read()
+    assert out["gpu", 0] == out["cpu", 0] == t["vcf"]
+    for i in range(1, nsamples):
+        assert out["gpu", i] == out["cpu", i]
+
+
 def test_construct_on_gpu_then_identical_genotypes(tmp_path):
     """`construct` with the CBF filled on the device, then both binaries genotype from that graph."""
     ref_bin, b200 = _integrated()

@@ -56,6 +56,7 @@ def _load() -> ctypes.CDLL:
         "vg_count_submit": (c_int, [c_void_p, c_void_p, c_uint64]),
         "vg_count_submit_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
         "vg_count_files": (c_int, [c_void_p, P(c_char_p), c_int, c_int, P(c_uint64)]),
+        "vg_count_files_multi": (c_int, [P(c_void_p), c_int, P(c_char_p), c_int, c_int, P(c_uint64)]),
         "vg_count_flush": (c_int, [c_void_p]),
         "vg_index_fastq_blocks": (c_uint64, [c_void_p]),
         "vg_fastq_record_boundary": (ctypes.c_int64, [c_char_p, c_uint64, c_uint64]),

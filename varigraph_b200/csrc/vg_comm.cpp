@@ -125,8 +125,12 @@ int vg_comm_create_local(vg_ctx* const* ctxs, int world, uint64_t arena_bytes, v
     for (int r = 0; r < world; ++r) {
         out[r] = nullptr;
         if (!ctxs[r]) return fail(VG_E_INVALID, "vg_comm_create_local: ctxs[%d] is NULL", r);
-        for (int q = 0; q < r; ++q)
-            if (ctxs[q]->device == ctxs[r]->device) return fail(VG_E_INVALID, "vg_comm_create_local: device %d listed twice", ctxs[r]->device);
+        for (int q = 0; q < r; ++q) {
+            if (ctxs[q] == ctxs[r]) return fail(VG_E_INVALID, "vg_comm_create_local: one context listed twice");
+            // two ranks on one device work (the tests of a 1-GPU box do that) but make no sense in production
+            if (ctxs[q]->device == ctxs[r]->device && !getenv("VG_ALLOW_SAME_DEVICE"))
+                return fail(VG_E_INVALID, "vg_comm_create_local: device %d listed twice", ctxs[r]->device);
+        }
     }
     int rc = VG_OK;
     for (int r = 0; r < world && rc == VG_OK; ++r) rc = vg_comm_create(ctxs[r], r, world, arena_bytes, &out[r]);
@@ -134,15 +138,17 @@ int vg_comm_create_local(vg_ctx* const* ctxs, int world, uint64_t arena_bytes, v
         DeviceGuard g(ctxs[r]->device);
         for (int q = 0; q < world && rc == VG_OK; ++q) {
             if (q == r) continue;
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
-            if (!can) {
-                rc = fail(VG_E_CUDA, "GPU %d cannot reach GPU %d's memory", ctxs[r]->device, ctxs[q]->device);
-                break;
+            if (ctxs[r]->device != ctxs[q]->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
+                if (!can) {
+                    rc = fail(VG_E_CUDA, "GPU %d cannot reach GPU %d's memory", ctxs[r]->device, ctxs[q]->device);
+                    break;
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail(VG_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                cudaGetLastError();
             }
-            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail(VG_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
-            cudaGetLastError();
             out[r]->peer_base[q] = out[q]->arena;
         }
         if (rc == VG_OK) {

@@ -135,6 +135,17 @@ class KseqReader {
     std::string qual_;
 };
 
+// The consumers of one feeder: one index per GPU (one for vg_count_files).  A staging slot belongs to one of them; its
+// id is sink * kSlotsPerSink + slot, and a chunk goes to the GPU whose slot a worker happened to fill.
+constexpr int kSlotsPerSink = 4096;
+struct Sinks {
+    std::vector<vg_index*> ix;
+    vg_ctx* ctx(int id) const { return ix[(size_t)(id / kSlotsPerSink)]->ctx; }
+    vg_index* index(int id) const { return ix[(size_t)(id / kSlotsPerSink)]; }
+    vg::StageSlot& slot(int id) const { return ctx(id)->ring[(size_t)(id % kSlotsPerSink)]; }
+    size_t chunk_bytes() const { return ix[0]->ctx->chunk_bytes; }
+};
+
 struct Filled {
     int slot;
     uint64_t len;
@@ -222,11 +233,11 @@ struct Feeder {
     }
 };
 
-void kseq_worker(Feeder* fd, vg_ctx* ctx, const std::vector<KseqItem>* items) {
+void kseq_worker(Feeder* fd, const Sinks* sinks, const std::vector<KseqItem>* items) {
     std::string seq;
     int slot = -1;
     uint64_t w = 0, bases = 0;
-    const uint64_t cap = ctx->chunk_bytes;
+    const uint64_t cap = sinks->chunk_bytes();
     for (;;) {
         int fi = fd->next_file.fetch_add(1);
         if (fi >= (int)items->size()) break;
@@ -258,7 +269,7 @@ void kseq_worker(Feeder* fd, vg_ctx* ctx, const std::vector<KseqItem>* items) {
                 if (slot < 0) { stop = true; break; }
                 w = 0;
             }
-            uint8_t* dst = ctx->ring[(size_t)slot].h_pin + w;
+            uint8_t* dst = sinks->slot(slot).h_pin + w;
             memcpy(dst, seq.data(), (size_t)use);
             dst[use] = '\n';
             w += use + 1;
@@ -374,7 +385,7 @@ static uint64_t strip_block(const char* p0, const char* end, bool last, uint8_t*
     return (uint64_t)(st.o - out);
 }
 
-void strip_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
+void strip_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
     for (;;) {
         int slot = fd->take_free();
         if (slot < 0) break;
@@ -388,7 +399,7 @@ void strip_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, co
         Filled out{slot, 0, (int64_t)idx};
         const char* bad = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
-        out.len = strip_block(f.map + it.start, f.map + it.end, it.last, ctx->ring[(size_t)slot].h_pin, out.bases, bad);
+        out.len = strip_block(f.map + it.start, f.map + it.end, it.last, sinks->slot(slot).h_pin, out.bases, bad);
         if (bad) out.bad_at = (uint64_t)(bad - f.map);
         {   // give the block's pages back right away, here, in parallel: tearing down the whole mapping at the end costs
             // the calling thread ~20 ms per GB (the kseq fallback re-opens the file, it does not need the mapping)
@@ -407,7 +418,7 @@ void strip_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, co
 
 // A slot first, then the next block: the lowest outstanding block always has a buffer, so the in-order
 // submission of the calling thread cannot starve.
-void raw_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
+void raw_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
     for (;;) {
         int slot = fd->take_free();
         if (slot < 0) break;
@@ -418,7 +429,7 @@ void raw_worker(Feeder* fd, vg_ctx* ctx, const std::vector<RawFile>* files, cons
         }
         const RawItem& it = (*items)[idx];
         const RawFile& f = (*files)[(size_t)it.file];
-        uint8_t* dst = ctx->ring[(size_t)slot].h_pin;
+        uint8_t* dst = sinks->slot(slot).h_pin;
         uint64_t len = it.end - it.start, got = 0;
         const auto t0 = std::chrono::steady_clock::now();
         while (got < len) {
@@ -478,7 +489,7 @@ bool raw_enabled() { return fastq_road() != kKseq; }
 
 // Route one path: plain text starting with '@' -> raw blocks (as far as record boundaries can be found),
 // anything else (gzip, FASTA, leading junk) -> the kseq reader.  false: cannot open.
-bool plan_file(const char* path, vg_ctx* ctx, std::vector<RawFile>& raws, std::vector<RawItem>& items,
+bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& raws, std::vector<RawItem>& items,
                std::vector<KseqItem>& kseqs) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) return false;
@@ -496,7 +507,7 @@ bool plan_file(const char* path, vg_ctx* ctx, std::vector<RawFile>& raws, std::v
     f.path = path;
     f.fd = fd;
     f.size = (uint64_t)st.st_size;
-    if (fastq_road() == kStrip) {
+    if (fastq_road() == kStrip || multi) {  // several GPUs: the host workers strip (the device road parses on ONE device)
         void* m = mmap(nullptr, (size_t)f.size, PROT_READ, MAP_SHARED, fd, 0);
         if (m == MAP_FAILED) {
             close(fd);
@@ -532,61 +543,80 @@ bool plan_file(const char* path, vg_ctx* ctx, std::vector<RawFile>& raws, std::v
 
 // One pass of workers over the given work; the calling thread copies and launches.  Raw blocks are submitted
 // strictly in item order (the per-file "bad from here on" flag relies on stream order).
-int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<RawFile>& raws,
+int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vector<RawFile>& raws,
                const std::vector<RawItem>& items, vg::FastqFileState* d_files, int threads, uint64_t* read_bases) {
-    vg_ctx* ctx = ix->ctx;
+    const int nsink = (int)sinks.ix.size();
     const bool strip = !raws.empty() && raws[0].map != nullptr;  // one road per call (plan_file decides)
     int nk = std::min<int>(threads, (int)kseqs.size());
     // device road: the workers only move bytes, 16 saturate the link; strip road: the scan is the work, take them all
     int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, strip ? 64 : 16), (int)items.size()));
     const int nworkers = nk + nr;
     if (nworkers == 0) return VG_OK;
-    const int nslots = std::max(3, nworkers + 2);
+    const int nslots = std::max(3, (nworkers + 2 + nsink - 1) / nsink + (nsink > 1 ? 1 : 0));
     // ring slots (pinned + device pairs); allocation is done here on the calling thread
-    while ((int)ctx->ring.size() < nslots) {
-        vg::StageSlot s;
-        cudaError_t e = cudaMalloc((void**)&s.d_buf, ctx->chunk_bytes + 256);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
-        if (e != cudaSuccess) return vg::fail(VG_E_NOMEM, "staging ring: %s", cudaGetErrorString(e));
-        ctx->ring.push_back(s);
-    }
-    for (auto& s : ctx->ring) {  // the feeder's workers fill the pinned twins directly
-        if (!s.h_pin && cudaHostAlloc((void**)&s.h_pin, ctx->chunk_bytes + 256, cudaHostAllocDefault) != cudaSuccess)
-            return vg::fail(VG_E_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    for (auto& sl : ctx->ring) {
-        if (sl.busy) {
-            cudaEventSynchronize(sl.done);
-            sl.busy = false;
+    for (vg_index* ix : sinks.ix) {
+        vg_ctx* ctx = ix->ctx;
+        vg::DeviceGuard g(ctx->device);
+        while ((int)ctx->ring.size() < nslots) {
+            vg::StageSlot s;
+            cudaError_t e = cudaMalloc((void**)&s.d_buf, ctx->chunk_bytes + 256);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+            if (e != cudaSuccess) return vg::fail(VG_E_NOMEM, "staging ring: %s", cudaGetErrorString(e));
+            ctx->ring.push_back(s);
         }
-    }
-    if (nr && !strip) {
-        int rc = vg::ctx_ensure_fastq(ctx);
-        if (rc) return rc;
+        for (auto& s : ctx->ring) {  // the feeder's workers fill the pinned twins directly
+            if (!s.h_pin && cudaHostAlloc((void**)&s.h_pin, ctx->chunk_bytes + 256, cudaHostAllocDefault) != cudaSuccess)
+                return vg::fail(VG_E_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        for (auto& sl : ctx->ring) {
+            if (sl.busy) {
+                cudaEventSynchronize(sl.done);
+                sl.busy = false;
+            }
+        }
+        if (nr && !strip) {
+            int rc = vg::ctx_ensure_fastq(ctx);
+            if (rc) return rc;
+        }
     }
     Feeder fd;
     const auto t_start = std::chrono::steady_clock::now();
-    for (int i = 0; i < (int)ctx->ring.size(); ++i) fd.free_q.push_back(i);
+    {   // free slots, the GPUs' interleaved: consecutive chunks go to different GPUs
+        size_t most = 0;
+        for (vg_index* ix : sinks.ix) most = std::max(most, ix->ctx->ring.size());
+        for (size_t i = 0; i < most; ++i)
+            for (int c = 0; c < nsink; ++c)
+                if (i < sinks.ix[(size_t)c]->ctx->ring.size()) fd.free_q.push_back(c * kSlotsPerSink + (int)i);
+    }
     fd.workers_left = nworkers;
     std::vector<std::thread> pool;
-    for (int i = 0; i < nk; ++i) pool.emplace_back(kseq_worker, &fd, ctx, &kseqs);
+    for (int i = 0; i < nk; ++i) pool.emplace_back(kseq_worker, &fd, &sinks, &kseqs);
     for (int i = 0; i < nr; ++i) {
-        if (strip) pool.emplace_back(strip_worker, &fd, ctx, &raws, &items);
-        else pool.emplace_back(raw_worker, &fd, ctx, &raws, &items);
+        if (strip) pool.emplace_back(strip_worker, &fd, &sinks, &raws, &items);
+        else pool.emplace_back(raw_worker, &fd, &sinks, &raws, &items);
     }
     uint64_t strip_bases = 0;
+    auto enqueue = [&](int id, uint64_t len) {  // a staged chunk of "sequence\n" records -> its GPU
+        vg::DeviceGuard g(sinks.ctx(id)->device);
+        return vg::enqueue_piece(sinks.index(id), id % kSlotsPerSink, (const char*)sinks.slot(id).h_pin, len);
+    };
 
     std::deque<int> inflight;
     std::map<int64_t, Filled> raw_ready;  // raw blocks that arrived ahead of their turn
     int64_t next_raw_submit = 0;
     int rc = VG_OK;
     for (;;) {
-        while (!inflight.empty() && cudaEventQuery(ctx->ring[(size_t)inflight.front()].done) == cudaSuccess) {
-            ctx->ring[(size_t)inflight.front()].busy = false;
-            fd.give_free(inflight.front());
-            inflight.pop_front();
+        for (auto it = inflight.begin(); it != inflight.end();) {  // per GPU in order; the GPUs finish independently
+            if (cudaEventQuery(sinks.slot(*it).done) == cudaSuccess) {
+                sinks.slot(*it).busy = false;
+                fd.give_free(*it);
+                it = inflight.erase(it);
+            } else {
+                ++it;
+            }
         }
+        cudaGetLastError();
         Filled f{-1, 0, -1};
         bool finished = false;
         {
@@ -603,7 +633,7 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
             }
         }
         if (f.slot >= 0 && f.raw_item < 0) {
-            rc = vg::enqueue_piece(ix, f.slot, (const char*)ctx->ring[(size_t)f.slot].h_pin, f.len);
+            rc = enqueue(f.slot, f.len);
             if (rc == VG_OK) inflight.push_back(f.slot);
         } else if (f.slot >= 0) {
             raw_ready[f.raw_item] = f;
@@ -619,13 +649,13 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
                     if (!skip && g.bad_at != ~0ull) rf.bad_from = g.bad_at;
                     if (!skip) {
                         strip_bases += g.bases;
-                        if (g.bad_at == ~0ull) ix->fastq_blocks += 1;
+                        if (g.bad_at == ~0ull) sinks.index(g.slot)->fastq_blocks += 1;
                     }
                     if (skip || g.len == 0) {
                         fd.give_free(g.slot);
                         continue;
                     }
-                    rc = vg::enqueue_piece(ix, g.slot, (const char*)ctx->ring[(size_t)g.slot].h_pin, g.len);
+                    rc = enqueue(g.slot, g.len);
                     if (rc == VG_OK) inflight.push_back(g.slot);
                     continue;
                 }
@@ -633,7 +663,7 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
                     fd.give_free(g.slot);
                     continue;
                 }
-                rc = vg::enqueue_raw_piece(ix, g.slot, g.len, d_files + item.file, item.block);
+                rc = vg::enqueue_raw_piece(sinks.ix[0], g.slot, g.len, d_files + item.file, item.block);  // device road: one GPU
                 if (rc == VG_OK) inflight.push_back(g.slot);
             }
         }
@@ -655,8 +685,12 @@ int run_feeder(vg_index* ix, const std::vector<KseqItem>& kseqs, std::vector<Raw
 
 }  // namespace
 
-int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
+// ixs: one index per GPU, all of them counting; the chunks of the files are dealt to them as they come.
+static int count_files_multi(const std::vector<vg_index*>& ixs, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
+    Sinks sinks{ixs};
+    vg_index* ix = ixs[0];
     vg_ctx* ctx = ix->ctx;
+    const bool multi = ixs.size() > 1;
     if (threads < 1) threads = 1;
     std::vector<KseqItem> kseqs;
     std::vector<RawFile> raws;
@@ -670,7 +704,7 @@ int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int thre
         }
     };
     for (int i = 0; i < npaths; ++i) {
-        if (!plan_file(paths[i], ctx, raws, items, kseqs)) {
+        if (!plan_file(paths[i], ctx, multi, raws, items, kseqs)) {
             close_all();
             return vg::fail(VG_E_IO, "'%s': No such file or directory.", paths[i]);
         }
@@ -686,13 +720,9 @@ int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int thre
             return vg::fail(VG_E_NOMEM, "FASTQ file states: %s", cudaGetErrorString(e));
         }
     }
-    int rc = run_feeder(ix, kseqs, raws, items, d_files, threads, read_bases);
-    if (rc == VG_OK && strip) {  // the pinned chunks must have left the host before the mappings go (they are copies: safe)
-        cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
-        if (e != cudaSuccess) rc = vg::fail(VG_E_CUDA, "vg_count_files: %s", cudaGetErrorString(e));
-    }
+    int rc = run_feeder(sinks, kseqs, raws, items, d_files, threads, read_bases);
     close_all();
-    // What the device refused (from the first block that is not plain four-line FASTQ on) and what could
+    // What was refused (from the first record / block that is not plain four-line FASTQ on) and what could
     // not be cut into blocks goes through the kseq reader now.
     std::vector<KseqItem> again;
     if (rc == VG_OK && strip) {
@@ -715,8 +745,12 @@ int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int thre
     }
     cudaFree(d_files);
     std::vector<RawFile> none;
-    if (rc == VG_OK && !again.empty()) rc = run_feeder(ix, again, none, {}, nullptr, threads, read_bases);
+    if (rc == VG_OK && !again.empty()) rc = run_feeder(sinks, again, none, {}, nullptr, threads, read_bases);
     return rc;
+}
+
+int vg::count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
+    return count_files_multi({ix}, paths, npaths, threads, read_bases);
 }
 
 extern "C" uint64_t vg_index_fastq_blocks(const vg_index* ix) { return ix ? ix->fastq_blocks : 0; }
@@ -745,6 +779,27 @@ extern "C" int64_t vg_fastq_strip_block(const char* text, uint64_t nbytes, int l
     if (bases) *bases = b;
     if (bad_at) *bad_at = bad ? (int64_t)(bad - text) : -1;
     return (int64_t)w;
+}
+
+extern "C" int vg_count_files_multi(vg_index* const* ixs, int nix, const char* const* paths, int npaths, int threads,
+                                    uint64_t* read_bases) {
+    if (!ixs || nix <= 0 || !paths || npaths <= 0) return vg::fail(VG_E_INVALID, "Parameter error: -f");
+    std::vector<vg_index*> v;
+    for (int i = 0; i < nix; ++i) {
+        if (!ixs[i]) return vg::fail(VG_E_INVALID, "vg_count_files_multi: ixs[%d] is NULL", i);
+        if (!ixs[i]->counting) return vg::fail(VG_E_STATE, "vg_count_files_multi before vg_count_begin (index %d)", i);
+        if (ixs[i]->sharded) return vg::fail(VG_E_STATE, "vg_count_files_multi is for replicas of an index, one per GPU");
+        if (ixs[i]->ctx->chunk_bytes != ixs[0]->ctx->chunk_bytes) return vg::fail(VG_E_INVALID, "vg_count_files_multi: contexts with different --buffer");
+        for (int j = 0; j < i; ++j)
+            if (ixs[j]->ctx == ixs[i]->ctx) return vg::fail(VG_E_INVALID, "vg_count_files_multi: one context listed twice");
+        v.push_back(ixs[i]);
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(v[0]->ctx->device);
+    int rc = count_files_multi(v, paths, npaths, threads, read_bases);
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
 }
 
 extern "C" int vg_count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {

@@ -18,10 +18,10 @@ static const char* kVersion = "1.0.8-b200";
 
 static void usage(const char* prog) {
     cerr << "Usage: " << prog << " construct -r FILE -v FILE [--save-graph FILE] [--vcf-ploidy INT] [-k INT] [--fast]\n"
-         << "                 [--use-unique-kmers] [--gpu INT] [--buffer MB] [-D] [-t INT]\n"
+         << "                 [--use-unique-kmers] [--gpu INT[,INT...]] [--buffer MB] [-D] [-t INT]\n"
          << "       " << prog << " genotype --load-graph FILE -s FILE [-g hom|het] [--sample-ploidy INT] [-n INT]\n"
          << "                 [--granularity FLOAT] [-m fre|rec] [--sv] [--min-support FLOAT] [--use-depth]\n"
-         << "                 [--gpu INT] [--buffer MB] [-D] [-t INT]\n"
+         << "                 [--gpu INT[,INT...]] [--buffer MB] [-D] [-t INT]\n"
          << "Options and defaults are those of varigraph v1.0.8 (GPU build); k-mer counting runs on a B200.\n";
 }
 
@@ -73,7 +73,22 @@ int main(int argc, char** argv) {
             case OPT_SV: cfg.svGenotypeBool = true; break;
             case OPT_MINSUP: cfg.minSupportingGQ = stof(optarg); break;
             case OPT_DEPTH: cfg.useDepth = true; break;
-            case OPT_GPU: cfg.gpu = stoi(optarg); break;
+            case OPT_GPU: {  // one id (main.cu:141-143) or a list: 0,1,2,3
+                cfg.gpus.clear();
+                string tok;
+                for (const char* q = optarg;; ++q) {
+                    if (*q == ',' || *q == 0) {
+                        if (tok.empty() || tok.find_first_not_of("0123456789") != string::npos) return fail(argv[0], "--gpu");
+                        cfg.gpus.push_back(stoi(tok));
+                        tok.clear();
+                        if (*q == 0) break;
+                    } else {
+                        tok += *q;
+                    }
+                }
+                cfg.gpu = cfg.gpus[0];
+                break;
+            }
             case OPT_BUFFER: cfg.buffer = stoi(optarg); break;
             case 'D': cfg.debug = true; break;
             case 't': cfg.threads = max(stoi(optarg), 1); break;
