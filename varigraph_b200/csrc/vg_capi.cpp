@@ -425,6 +425,12 @@ int vg::enqueue_raw_piece(vg_index* ix, int si, uint64_t len, vg::FastqFileState
     return vg::enqueue_piece(ix, si, nullptr, len, &d_file->bad);
 }
 
+int vg::commit_stripped(vg_index* ix, vg::FastqFileState* d_file, uint64_t bases, bool whole_block) {
+    CU(vg::launch_fastq_strip_commit(d_file, bases, whole_block, ix->ctx->compute_stream));
+    ix->launches += 1;
+    return VG_OK;
+}
+
 // Enqueue one staged piece that already sits in ring slot `si`'s pinned buffer (or at `src`); src == nullptr:
 // the piece is already on the device in ctx->d_masked (and is skipped if *d_skip turns out non-zero).
 int vg::enqueue_piece(vg_index* ix, int si, const char* src, uint64_t len, const unsigned int* d_skip) {

@@ -8,13 +8,15 @@
 // parsing overlap and R1/R2 are read concurrently.
 //
 // Plain (not gzip) four-line FASTQ takes a shorter road, cut into record-aligned blocks that many
-// workers handle at once.  Two variants (VG_FASTQ_ROAD):
-//   strip (default)  the workers scan the memory-mapped file with vector compares (64 bytes per step), check every
+// workers handle at once.  Two ways to take a block, and by default (VG_FASTQ_ROAD=hybrid) both at once, because one
+// is bound by the host cores and the other by PCIe: VG_STRIP_SHARE (default 0.6) of the blocks are stripped, the rest
+// go to the device as raw text, in one submission order, so the pipeline runs at the sum of the two rates.
+//   strip            the workers scan the memory-mapped file with vector compares (64 bytes per step), check every
 //                    record against what kseq reads as a four-line record, and copy only the sequences into the
 //                    pinned chunks: 0.49 bytes cross PCIe per byte of FASTQ, and the page cache is read in place
 //                    (a pread() of the same pages runs at a third of the speed of a scan over the mapping);
-//   device           the workers pread() raw text into the pinned chunks and the GPU finds the lines, checks the
-//                    records and blanks everything but the sequences (fastq_*_kernel in vg_kernels.cu).
+//   device           the workers copy raw text from the mapping into the pinned chunks and the GPU finds the lines, checks
+//                    the records and blanks everything but the sequences (fastq_*_kernel in vg_kernels.cu).
 // Whatever fails the check -- multi-line records, FASTA, a truncated tail, NUL bytes -- is not counted from the
 // offending record (strip) or block (device) on and is re-read with the kseq reader, so the result is the
 // reference's for any input.  VG_FASTQ_ROAD=kseq (or VG_RAW_FASTQ=0) sends every file through the kseq reader.
@@ -174,6 +176,7 @@ struct RawItem {
     uint32_t block;
     uint64_t start, end;
     bool last;  // ends at EOF: make sure the text ends with a newline, as kseq treats EOF
+    bool strip; // stripped to its sequences by a host worker (else: shipped as raw text, parsed on the device)
 };
 
 struct Feeder {
@@ -385,40 +388,9 @@ static uint64_t strip_block(const char* p0, const char* end, bool last, uint8_t*
     return (uint64_t)(st.o - out);
 }
 
-void strip_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
-    for (;;) {
-        int slot = fd->take_free();
-        if (slot < 0) break;
-        const size_t idx = fd->next_raw.fetch_add(1);
-        if (idx >= items->size()) {
-            fd->give_free(slot);
-            break;
-        }
-        const RawItem& it = (*items)[idx];
-        const RawFile& f = (*files)[(size_t)it.file];
-        Filled out{slot, 0, (int64_t)idx};
-        const char* bad = nullptr;
-        const auto t0 = std::chrono::steady_clock::now();
-        out.len = strip_block(f.map + it.start, f.map + it.end, it.last, sinks->slot(slot).h_pin, out.bases, bad);
-        if (bad) out.bad_at = (uint64_t)(bad - f.map);
-        {   // give the block's pages back right away, here, in parallel: tearing down the whole mapping at the end costs
-            // the calling thread ~20 ms per GB (the kseq fallback re-opens the file, it does not need the mapping)
-            const uint64_t page = 4096, a = (it.start + page - 1) & ~(page - 1), b = it.end & ~(page - 1);
-            if (b > a) munmap((void*)(f.map + a), (size_t)(b - a));
-        }
-        fd->busy_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
-        {
-            std::lock_guard<std::mutex> lk(fd->mu);
-            fd->ready_q.push_back(out);
-        }
-        fd->cv_ready.notify_one();
-    }
-    fd->worker_done();
-}
-
 // A slot first, then the next block: the lowest outstanding block always has a buffer, so the in-order
 // submission of the calling thread cannot starve.
-void raw_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
+void block_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* files, const std::vector<RawItem>* items) {
     for (;;) {
         int slot = fd->take_free();
         if (slot < 0) break;
@@ -430,20 +402,28 @@ void raw_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* file
         const RawItem& it = (*items)[idx];
         const RawFile& f = (*files)[(size_t)it.file];
         uint8_t* dst = sinks->slot(slot).h_pin;
-        uint64_t len = it.end - it.start, got = 0;
+        Filled out{slot, 0, (int64_t)idx};
         const auto t0 = std::chrono::steady_clock::now();
-        while (got < len) {
-            ssize_t r = pread(f.fd, dst + got, (size_t)(len - got), (off_t)(it.start + got));
-            if (r <= 0) break;
-            got += (uint64_t)r;
+        if (it.strip) {
+            const char* bad = nullptr;
+            out.len = strip_block(f.map + it.start, f.map + it.end, it.last, dst, out.bases, bad);
+            if (bad) out.bad_at = (uint64_t)(bad - f.map);
+        } else {  // raw text for the device parser (a copy out of the mapping runs at 2.5x the speed of a pread)
+            out.len = it.end - it.start;
+            memcpy(dst, f.map + it.start, (size_t)out.len);
+            if (it.last && out.len && dst[out.len - 1] != '\n') dst[out.len++] = '\n';
         }
-        if (got != len) {
-            fd->set_error(VG_E_IO, "'" + f.path + "': read error");
-            break;
+        {   // give the block's pages back right away, here, in parallel: tearing down the whole mapping at the end costs
+            // the calling thread ~20 ms per GB (the kseq fallback re-opens the file, it does not need the mapping)
+            const uint64_t page = 4096, a = (it.start + page - 1) & ~(page - 1), b = it.end & ~(page - 1);
+            if (b > a) munmap((void*)(f.map + a), (size_t)(b - a));
         }
-        if (it.last && len && dst[len - 1] != '\n') dst[len++] = '\n';
         fd->busy_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
-        fd->push_ready(slot, len, (int64_t)idx);
+        {
+            std::lock_guard<std::mutex> lk(fd->mu);
+            fd->ready_q.push_back(out);
+        }
+        fd->cv_ready.notify_one();
     }
     fd->worker_done();
 }
@@ -476,14 +456,24 @@ int64_t record_boundary(int fd, uint64_t at, uint64_t size, uint64_t window, std
     return -1;
 }
 
-enum Road { kKseq, kDevice, kStrip };
+enum Road { kKseq, kDevice, kStrip, kHybrid };
 Road fastq_road() {
     const char* e = getenv("VG_RAW_FASTQ");
     if (e && atoi(e) == 0) return kKseq;
     const char* r = getenv("VG_FASTQ_ROAD");
     if (r && !strcmp(r, "kseq")) return kKseq;
     if (r && !strcmp(r, "device")) return kDevice;
-    return kStrip;
+    if (r && !strcmp(r, "strip")) return kStrip;
+    return kHybrid;
+}
+// share of a file's blocks the host workers strip (the rest is parsed on the device)
+double strip_share(bool multi) {
+    const Road r = fastq_road();
+    if (multi || r == kStrip) return 1.0;  // several GPUs: host only (the device road's per-file state lives on ONE device)
+    if (r == kDevice) return 0.0;
+    const char* e = getenv("VG_STRIP_SHARE");
+    const double v = e ? atof(e) : 0.6;
+    return v < 0 ? 0 : (v > 1 ? 1 : v);
 }
 bool raw_enabled() { return fastq_road() != kKseq; }
 
@@ -507,7 +497,7 @@ bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& 
     f.path = path;
     f.fd = fd;
     f.size = (uint64_t)st.st_size;
-    if (fastq_road() == kStrip || multi) {  // several GPUs: the host workers strip (the device road parses on ONE device)
+    {
         void* m = mmap(nullptr, (size_t)f.size, PROT_READ, MAP_SHARED, fd, 0);
         if (m == MAP_FAILED) {
             close(fd);
@@ -535,8 +525,11 @@ bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& 
         f.cut.push_back((uint64_t)b);
     }
     const int fi = (int)raws.size();
-    for (size_t b = 0; b + 1 < f.cut.size(); ++b)
-        items.push_back({fi, (uint32_t)b, f.cut[b], f.cut[b + 1], f.cut[b + 1] == f.size});
+    const double share = strip_share(multi);
+    for (size_t b = 0; b + 1 < f.cut.size(); ++b) {
+        const bool strip = (uint64_t)((double)(b + 1) * share) > (uint64_t)((double)b * share);  // evenly spread over the file
+        items.push_back({fi, (uint32_t)b, f.cut[b], f.cut[b + 1], f.cut[b + 1] == f.size, strip});
+    }
     raws.push_back(std::move(f));
     return true;
 }
@@ -546,10 +539,10 @@ bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& 
 int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vector<RawFile>& raws,
                const std::vector<RawItem>& items, vg::FastqFileState* d_files, int threads, uint64_t* read_bases) {
     const int nsink = (int)sinks.ix.size();
-    const bool strip = !raws.empty() && raws[0].map != nullptr;  // one road per call (plan_file decides)
+    bool any_strip = false, any_raw = false;
+    for (const auto& it : items) (it.strip ? any_strip : any_raw) = true;
     int nk = std::min<int>(threads, (int)kseqs.size());
-    // device road: the workers only move bytes, 16 saturate the link; strip road: the scan is the work, take them all
-    int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, strip ? 64 : 16), (int)items.size()));
+    int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, 64), (int)items.size()));
     const int nworkers = nk + nr;
     if (nworkers == 0) return VG_OK;
     const int nslots = std::max(3, (nworkers + 2 + nsink - 1) / nsink + (nsink > 1 ? 1 : 0));
@@ -575,7 +568,7 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
                 sl.busy = false;
             }
         }
-        if (nr && !strip) {
+        if (any_raw) {
             int rc = vg::ctx_ensure_fastq(ctx);
             if (rc) return rc;
         }
@@ -592,14 +585,11 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
     fd.workers_left = nworkers;
     std::vector<std::thread> pool;
     for (int i = 0; i < nk; ++i) pool.emplace_back(kseq_worker, &fd, &sinks, &kseqs);
-    for (int i = 0; i < nr; ++i) {
-        if (strip) pool.emplace_back(strip_worker, &fd, &sinks, &raws, &items);
-        else pool.emplace_back(raw_worker, &fd, &sinks, &raws, &items);
-    }
+    for (int i = 0; i < nr; ++i) pool.emplace_back(block_worker, &fd, &sinks, &raws, &items);
     uint64_t strip_bases = 0;
-    auto enqueue = [&](int id, uint64_t len) {  // a staged chunk of "sequence\n" records -> its GPU
+    auto enqueue = [&](int id, uint64_t len, const unsigned int* d_skip = nullptr) {  // a staged chunk of "sequence\n" records -> its GPU
         vg::DeviceGuard g(sinks.ctx(id)->device);
-        return vg::enqueue_piece(sinks.index(id), id % kSlotsPerSink, (const char*)sinks.slot(id).h_pin, len);
+        return vg::enqueue_piece(sinks.index(id), id % kSlotsPerSink, (const char*)sinks.slot(id).h_pin, len, d_skip);
     };
 
     std::deque<int> inflight;
@@ -643,23 +633,29 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
                 const Filled g = it->second;
                 raw_ready.erase(it);
                 ++next_raw_submit;
-                if (strip) {  // in file order: nothing behind a file's first irregular record is ever submitted
-                    RawFile& rf = raws[(size_t)item.file];
-                    const bool skip = rf.bad_from != ~0ull;
+                // in file order: nothing behind the first irregular record a HOST worker found is ever submitted; what a
+                // DEVICE check refuses raises the file's flag on the device, and everything submitted after it -- raw block
+                // or stripped chunk -- is skipped there (stream order), bases included
+                RawFile& rf = raws[(size_t)item.file];
+                const bool skip = rf.bad_from != ~0ull;
+                if (item.strip) {
                     if (!skip && g.bad_at != ~0ull) rf.bad_from = g.bad_at;
-                    if (!skip) {
+                    if (!skip && !d_files) {  // host-only bookkeeping (no device road in this call)
                         strip_bases += g.bases;
                         if (g.bad_at == ~0ull) sinks.index(g.slot)->fastq_blocks += 1;
                     }
-                    if (skip || g.len == 0) {
+                    if (skip || (g.len == 0 && g.bases == 0)) {
                         fd.give_free(g.slot);
                         continue;
                     }
-                    rc = enqueue(g.slot, g.len);
-                    if (rc == VG_OK) inflight.push_back(g.slot);
+                    vg::FastqFileState* df = d_files ? d_files + item.file : nullptr;
+                    if (g.len) rc = enqueue(g.slot, g.len, df ? &df->bad : nullptr);
+                    if (rc == VG_OK && df) rc = vg::commit_stripped(sinks.ix[0], df, g.bases, g.bad_at == ~0ull);
+                    if (rc == VG_OK && g.len) inflight.push_back(g.slot);
+                    else fd.give_free(g.slot);
                     continue;
                 }
-                if (g.len == 0) {
+                if (skip || g.len == 0) {
                     fd.give_free(g.slot);
                     continue;
                 }
@@ -676,7 +672,7 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
     for (auto& t : pool) t.join();
     if (getenv("VG_FEEDER_DEBUG"))
         fprintf(stderr, "[vg_feeder] %d kseq + %d block workers (%s road), %zu blocks, workers busy %.1f ms in total, wall %.1f ms\n", nk, nr,
-                strip ? "strip" : "device", items.size(), fd.busy_ns.load() * 1e-6,
+                any_strip && any_raw ? "strip + device" : (any_strip ? "strip" : "device"), items.size(), fd.busy_ns.load() * 1e-6,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (read_bases) *read_bases += fd.read_bases.load() + strip_bases;
     if (fd.err != VG_OK) return vg::fail(fd.err, "%s", fd.err_msg.c_str());
@@ -709,9 +705,10 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
             return vg::fail(VG_E_IO, "'%s': No such file or directory.", paths[i]);
         }
     }
-    const bool strip = !raws.empty() && raws[0].map != nullptr;
+    bool any_raw = false;
+    for (const auto& it : items) any_raw |= !it.strip;
     vg::FastqFileState* d_files = nullptr;
-    if (!raws.empty() && !strip) {
+    if (any_raw) {  // per-file state on the device: the raw blocks' verdicts, and the bases of what was counted
         cudaError_t e = cudaMalloc((void**)&d_files, raws.size() * sizeof(vg::FastqFileState));
         if (e == cudaSuccess) e = cudaMemsetAsync(d_files, 0, raws.size() * sizeof(vg::FastqFileState), ctx->compute_stream);
         if (e != cudaSuccess) {
@@ -725,12 +722,12 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
     // What was refused (from the first record / block that is not plain four-line FASTQ on) and what could
     // not be cut into blocks goes through the kseq reader now.
     std::vector<KseqItem> again;
-    if (rc == VG_OK && strip) {
+    if (rc == VG_OK && !d_files) {
         for (auto& f : raws) {
             const uint64_t from = std::min(f.tail_from, f.bad_from);
             if (from != ~0ull && from < f.size) again.push_back({f.path, from});
         }
-    } else if (rc == VG_OK && !raws.empty()) {
+    } else if (rc == VG_OK) {
         std::vector<vg::FastqFileState> st(raws.size());
         cudaError_t e = cudaStreamSynchronize(ctx->compute_stream);
         if (e == cudaSuccess) e = cudaMemcpy(st.data(), d_files, st.size() * sizeof(vg::FastqFileState), cudaMemcpyDeviceToHost);
@@ -738,8 +735,8 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
         for (size_t i = 0; rc == VG_OK && i < raws.size(); ++i) {
             if (read_bases) *read_bases += st[i].read_bases;
             ix->fastq_blocks += st[i].blocks_ok;
-            uint64_t from = raws[i].tail_from;
-            if (st[i].bad) from = raws[i].cut[st[i].first_bad_block];
+            uint64_t from = std::min(raws[i].tail_from, raws[i].bad_from);  // what the host found ...
+            if (st[i].bad) from = std::min(from, raws[i].cut[st[i].first_bad_block]);  // ... and what the device refused
             if (from != ~0ull && from < raws[i].size) again.push_back({raws[i].path, from});
         }
     }

@@ -174,6 +174,7 @@ int sharded_end(vg_index* ix, uint8_t* c_out);        // vg_comm.cpp: extract ow
 int enqueue_piece(vg_index* ix, int slot, const char* src, uint64_t len, const unsigned int* d_skip = nullptr);
 // raw four-line FASTQ text in ring slot `slot`'s pinned buffer: copy, parse and check on the device, count
 int enqueue_raw_piece(vg_index* ix, int slot, uint64_t len, FastqFileState* d_file, uint32_t block_no);
+int commit_stripped(vg_index* ix, FastqFileState* d_file, uint64_t bases, bool whole_block);
 int ctx_ensure_fastq(vg_ctx* c);
 int count_files(vg_index* ix, const char* const* paths, int npaths, int threads, uint64_t* read_bases);
 }  // namespace vg

@@ -110,6 +110,9 @@ struct FastqScratch {
 cudaError_t launch_fastq_block(const uint8_t* d_raw, uint32_t len, uint8_t* d_masked, const FastqScratch& sc,
                                FastqFileState* d_file, uint32_t block_no, cudaStream_t s);
 
+// the bookkeeping of a chunk the host stripped: file->read_bases += bases (and blocks_ok) unless the file is already bad
+cudaError_t launch_fastq_strip_commit(FastqFileState* d_file, unsigned long long bases, bool whole_block, cudaStream_t s);
+
 struct CbfView {
     uint8_t* cells;                 // m saturating u8 counters
     uint64_t m;

@@ -1424,6 +1424,14 @@ __global__ void fastq_commit_kernel(const FastqBlockState* blk, FastqFileState* 
     }
 }
 
+// A chunk a HOST worker stripped (hybrid road): its bases count only while no earlier block of the file was refused
+// on the device -- the chunk's own count kernel was skipped by the same flag (Chunk::skip), in the same stream order.
+__global__ void fastq_strip_commit_kernel(FastqFileState* file, unsigned long long bases, unsigned int whole_block) {
+    if (file->bad) return;
+    file->read_bases += bases;
+    file->blocks_ok += whole_block;
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -1795,6 +1803,11 @@ cudaError_t launch_fastq_block(const uint8_t* d_raw, uint32_t len, uint8_t* d_ma
     const uint32_t lines_cap = len < sc.max_lines ? len : sc.max_lines;
     fastq_validate_kernel<<<(lines_cap + 255) / 256, 256, 0, s>>>(d_raw, sc.nlpos, sc.max_lines, sc.blk);
     fastq_commit_kernel<<<1, 1, 0, s>>>(sc.blk, d_file, block_no);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fastq_strip_commit(FastqFileState* d_file, unsigned long long bases, bool whole_block, cudaStream_t s) {
+    fastq_strip_commit_kernel<<<1, 1, 0, s>>>(d_file, bases, whole_block ? 1u : 0u);
     return cudaGetLastError();
 }
 

@@ -62,6 +62,9 @@ public:
         auto& dev = vgb200::DeviceGraphIndex::get(graphMap, kmerLen_, buffer_);
         ensure_flags(dev);
         const size_t G = dev.ngpus(), S = sampleConfigTupleVec_.size();
+        if (G > 1)
+            cerr << "[" << __func__ << "::" << getTime() << "] " << S << " sample(s), " << G << " GPUs: "
+                 << (S >= G ? "the samples are dealt over the GPUs" : "every sample's reads are spread over all GPUs") << endl << endl;
         if (G > 1 && S >= G) {
             struct Result {
                 vector<uint8_t> c;
