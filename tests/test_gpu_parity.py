@@ -766,8 +766,9 @@ def test_genotype_on_two_gpus_from_the_host_binary(tmp_path, monkeypatch, nsampl
         log = _run([exe, "genotype", "--load-graph", str(tmp_path / "graph.bin"), "-s", str(tmp_path / "samples.cfg"), "-t", "4"] + extra,
                    cwd=str(d))
         if name == "gpu":
-            assert "replicas on 1 more" in log and "too small" not in log, log[-3000:]
-            assert ("counted on GPU" in log) == (nsamples >= 2), log[-3000:]
+            said = "\n".join(ln for ln in log.splitlines() if "GPU" in ln or "replica" in ln)
+            assert "replicas on 1 more" in log and "too small" not in log, said
+            assert ("counted on GPU" in log) == (nsamples >= 2), said
         for i in range(nsamples):
             with gzip.open(d / f"S{i}.varigraph.vcf.gz", "rb") as f:
                 out[name, i] = f.read()

@@ -262,6 +262,20 @@ __device__ __forceinline__ uint32_t encode_word(const Chunk& c, const Src& src, 
     return v;
 }
 
+// The same for a word that lies wholly inside the chunk, without the table where it is not needed: the code of A C G T
+// (either case) is ((b >> 1) ^ (b >> 2)) & 3, done on the four bytes at once; a byte permute turns the codes back into
+// the letters they stand for, and a word that equals that (case folded) holds four valid bases.  Any other word -- it
+// holds an N, a newline, a U, one of the bytes 0-3 the reference's table also accepts, ... -- takes the table.
+// 13 instructions per word instead of ~50 (text is almost all ACGT).
+__device__ __forceinline__ uint32_t encode_word_in_range(uint32_t w, const uint8_t* lut) {
+    const uint32_t t = ((w >> 1) ^ (w >> 2)) & 0x03030303u;        // code of byte i in bits 8i, 8i+1
+    const uint32_t u = (t | (t >> 4)) & 0x00330033u;               // codes of bytes 0,1 in nibbles 0,1; of bytes 2,3 in nibbles 4,5
+    const uint32_t letters = __byte_perm(0x54474341u, 0u, __byte_perm(u, 0u, 0x4420));  // selector nibble i = code of byte i
+    if (((w & 0xDFDFDFDFu) ^ letters) == 0u) return ((t * 0x40100401u) >> 24) | 0xf00u;
+    const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
+    return (uint32_t)w4[w & 0xffu] | w4[256 + ((w >> 8) & 0xffu)] | w4[512 + ((w >> 16) & 0xffu)] | w4[768 + (w >> 24)];
+}
+
 // Encode one 16-byte segment to (2-bit packed, first base in the top bits; validity mask, first
 // base in bit 15).  Out-of-range bytes are invalid.
 template <class Src>
@@ -272,12 +286,16 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, const Src& src, int64
     if (off + kSegBytes <= c.lo || off >= c.hi || off < 0) return;
     uint4 w = src.ld16(off);
     uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-    const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#ifdef VG_LUT_ENCODER
         const uint32_t t = ws[i];
+        const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
         const uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] |
                            w4[768 + (t >> 24)];
+#else
+        const uint32_t v = encode_word_in_range(ws[i], lut);
+#endif
         packed = (packed << 8) | (v & 0xffu);
         vmask = (vmask << 4) | (v >> 8);
     }
@@ -296,7 +314,14 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, const Src& src, int64
 // from its two left neighbours by shuffle (lanes 0/1 re-read them from memory).
 // Warp-cooperative set-up, then per-lane rolling a few positions at a time so that only one probe
 // batch of keys is live at once (the sector loads in flight per lane are the register budget).
-struct OddEncoder {
+// reverse complement of 16 bases held in a word (first base in the top bits)
+__device__ __forceinline__ uint32_t revcomp16(uint32_t x) {
+    const uint32_t y = __brev(~x);
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
+#ifdef VG_ROLLING_ENCODER
+struct OddEncoder {  // rolling registers (A/B build: -DVG_ROLLING_ENCODER)
     uint64_t fwd, rev;
     uint32_t p0;     // own 16 bases, 2 bits each, first base in the top bits
     uint32_t all_k;  // bit (15 - j): the k bytes ending at own position j are all valid
@@ -385,6 +410,103 @@ struct OddEncoder {
         return emit;
     }
 };
+
+#else
+// Window extraction instead of rolling registers: the lane's 48 bases in view are three words (p2 p1 p0), the k-mer
+// that ends at own position j is a 2k-bit window of them -- two funnel shifts and a mask -- and its reverse complement
+// is the mirrored window of the reverse-complemented words (computed once per segment, pre-shifted by the part of
+// the offset that depends on k).  Every position is independent of the others: no serial chain through fwd / rev,
+// and roughly half the instructions of the rolling update.
+struct OddEncoder {
+    uint32_t p0, p1, p2;  // own 16 bases and the 32 in front of them, 2 bits each, first base in the top bits
+    uint32_t l0, l1, l2;  // revcomp(p2 p1 p0) >> (66 - 2k): the window of position j starts at bit 2j
+    uint32_t all_k;       // bit (15 - j): the k bytes ending at own position j are all valid
+    uint32_t pos;         // own positions consumed so far
+
+    __device__ __forceinline__ void init(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        init(c, GlobalText{c.al}, off, kp, lut);
+    }
+    template <class Src>
+    __device__ __forceinline__ void init(const Chunk& c, const Src& src, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        const int lane = threadIdx.x & 31;
+        uint32_t v0;
+        encode_seg(c, src, off, lut, p0, v0);
+        // The 32 bases in front of the warp's text (what lanes 0 and 1 lack a left neighbour for): lanes 0-7 encode one
+        // 32-bit word each and everybody collects the eight results -- a few dozen instructions, where two lanes
+        // running the whole 16-byte encoder would cost every warp two full segments' worth of issue slots.
+        uint32_t wv = 0;
+        if (lane < 8) wv = encode_word(c, src, off - 16 * lane - 32 + 4 * lane, lut);
+        uint32_t x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = __shfl_sync(kFullMask, wv, q);
+        // segment (warp_off - 32) from words 0-3, segment (warp_off - 16) from words 4-7
+        const uint32_t ex0 = ((x[0] & 0xffu) << 24) | ((x[1] & 0xffu) << 16) | ((x[2] & 0xffu) << 8) | (x[3] & 0xffu);
+        const uint32_t exv0 = ((x[0] >> 8) << 12) | ((x[1] >> 8) << 8) | ((x[2] >> 8) << 4) | (x[3] >> 8);
+        const uint32_t ex1 = ((x[4] & 0xffu) << 24) | ((x[5] & 0xffu) << 16) | ((x[6] & 0xffu) << 8) | (x[7] & 0xffu);
+        const uint32_t exv1 = ((x[4] >> 8) << 12) | ((x[5] >> 8) << 8) | ((x[6] >> 8) << 4) | (x[7] >> 8);
+        uint32_t v1 = __shfl_up_sync(kFullMask, v0, 1), v2 = __shfl_up_sync(kFullMask, v0, 2);
+        p1 = __shfl_up_sync(kFullMask, p0, 1);
+        p2 = __shfl_up_sync(kFullMask, p0, 2);
+        if (lane == 0) { p1 = ex1; v1 = exv1; p2 = ex0; v2 = exv0; }
+        if (lane == 1) { p2 = ex1; v2 = exv1; }
+        // V: validity of the 48 bases in view, first base in bit 47.  f(n)[i] = bits i..i+n-1 all
+        // set = "the n bytes ending at the base of bit i are valid"; f(a+b) = f(a) & (f(b) >> a),
+        // so f(k) falls out of the binary decomposition of k.
+        const uint64_t V = ((uint64_t)v2 << 32) | ((uint64_t)v1 << 16) | v0;
+        uint64_t pw = V, acc = ~0ULL;
+        uint32_t have = 0;
+#pragma unroll
+        for (int bit = 0; bit < 5; ++bit) {
+            if (kp.k & (1u << bit)) {
+                acc &= pw >> have;
+                have += 1u << bit;
+            }
+            pw &= pw >> (1u << bit);
+        }
+        all_k = (uint32_t)acc & 0xffffu;
+        // reverse complement of the 96 bits in view, top word first: rc(p0) rc(p1) rc(p2); shifted right by 66 - 2k
+        const uint32_t rt = revcomp16(p0), rm = revcomp16(p1), rb = revcomp16(p2);
+        const uint32_t base = 66u - 2u * kp.k;  // 10 .. 64 for k = 28 .. 1 (uniform)
+        if (base < 32u) {
+            l0 = __funnelshift_r(rb, rm, base);
+            l1 = __funnelshift_r(rm, rt, base);
+            l2 = rt >> base;
+        } else if (base < 64u) {
+            l0 = __funnelshift_r(rm, rt, base - 32u);
+            l1 = rt >> (base - 32u);
+            l2 = 0;
+        } else {
+            l0 = rt;
+            l1 = l2 = 0;
+        }
+        pos = 0;
+    }
+
+    // Consumes the next N own positions: keys[j] = the canonical k-mer ending there (kHashed: its
+    // hash64, i.e. the reference's key >> 8); returns the N-bit emit mask (bit j: the reference encoder
+    // emits; keys[j] is meaningless where it does not).  With kPairs, pairs[q] = the pre-filter entry that
+    // speaks for positions q * kSpan ... (q + 1) * kSpan - 1 (see shared_smer).
+    template <int N, bool kHashed = true, bool kPairs = false, int kSpan = 4>
+    __device__ __forceinline__ uint32_t next(const KmerParams& kp, uint64_t (&keys)[N], uint64_t* pairs = nullptr) {
+        const uint32_t mask_lo = (uint32_t)kp.mask, mask_hi = (uint32_t)(kp.mask >> 32);
+        uint32_t emit = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const uint32_t q = pos + j;        // own position 0..15 (a constant wherever the caller's loop is unrolled)
+            const uint32_t sf = 30u - 2u * q;  // the forward window ends 2(15 - q) bits above the bottom of p0
+            const uint32_t sr = 2u * q;
+            const uint64_t fwd = ((uint64_t)(__funnelshift_r(p1, p2, sf) & mask_hi) << 32) | (__funnelshift_r(p0, p1, sf) & mask_lo);
+            const uint64_t rev = ((uint64_t)(__funnelshift_r(l1, l2, sr) & mask_hi) << 32) | (__funnelshift_r(l0, l1, sr) & mask_lo);
+            const uint64_t canon = fwd < rev ? fwd : rev;
+            keys[j] = kHashed ? hash64(canon, kp.mask) : canon;
+            if (kPairs && j % kSpan == 0) pairs[j / kSpan] = shared_smer<kSpan>(fwd, rev, kp.mask);
+            emit |= ((all_k >> (15u - q)) & 1u) << j;
+        }
+        pos += N;
+        return emit;
+    }
+};
+#endif
 
 // Whole segment at once (used where register pressure does not matter).
 __device__ __forceinline__ uint32_t encode_keys_odd(const Chunk& c, int64_t off, const KmerParams& kp,

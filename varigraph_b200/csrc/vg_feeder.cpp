@@ -192,10 +192,15 @@ struct Feeder {
     std::atomic<size_t> next_raw{0};
     std::atomic<uint64_t> read_bases{0};
     std::atomic<uint64_t> busy_ns{0};   // time the block workers spent working (VG_FEEDER_DEBUG)
+    std::atomic<uint64_t> wait_ns{0};   // ... and waiting for a free staging slot
 
     int take_free() {
         std::unique_lock<std::mutex> lk(mu);
-        cv_free.wait(lk, [&] { return abort || !free_q.empty(); });
+        if (free_q.empty() && !abort) {
+            const auto t0 = std::chrono::steady_clock::now();
+            cv_free.wait(lk, [&] { return abort || !free_q.empty(); });
+            wait_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+        }
         if (abort) return -1;
         int s = free_q.front();
         free_q.pop_front();
@@ -431,10 +436,28 @@ void block_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* fi
 // First record start at or after `at`: a line that begins with '@' whose next-but-one line begins with '+'.
 // (A quality line may begin with '@' too, but then the line two further on is a sequence, which never
 // begins with '+' in the four-line format the device goes on to verify record by record.)  -1: none in the window.
-int64_t record_boundary(int fd, uint64_t at, uint64_t size, uint64_t window, std::vector<char>& buf) {
+// `text` = the n bytes of the file from offset `from` = at - 1 on
+int64_t record_boundary_in(const char* text, uint64_t n, uint64_t from) {
+    for (uint64_t i = 1; i < n; ++i) {
+        if (text[i - 1] != '\n' || text[i] != '@') continue;
+        const char* e1 = (const char*)memchr(text + i, '\n', (size_t)(n - i));
+        if (!e1) return -1;
+        const uint64_t l2 = (uint64_t)(e1 - text) + 1;
+        const char* e2 = l2 < n ? (const char*)memchr(text + l2, '\n', (size_t)(n - l2)) : nullptr;
+        if (!e2) return -1;
+        const uint64_t l3 = (uint64_t)(e2 - text) + 1;
+        if (l3 >= n) return -1;
+        if (text[l3] == '+') return (int64_t)(from + i);
+    }
+    return -1;
+}
+// map (optional): the file, memory-mapped -- the search then touches the few hundred bytes it needs instead of
+// reading the whole window
+int64_t record_boundary(int fd, const char* map, uint64_t at, uint64_t size, uint64_t window, std::vector<char>& buf) {
     if (at == 0) return 0;
     if (at >= size) return (int64_t)size;
     const uint64_t from = at - 1, n = std::min<uint64_t>(window + 1, size - from);
+    if (map) return record_boundary_in(map + from, n, from);
     buf.resize((size_t)n);
     uint64_t got = 0;
     while (got < n) {
@@ -442,18 +465,7 @@ int64_t record_boundary(int fd, uint64_t at, uint64_t size, uint64_t window, std
         if (r <= 0) return -1;
         got += (uint64_t)r;
     }
-    for (uint64_t i = 1; i < n; ++i) {
-        if (buf[i - 1] != '\n' || buf[i] != '@') continue;
-        const char* e1 = (const char*)memchr(buf.data() + i, '\n', (size_t)(n - i));
-        if (!e1) return -1;
-        const uint64_t l2 = (uint64_t)(e1 - buf.data()) + 1;
-        const char* e2 = l2 < n ? (const char*)memchr(buf.data() + l2, '\n', (size_t)(n - l2)) : nullptr;
-        if (!e2) return -1;
-        const uint64_t l3 = (uint64_t)(e2 - buf.data()) + 1;
-        if (l3 >= n) return -1;
-        if (buf[l3] == '+') return (int64_t)(from + i);
-    }
-    return -1;
+    return record_boundary_in(buf.data(), n, from);
 }
 
 enum Road { kKseq, kDevice, kStrip, kHybrid };
@@ -517,7 +529,7 @@ bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& 
             f.cut.push_back(f.size);
             break;
         }
-        const int64_t b = record_boundary(fd, target, f.size, window, buf);
+        const int64_t b = record_boundary(fd, f.map, target, f.size, window, buf);
         if (b < 0) {  // records longer than the window, or not four-line FASTQ: the host parser takes over here
             f.tail_from = f.cut.back();
             break;
@@ -545,7 +557,9 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
     int nr = items.empty() ? 0 : std::max(1, std::min(std::min(threads - nk, 64), (int)items.size()));
     const int nworkers = nk + nr;
     if (nworkers == 0) return VG_OK;
-    const int nslots = std::max(3, (nworkers + 2 + nsink - 1) / nsink + (nsink > 1 ? 1 : 0));
+    // a slot stays taken from the moment a worker starts filling it until the kernel that read its device twin is done, and
+    // blocks are submitted in file order: two slots per worker keep the workers busy while finished chunks wait their turn
+    const int nslots = std::max(3, (2 * nworkers + 4 + nsink - 1) / nsink);
     // ring slots (pinned + device pairs); allocation is done here on the calling thread
     for (vg_index* ix : sinks.ix) {
         vg_ctx* ctx = ix->ctx;
@@ -671,8 +685,8 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
     }
     for (auto& t : pool) t.join();
     if (getenv("VG_FEEDER_DEBUG"))
-        fprintf(stderr, "[vg_feeder] %d kseq + %d block workers (%s road), %zu blocks, workers busy %.1f ms in total, wall %.1f ms\n", nk, nr,
-                any_strip && any_raw ? "strip + device" : (any_strip ? "strip" : "device"), items.size(), fd.busy_ns.load() * 1e-6,
+        fprintf(stderr, "[vg_feeder] %d kseq + %d block workers (%s road), %zu blocks, workers busy %.1f ms / waiting for slots %.1f ms in total, wall %.1f ms\n", nk, nr,
+                any_strip && any_raw ? "strip + device" : (any_strip ? "strip" : "device"), items.size(), fd.busy_ns.load() * 1e-6, fd.wait_ns.load() * 1e-6,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (read_bases) *read_bases += fd.read_bases.load() + strip_bases;
     if (fd.err != VG_OK) return vg::fail(fd.err, "%s", fd.err_msg.c_str());
@@ -684,6 +698,7 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
 // ixs: one index per GPU, all of them counting; the chunks of the files are dealt to them as they come.
 static int count_files_multi(const std::vector<vg_index*>& ixs, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
     Sinks sinks{ixs};
+    const auto t_plan = std::chrono::steady_clock::now();
     vg_index* ix = ixs[0];
     vg_ctx* ctx = ix->ctx;
     const bool multi = ixs.size() > 1;
@@ -707,6 +722,9 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
     }
     bool any_raw = false;
     for (const auto& it : items) any_raw |= !it.strip;
+    if (getenv("VG_FEEDER_DEBUG"))
+        fprintf(stderr, "[vg_feeder] %d file(s) planned in %.1f ms\n", npaths,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
     vg::FastqFileState* d_files = nullptr;
     if (any_raw) {  // per-file state on the device: the raw blocks' verdicts, and the bases of what was counted
         cudaError_t e = cudaMalloc((void**)&d_files, raws.size() * sizeof(vg::FastqFileState));
@@ -761,7 +779,7 @@ extern "C" int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint6
     int64_t r = -2;
     if (fstat(fd, &st) == 0) {
         std::vector<char> buf;
-        r = record_boundary(fd, at, (uint64_t)st.st_size, window, buf);
+        r = record_boundary(fd, nullptr, at, (uint64_t)st.st_size, window, buf);
     }
     close(fd);
     return r;
