@@ -757,7 +757,7 @@ def test_genotype_on_two_gpus_from_the_host_binary(tmp_path, monkeypatch, nsampl
         cfg.append(f"S{i} {a} {b}")
     (tmp_path / "samples.cfg").write_text("\n".join(cfg) + "\n")
     gpus, env = _gpu_list()
-    for k, v in {"VG_PARTITION": "1", "VG_SLICE_BYTES": "262144", **env}.items():  # a 2.8 MB table, driven through the sweep
+    for k, v in {"VG_PARTITION": "1", "VG_SLICE_BYTES": "16384", **env}.items():  # a 170 KB table, driven through the sweep
         monkeypatch.setenv(k, v)
     out = {}
     for name, exe, extra in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", gpus, "--buffer", "1"])):
@@ -775,6 +775,62 @@ def test_genotype_on_two_gpus_from_the_host_binary(tmp_path, monkeypatch, nsampl
     assert out["gpu", 0] == out["cpu", 0] == t["vcf"]
     for i in range(1, nsamples):
         assert out["gpu", i] == out["cpu", i]
+
+
+def _graph_and_samples(tmp_path, ref_bin, genome_len, nvar, nsamples, ploidy, coverage, reads_for, seed, construct_extra=()):
+    """Synthetic genome + VCF -> `varigraph_ref construct` -> graph.bin, plus PE150 FASTQ pairs drawn from the
+    haplotypes of the listed samples; returns (graph path, samples.cfg path)."""
+    g = synth.make_genome(genome_len, seed)
+    v = synth.make_variants(g, nvar, nsamples, ploidy, seed + 1)
+    fa, vcf, graph = str(tmp_path / "ref.fa"), str(tmp_path / "var.vcf"), str(tmp_path / "graph.bin")
+    synth.write_fasta(fa, g)
+    synth.write_vcf(vcf, v, len(g))
+    _run([ref_bin, "construct", "-r", fa, "-v", vcf, "--save-graph", graph, "-t", "8", *construct_extra], cwd=str(tmp_path))
+    cfg = []
+    for smp in reads_for:
+        haps = [synth.apply_haplotype(g, v, smp, h) for h in range(ploidy)]
+        m1, m2 = synth.make_reads(haps, coverage, len(g), seed=seed + 10 + smp)
+        f1, f2 = str(tmp_path / f"S{smp}_1.fq"), str(tmp_path / f"S{smp}_2.fq")
+        synth.write_fastq(f1, m1, "a")
+        synth.write_fastq(f2, m2, "b")
+        cfg.append(f"S{smp} {f1} {f2}")
+    (tmp_path / "samples.cfg").write_text("\n".join(cfg) + "\n")
+    return graph, str(tmp_path / "samples.cfg")
+
+
+def _genotype_both(tmp_path, ref_bin, b200, graph, cfg, samples, extra=()):
+    out = {}
+    for name, exe, more in (("cpu", ref_bin, []), ("gpu", b200, ["--gpu", "0", "--buffer", "4"])):
+        d = tmp_path / name
+        d.mkdir()
+        _run([exe, "genotype", "--load-graph", graph, "-s", cfg, "-t", "8", *extra, *more], cwd=str(d))
+        for smp in samples:
+            with gzip.open(d / f"S{smp}.varigraph.vcf.gz", "rb") as f:
+                out[name, smp] = f.read()
+    return out
+
+
+def test_baseline_config1_full_size_identical_vcf(tmp_path):
+    """BASELINE configs[0] at its stated size: 1 Mb reference, 2 000 SNP / indel variants, 30x PE150, default k --
+    graph built by the reference, genotyped by the reference CPU path and by the drop-in on the GPU: identical VCFs."""
+    ref_bin, b200 = _integrated()
+    graph, cfg = _graph_and_samples(tmp_path, ref_bin, 1_000_000, 2000, 5, 2, 30.0, reads_for=[0], seed=41)
+    out = _genotype_both(tmp_path, ref_bin, b200, graph, cfg, [0])
+    assert out["gpu", 0] == out["cpu", 0] and out["cpu", 0].count(b"\n") > 2000
+
+
+def test_baseline_config4_tetraploid_use_depth_identical_vcf(tmp_path):
+    """BASELINE configs[3] in miniature: a tetraploid population graph (--vcf-ploidy 4), three samples genotyped with
+    --sample-ploidy 4 --use-depth at 40x -- the ploidy loop and the useDepth_ branch of the coverage model
+    (src/varigraph.cpp:220-296) sit between our counts and the VCF.  13 haplotypes <= -n 15 keeps the reference
+    deterministic."""
+    ref_bin, b200 = _integrated()
+    graph, cfg = _graph_and_samples(tmp_path, ref_bin, 150_000, 300, 3, 4, 40.0, reads_for=[0, 1, 2], seed=53,
+                                    construct_extra=("--vcf-ploidy", "4"))
+    out = _genotype_both(tmp_path, ref_bin, b200, graph, cfg, [0, 1, 2], extra=("--sample-ploidy", "4", "--use-depth"))
+    for smp in (0, 1, 2):
+        assert out["gpu", smp] == out["cpu", smp], smp
+    assert out["cpu", 0] != out["cpu", 1]
 
 
 def test_construct_on_gpu_then_identical_genotypes(tmp_path):

@@ -266,7 +266,9 @@ __device__ __forceinline__ uint32_t encode_word(const Chunk& c, const Src& src, 
 // (either case) is ((b >> 1) ^ (b >> 2)) & 3, done on the four bytes at once; a byte permute turns the codes back into
 // the letters they stand for, and a word that equals that (case folded) holds four valid bases.  Any other word -- it
 // holds an N, a newline, a U, one of the bytes 0-3 the reference's table also accepts, ... -- takes the table.
-// 13 instructions per word instead of ~50 (text is almost all ACGT).
+// 13 instructions per word instead of ~50 (text is almost all ACGT) -- and yet SLOWER in the scatter kernel than the
+// table (7.50 vs 7.22 ms on the chr20 workload): the lookups ride on the otherwise idle shared-memory pipe, the extra
+// integer work does not.  Kept for the record as an A/B build (-DVG_ARITH_ENCODER); the table is the default.
 __device__ __forceinline__ uint32_t encode_word_in_range(uint32_t w, const uint8_t* lut) {
     const uint32_t t = ((w >> 1) ^ (w >> 2)) & 0x03030303u;        // code of byte i in bits 8i, 8i+1
     const uint32_t u = (t | (t >> 4)) & 0x00330033u;               // codes of bytes 0,1 in nibbles 0,1; of bytes 2,3 in nibbles 4,5
@@ -288,7 +290,7 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, const Src& src, int64
     uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#ifdef VG_LUT_ENCODER
+#ifndef VG_ARITH_ENCODER
         const uint32_t t = ws[i];
         const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
         const uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] |
