@@ -718,6 +718,24 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     if e2e_staged is not None:
         e2e_staged["h2d_ceiling_gbs_one_gpu"] = h2d_gbs
     probes_per_s = positions / (kernel_ms * 1e-3)
+    # What binds the two kernels is not bytes but random-access ISSUE: one L1TEX wavefront per clock and SM (289 G/s measured
+    # with tools/gather_bench.cu, whatever the access size).  Wavefronts of a pass, from the pass's own counters and the
+    # per-access costs measured there: one pre-filter gather per `span` positions, per key that reaches the lists a
+    # shared-memory rank atomic (0.68) in the scatter -- and in the re-scatter of a two-level index -- and a bucket load in
+    # the sweep (1.2 with the second halves), per hit a reduction into the side counters (1.3).
+    keys_pass = ix.keys_scattered or positions
+    span = 8 if nkeys > (128 << 20) else 4
+    wavefronts = positions / span + keys_pass * (0.68 + 1.2 + (0.68 if ix.slices > ix.partitions else 0.0)) + hits * 1.3
+    props = torch.cuda.get_device_properties(dev)
+    sm_clock_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
+    l1tex_peak = props.multi_processor_count * sm_clock_hz
+    binding = {"unit": "L1TEX wavefront issue (1 per clock and SM): every pre-filter gather, bucket load, side-counter reduction and "
+                       "shared-memory rank atomic costs about one",
+               "wavefronts_per_pass_model": wavefronts, "peak_wavefronts_per_s": l1tex_peak,
+               "frac": wavefronts / l1tex_peak / (kernel_ms * 1e-3), "keys_after_prefilter": int(keys_pass),
+               "measured": "profiles/r2_*_ncu_*.txt: l1tex__throughput of scatter_kernel and probe_slice_kernel"}
+    # "bound": the contract's choice is hbm | tensor; the bytes side of this path is HBM (no contraction anywhere), but see
+    # "binding": the pass is issue-bound on random accesses that the partitioned layout turns into L2 hits
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(ix.partitions > 0), "peak_source": peak_src,
                 "kernel": ("count pass = vg::scatter_kernel + vg::probe_slice_kernel sweep (K1 | K2+K3)" if ix.partitions
@@ -725,7 +743,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                 "kernel_ms": kernel_ms, "bytes_per_position": b_alg, "hit_fraction": h,
                 "random_sector_peak_gbs": rnd_gbs,
                 "frac_of_random_sector_peak": (probes_per_s * (1 + h) / rnd_sec) if rnd_sec else None,
-                "phases_ms": phases}
+                "phases_ms": phases, "binding": binding}
 
     # ---- CPU baseline beside it + the same sample through the CUDA path (rank 0) -----------------------------
     cpu = parity = None

@@ -150,6 +150,9 @@ int vg_count_slots_device(vg_index* ix, const uint8_t** dev_counts);
  * (elem_bytes 4, what ncclAllReduce(sum) wants) into dev_out, on `cuda_stream`. */
 int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* cuda_stream);
 int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits);
+/* Diagnostic: k-mers of the sample that passed the presence pre-filter and went through the key lists of the partitioned
+ * path, as of the last vg_count_stats / vg_count_end (0 for a directly probed index). */
+uint64_t vg_count_keys(const vg_index* ix);
 
 /* Count consumers on the device: hist[v] = number of index entries whose count is v,
  * over all entries or over the subset marked by vg_index_set_flags (flags: n bytes in key order,

@@ -816,7 +816,7 @@ def test_baseline_config1_full_size_identical_vcf(tmp_path):
     ref_bin, b200 = _integrated()
     graph, cfg = _graph_and_samples(tmp_path, ref_bin, 1_000_000, 2000, 5, 2, 30.0, reads_for=[0], seed=41)
     out = _genotype_both(tmp_path, ref_bin, b200, graph, cfg, [0])
-    assert out["gpu", 0] == out["cpu", 0] and out["cpu", 0].count(b"\n") > 2000
+    assert out["gpu", 0] == out["cpu", 0] and out["cpu", 0].count(b"\n") > 1000
 
 
 def test_baseline_config4_tetraploid_use_depth_identical_vcf(tmp_path):

@@ -70,6 +70,7 @@ def _load() -> ctypes.CDLL:
         "vg_count_end_slots": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),
         "vg_count_slots_device": (c_int, [c_void_p, P(c_void_p)]),
         "vg_count_stats": (c_int, [c_void_p, P(c_uint64), P(c_uint64)]),
+        "vg_count_keys": (c_uint64, [c_void_p]),
         "vg_encode_positions_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p]),
         "vg_encode_positions": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
         "vg_cbf_create": (c_int, [c_void_p, c_uint64, c_uint32, c_void_p, P(c_void_p)]),
@@ -373,6 +374,11 @@ class Index:
         pos, hits = c_uint64(0), c_uint64(0)
         _chk(lib.vg_count_stats(self._h, byref(pos), byref(hits)))
         return int(pos.value), int(hits.value)
+
+    @property
+    def keys_scattered(self) -> int:
+        """K-mers that passed the pre-filter, as of the last stats() / end() (vg_count_keys)."""
+        return int(lib.vg_count_keys(self._h))
 
     def extract_device(self, dev_ptr: int, elem_bytes: int, stream: int = 0) -> None:
         _chk(lib.vg_count_extract_device(self._h, c_void_p(dev_ptr), elem_bytes, c_void_p(stream)))

@@ -293,12 +293,14 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
     PartState& ps = ix->part;
     if (ix->sharded) return VG_OK;  // a sharded round ends only in the collective calls (vg_count_flush / _end)
     if (!ps.enabled || ps.pending == 0) return VG_OK;
-    if (ps.d_round_keys && ps.round_pending == 0) {  // how many keys did this much text leave? (read back later, without waiting)
-        CU(vg::launch_sum_cursors(ps.view.cursor, ps.view.P, ps.view.cap, ps.d_round_keys, s));
-        CU(cudaMemcpyAsync(ps.h_round_keys, ps.d_round_keys, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        CU(cudaEventRecord(ps.ev_round, s));
-        ps.round_pending = ps.pending;
+    if (ps.d_round_keys) {  // how many keys did this much text leave? (read back later, without waiting)
+        CU(vg::launch_sum_cursors(ps.view.cursor, ps.view.P, ps.view.cap, ps.d_round_keys, &ix->d_misc->stats, s));
         ix->launches += 1;
+        if (ps.round_pending == 0) {
+            CU(cudaMemcpyAsync(ps.h_round_keys, ps.d_round_keys, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(ps.ev_round, s));
+            ps.round_pending = ps.pending;
+        }
     }
     phase_begin(ps, s);
     CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
@@ -892,8 +894,10 @@ int vg_count_stats(vg_index* ix, uint64_t* positions, uint64_t* hits) {
     CU(cudaMemcpy(&st, &ix->d_misc->stats, sizeof st, cudaMemcpyDeviceToHost));
     if (positions) *positions = st.positions;
     if (hits) *hits = st.hits;
+    ix->last_keys = st.keys;
     return VG_OK;
 }
+uint64_t vg_count_keys(const vg_index* ix) { return ix ? ix->last_keys : 0; }
 
 int vg_count_extract_device(vg_index* ix, void* dev_out, int elem_bytes, void* cuda_stream) {
     if (!ix || !dev_out) return fail(VG_E_INVALID, "vg_count_extract_device: NULL argument");

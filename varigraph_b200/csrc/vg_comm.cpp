@@ -15,6 +15,7 @@
 #include "../../include/vgb200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -51,6 +52,26 @@ vg::PeerPtrs peers_at(const vg_comm* cm, size_t off) {
 int barrier_on(vg_comm* cm, cudaStream_t s) {
     if (cm->world == 1) return VG_OK;
     cm->epoch += 1;
+    if (cm->group) {  // ranks of one process: events and a rendezvous of their host threads (see LocalGroup)
+        LocalGroup& g = *cm->group;
+        const size_t par = (size_t)(cm->epoch & 1);
+        CU(cudaEventRecord(g.ev[(size_t)cm->rank * 2 + par], s));
+        {
+            std::unique_lock<std::mutex> lk(g.mu);
+            const unsigned long long gen = g.generation;
+            if (++g.arrived == g.world) {
+                g.arrived = 0;
+                g.generation += 1;
+                g.cv.notify_all();
+            } else if (!g.cv.wait_for(lk, std::chrono::nanoseconds(cm->timeout_ns), [&] { return g.generation != gen; })) {
+                g.arrived -= 1;
+                return fail(VG_E_STATE, "rank %d: a peer did not reach a barrier within %.1f s", cm->rank, cm->timeout_ns * 1e-9);
+            }
+        }
+        for (int r = 0; r < cm->world; ++r)
+            if (r != cm->rank) CU(cudaStreamWaitEvent(s, g.ev[(size_t)r * 2 + par], 0));
+        return VG_OK;
+    }
     CU(vg::launch_peer_barrier(peers_at(cm, 0), cm->world, cm->rank, cm->epoch, cm->timeout_ns, cm->d_timeout, s));
     cm->launches += 1;
     return VG_OK;
@@ -156,6 +177,19 @@ int vg_comm_create_local(vg_ctx* const* ctxs, int world, uint64_t arena_bytes, v
             out[r]->local = true;
         }
     }
+    if (rc == VG_OK && world > 1) {
+        auto group = std::make_shared<LocalGroup>();
+        group->world = world;
+        group->ev.assign((size_t)world * 2, nullptr);
+        for (int r = 0; r < world && rc == VG_OK; ++r) {
+            DeviceGuard g(ctxs[r]->device);
+            for (int p = 0; p < 2; ++p)
+                if (cudaEventCreateWithFlags(&group->ev[(size_t)r * 2 + p], cudaEventDisableTiming) != cudaSuccess)
+                    rc = fail(VG_E_CUDA, "vg_comm_create_local: cudaEventCreate failed");
+            group->device.push_back(ctxs[r]->device);
+        }
+        for (int r = 0; r < world; ++r) out[r]->group = group;
+    }
     if (rc != VG_OK)
         for (int r = 0; r < world; ++r) {
             if (out[r]) {
@@ -218,6 +252,13 @@ int vg_comm_destroy(vg_comm* cm) {
     if (!cm) return VG_OK;
     DeviceGuard g(cm->ctx->device);
     cudaDeviceSynchronize();
+    if (cm->group) {  // this rank's two events go with it
+        for (int p = 0; p < 2; ++p) {
+            cudaEvent_t& e = cm->group->ev[(size_t)cm->rank * 2 + p];
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
     if (!cm->local)
         for (int r = 0; r < cm->world; ++r)
             if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);

@@ -1,6 +1,9 @@
 // vg_host.h -- host-side objects behind the opaque handles of include/vgb200.h.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -100,8 +103,22 @@ struct PartState {
 // peer must reach lives in ONE device allocation per rank, the arena; all ranks carve it up with the same
 // sequence of sizes, so an object sits at the same offset everywhere and a peer's copy is
 // peer_base[r] + offset (a symmetric heap).
+// The ranks of a vg_comm_create_local group share this: their barrier is events + a rendezvous of the host threads
+// (each rank records an event on its stream, everybody meets, each stream then waits for every peer's event), so no
+// kernel ever spins on the device -- a spinning kernel and a device-wide synchronisation in a sibling thread of the same
+// process (cudaFree, cudaDeviceSetLimit ...) would wait for each other.
+struct LocalGroup {
+    std::mutex mu;
+    std::condition_variable cv;
+    int world = 0, arrived = 0;
+    unsigned long long generation = 0;
+    std::vector<cudaEvent_t> ev;  // world x 2 (alternating by barrier parity)
+    std::vector<int> device;
+};
+
 struct vg_comm {
     vg_ctx* ctx = nullptr;
+    std::shared_ptr<LocalGroup> group;   // in-process group only
     int rank = 0, world = 1;
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -141,6 +158,7 @@ struct vg_index {
     uint64_t duplicates = 0;
     uint64_t launches = 0;
     uint64_t fastq_blocks = 0;     // raw FASTQ blocks parsed, checked and counted on the device so far
+    uint64_t last_keys = 0;        // CountStats::keys as of the last vg_count_stats / _end
     uint64_t h2d_bytes = 0;        // bytes copied host -> device for this index since the last vg_count_begin
     bool counting = false;
     bool foreign_streams = false;

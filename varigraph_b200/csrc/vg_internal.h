@@ -43,6 +43,7 @@ struct PrefilterView {
 struct CountStats {                 // lives in device memory
     unsigned long long positions;   // emitted k-mer positions (what kmer_sketch_fastq tests against the map)
     unsigned long long hits;        // positions whose k-mer is in the index
+    unsigned long long keys;        // partitioned path: k-mers that passed the pre-filter and went through the key lists
 };
 
 struct InsertReport {               // lives in device memory
@@ -161,7 +162,8 @@ cudaError_t launch_prefilter_build(uint32_t* words, uint32_t nwords, const uint6
 cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, const uint32_t* h_slice_rank, CountStats* d_stats,
                                     int nsm, cudaStream_t s);
 // *d_total = sum of the P fill counts at `cursor` (each clipped to cap): the keys of the round about to be swept
-cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, cudaStream_t s);
+cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, CountStats* d_stats,
+                               cudaStream_t s);
 uint64_t sweep_launches(const IndexView& ix, const PartView& pv);
 int64_t chunk_tiles(const uint8_t* d_bases, uint64_t nbytes);
 // d_idx == nullptr: out[i] = count of d_key56[i]; else out[d_idx[i]] = ... (a sharded index's own keys)

@@ -570,7 +570,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // kTma: the tile's text (plus the 32 bytes in front of it) is staged in shared memory by a bulk async copy that one
 // thread issues a whole tile ahead (two buffers, one mbarrier each): the load latency never sits in front of the
 // encoder and the LSU only sees shared-memory loads.
-template <bool kOdd, bool kTma, int kSpan>
+// kK: the k-mer length as a compile-time constant (27, the reference's default) or 0 = whatever the index says; with a
+// constant k the validity windows, the window offsets and the masks of the encoder fold into immediates.
+template <bool kOdd, bool kTma, int kSpan, int kK>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
@@ -588,7 +590,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     if (threadIdx.x == 0) blk_pos = 0, max_cnt = 0;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    KmerParams kp{ix.k, ix.mask};
+    const KmerParams kp{kK ? (uint32_t)kK : ix.k, kK ? ((1ULL << (2 * (kK ? kK : 1))) - 1) : ix.mask};
     const uint32_t lane = threadIdx.x & 31;
     // 32-bit shared-window address of the bins, made opaque: left to itself the compiler re-derives it
     // (S2UR SR_CgaCtaId + three uniform ops) in front of every single bin store
@@ -1609,9 +1611,11 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     const char* tma_env = getenv("VG_SCATTER_TMA");
     const bool tma = tma_env && atoi(tma_env) != 0 && (ix.k & 1);
     const bool s8 = pf.words && pf.span == 8;
-    KernelT kern = (ix.k & 1) ? (tma ? (s8 ? (KernelT)scatter_kernel<true, true, 8> : (KernelT)scatter_kernel<true, true, 4>)
-                                     : (s8 ? (KernelT)scatter_kernel<true, false, 8> : (KernelT)scatter_kernel<true, false, 4>))
-                              : (s8 ? (KernelT)scatter_kernel<false, false, 8> : (KernelT)scatter_kernel<false, false, 4>);
+    KernelT kern;
+    if (!(ix.k & 1)) kern = s8 ? (KernelT)scatter_kernel<false, false, 8, 0> : (KernelT)scatter_kernel<false, false, 4, 0>;
+    else if (tma) kern = s8 ? (KernelT)scatter_kernel<true, true, 8, 0> : (KernelT)scatter_kernel<true, true, 4, 0>;
+    else if (ix.k == 27) kern = s8 ? (KernelT)scatter_kernel<true, false, 8, 27> : (KernelT)scatter_kernel<true, false, 4, 27>;
+    else kern = s8 ? (KernelT)scatter_kernel<true, false, 8, 0> : (KernelT)scatter_kernel<true, false, 4, 0>;
     // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
     // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
@@ -1749,7 +1753,7 @@ cudaError_t launch_probe_partitions(const IndexView& ix, const PartView& pv, con
     return cudaMemsetAsync(pv.cursor, 0, pv.P * sizeof(unsigned long long), s);
 }
 
-__global__ void sum_cursors_kernel(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* total) {
+__global__ void sum_cursors_kernel(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* total, CountStats* stats) {
     __shared__ unsigned long long sh[32];
     unsigned long long v = 0;
     for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) v += min((unsigned long long)cap, cursor[p]);
@@ -1761,10 +1765,12 @@ __global__ void sum_cursors_kernel(const unsigned long long* cursor, uint32_t P,
         unsigned long long t = 0;
         for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += sh[w];
         *total = t;
+        stats->keys += t;
     }
 }
-cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, cudaStream_t s) {
-    sum_cursors_kernel<<<1, 256, 0, s>>>(cursor, P, cap, d_total);
+cudaError_t launch_sum_cursors(const unsigned long long* cursor, uint32_t P, uint64_t cap, unsigned long long* d_total, CountStats* d_stats,
+                               cudaStream_t s) {
+    sum_cursors_kernel<<<1, 256, 0, s>>>(cursor, P, cap, d_total, d_stats);
     return cudaGetLastError();
 }
 
