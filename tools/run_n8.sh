@@ -1,11 +1,12 @@
 #!/bin/bash
-# one bench.py run on N GPUs (gpurun --gpus N -- 'bash tools/run_n8.sh N [bench flags]')
-cd "$GRAFT_REPO_ROOT"
-N=${1:-8}
-shift
-timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 "$@" 2> gpurun_out/n${N}_err.log | tee -a gpurun_out/bench_n$N.jsonl | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('N=%d value %.4g e2e %.4g ms %.2f pass_ms %.2f | %s | eq=%s launches=%s'%(d['n_gpus'],d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['config']['parallelism'],d['e2e']['counts_equal_device_path'],d['gpu_launches']))"
-grep -v "OMP_NUM\|\*\*\*\*" gpurun_out/n${N}_err.log | tail -5 | cut -c1-300
+# the whole box: gpurun --gpus 8 -- 'bash tools/run_n8.sh'
+mkdir -p gpurun_out
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512"
+nvidia-smi topo -m > gpurun_out/n8_topo.txt 2>&1; nproc >> gpurun_out/n8_topo.txt; free -g >> gpurun_out/n8_topo.txt
+# 1. what the driver runs: the chr20 line (weak scaling) + the human-scale section (one 30x sample over the box)
+timeout 900 $T bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/n8_default.json 2> gpurun_out/n8_default.err; echo "rc=$?" >> gpurun_out/n8_default.err
+# 2. one chr20 sample cut over the box
+timeout 600 $T bench.py --gpus 8 --steps 10 --warmup 3 --scaling strong --no-files-e2e --human off > gpurun_out/n8_chr20_strong.json 2> gpurun_out/n8_chr20_strong.err; echo "rc=$?" >> gpurun_out/n8_chr20_strong.err
+# 3. the human-scale index cut over the box (index > HBM layout), one 30x sample
+timeout 900 $T bench.py --gpus 8 --config human --coverage 30 --scaling strong --index sharded --steps 2 --warmup 3 --no-files-e2e --no-cpu-baseline > gpurun_out/n8_human_sharded.json 2> gpurun_out/n8_human_sharded.err; echo "rc=$?" >> gpurun_out/n8_human_sharded.err
+tail -qn2 gpurun_out/n8_*.err
