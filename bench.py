@@ -232,51 +232,62 @@ def write_fastq_sample(path: str, lines: np.ndarray, nreads: int, first: int = 0
 # helpers
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line), sampled through NVML
+    in a thread of this process (nvidia-smi takes longer to start than a short timed region lasts); falls back to one
+    nvidia-smi query if NVML is not importable."""
 
     def __init__(self, gpu_index: int):
         self.rows = []
-        self.proc = None
+        self.gpu_index = gpu_index
+        self.stop_flag = False
+        self.nv = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+        nv = self.nv
+        R = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), sm, [k for k, bit in R.items() if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def mark(self):
         return time.time()
 
     def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
-        sm, smax, reasons = [], [], set()
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=20).stdout
+                f = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": [], "samples": 1, "how": "one nvidia-smi query after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.th.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        reasons = sorted({x for r in rows for x in r[2]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(rows), "how": "NVML, every 10 ms during the timed region"}
 
 
 def measured_peak_gbs():
@@ -501,6 +512,8 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         ix.flush()
         if kev:
             kev[1].record(stream)
+        if replica and a.replicas_only:  # independent samples: the rank's own counts are the result
+            return ix.slots_device()
         if replica:  # reduce-scatter + all-gather over peer memory, in place, in slot order
             return comm.allreduce_slots(ix, want_host=False)[1]
         if world > 1:  # --reduce nccl: all-reduce of u32, clamp to 255
@@ -517,6 +530,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         device_step()
     barrier()
     positions, hits = ix.stats()
+    keys_pass = ix.keys_scattered or positions  # k-mers of one sample that passed the pre-filter
     launches0 = ix.launches
     clocks = ClockSampler(local)
     kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -723,7 +737,6 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
     # per-access costs measured there: one pre-filter gather per `span` positions, per key that reaches the lists a
     # shared-memory rank atomic (0.68) in the scatter -- and in the re-scatter of a two-level index -- and a bucket load in
     # the sweep (1.2 with the second halves), per hit a reduction into the side counters (1.3).
-    keys_pass = ix.keys_scattered or positions
     span = 8 if nkeys > (128 << 20) else 4
     wavefronts = positions / span + keys_pass * (0.68 + 1.2 + (0.68 if ix.slices > ix.partitions else 0.0)) + hits * 1.3
     props = torch.cuda.get_device_properties(dev)
@@ -786,8 +799,10 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                            "parallelism": (f"reads sharded x{world}, index "
                                            + (f"sharded x{world} (k-mer all-to-all fused into the scatter over NVLink, "
                                               f"{len(round_cuts)} rounds)" if sharded else
-                                              ("built on rank 0 and replicated over NVLink, counts combined in slot order by a "
-                                               "reduce-scatter + all-gather over peer memory" if replica else f"replicated, counts reduced by {reduce_how}"))
+                                              ("built on rank 0 and replicated over NVLink, " +
+                                               ("every rank counts samples of its own: no exchange" if a.replicas_only else
+                                                "counts combined in slot order by a reduce-scatter + all-gather over peer memory")
+                                               if replica else f"replicated, counts reduced by {reduce_how}"))
                                            if world > 1 else "1 GPU"),
                            "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush",
                            "generate_s": t_gen, "index_build_s": t_build, "index_replicate_s": t_repl if replica else None},
@@ -819,6 +834,8 @@ def main() -> None:
     ap.add_argument("--coverage", type=float, default=None)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank counts its own --coverage sample; strong: one --coverage sample cut over the ranks")
+    ap.add_argument("--replicas-only", action="store_true",
+                    help="N > 1: every rank counts samples of its own, nothing is exchanged (BASELINE config 5: samples dealt over the GPUs)")
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files-e2e", action="store_true")

@@ -302,6 +302,10 @@ static int part_flush(vg_index* ix, cudaStream_t s) {
             ps.round_pending = ps.pending;
         }
     }
+    if (getenv("VG_ROUND_DEBUG"))
+        fprintf(stderr, "[vg round] sweep after %.3f G bytes of text; lists for %.3f G keys (%u x %llu), key share %.3f, last round %llu keys of %llu bytes\n",
+                ps.pending * 1e-9, ps.round_keys * 1e-9, ps.view.P, (unsigned long long)ps.view.cap, ps.key_share,
+                ps.h_round_keys ? *ps.h_round_keys : 0ull, (unsigned long long)ps.round_pending);
     phase_begin(ps, s);
     CU(vg::launch_probe_partitions(ix->view, ps.view, ps.slice_rank.empty() ? nullptr : ps.slice_rank.data(), &ix->d_misc->stats,
                                    ix->ctx->nsm, s));
