@@ -170,8 +170,15 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
 // Fibonacci multiply: the product's high word (bucket, filter word) depends on every bit of the k-mer, the top
 // of its low word (filter bits) on the 16 most recent bases.
 __device__ __forceinline__ uint64_t key_mix(uint64_t key56) { return key56 * 0x9E3779B97F4A7C15ULL; }
+// high word of key56 * 0x9E3779B97F4A7C15 in three multiply-adds (the compiler's 64-bit product takes four and an add)
+__device__ __forceinline__ uint32_t key_mix_hi(uint64_t key56) {
+    const uint32_t lo = (uint32_t)key56, hi = (uint32_t)(key56 >> 32);
+    uint32_t t = __umulhi(lo, 0x7F4A7C15u);
+    t = lo * 0x9E3779B9u + t;
+    return hi * 0x7F4A7C15u + t;
+}
 __device__ __forceinline__ uint32_t bucket_of(uint64_t key56, uint32_t nbuckets) {
-    return __umulhi((uint32_t)(key_mix(key56) >> 32), nbuckets);
+    return __umulhi(key_mix_hi(key56), nbuckets);
 }
 
 // ---- presence pre-filter (word-blocked Bloom, 2 bits per entry in one 32-bit word) -----------

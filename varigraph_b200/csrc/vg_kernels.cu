@@ -599,6 +599,13 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     uint32_t stride = cfg.stride;  // likewise: otherwise a constant-bank load sits between every rank and its store
     asm volatile("" : "+r"(stride));
     const uint32_t base_a = bins_s + ((P * stride) << 3);  // base_s[], same address space, same reason
+    // the three constants of a bin insert, likewise pinned: left in the parameter bank they are re-loaded (LDCU) for
+    // every single read position
+    // (an empty asm does not stop ptxas from re-loading a kernel parameter; a zero that comes out of shared memory does)
+    const uint32_t zero_r = max_cnt;  // 0: set above, read after the barrier
+    const uint32_t nb_total_r = ix.nb_total + zero_r, shift_r = pv.shift + zero_r, cap_r = cap + zero_r;
+    stride += zero_r;
+    const uint32_t hist_a = (uint32_t)__cvta_generic_to_shared(hist) + zero_r;
     uint32_t n_pos = 0;
     constexpr int kStage = kTileBytes + 32;
     __shared__ __align__(16) uint8_t tile_s[kTma ? 2 * kStage : 16];
@@ -655,9 +662,10 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if ((emit >> j) & 1u) {
-                    const uint32_t p = bucket_of(keys[j], ix.nb_total) >> pv.shift;
-                    const uint32_t r = atomicAdd(&hist[p], 1u);
-                    if (r < cap) st_shared_u64(bins_s + ((p * stride + r) << 3), keys[j]);
+                    const uint32_t p = __umulhi(key_mix_hi(keys[j]), nb_total_r) >> shift_r;
+                    uint32_t r;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(hist_a + (p << 2)) : "memory");
+                    if (r < cap_r) st_shared_u64(bins_s + ((p * stride + r) << 3), keys[j]);
                     else over |= 1u << j;
                 }
             }
