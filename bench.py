@@ -458,9 +458,9 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
             keys_np = keys.cpu().numpy().view(np.uint64)
             sample_keys_np = keys_np
     t_build0 = time.perf_counter()
-    if sharded:
-        if keys_np is None:
-            keys_np = keys.cpu().numpy().view(np.uint64)
+    if sharded and big:  # every rank made the keys on its own GPU: they are read where they lie
+        ix = capi.Index(ctx, (keys.data_ptr(), nkeys), K, a.load_factor, comm=comm, round_bytes=(a.round_mb << 20))
+    elif sharded:
         ix = capi.Index(ctx, keys_np, K, a.load_factor, comm=comm, round_bytes=(a.round_mb << 20))
     elif keys is None:
         ix = None

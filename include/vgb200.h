@@ -242,6 +242,10 @@ int vg_count_allreduce_slots(vg_comm* comm, vg_index* ix, uint8_t* c_slots_out, 
  *   - vg_count_extract_device / vg_count_histogram are not available. */
 int vg_index_create_sharded(vg_comm* comm, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
                             uint64_t round_bytes, vg_index** out);
+/* The same from keys resident in the memory of this rank's GPU (a graph generated or loaded there): no rank holds or
+ * stages the key array in host memory (16 GB per process at human scale). */
+int vg_index_create_sharded_device(vg_comm* comm, const uint64_t* dev_keys, uint64_t n, uint32_t k, double load_factor,
+                                   uint64_t round_bytes, vg_index** out);
 uint64_t vg_index_own_keys(const vg_index* ix);  /* keys in this rank's part of the table */
 uint64_t vg_count_room(const vg_index* ix);      /* bytes of bases the current round still takes; ~0 if unlimited */
 

@@ -64,3 +64,40 @@ EDGE_FASTQS = {
                b"IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n",
     "leading_junk": b"junk line\n\n@r1\nACGTACGTACGTACGTACGTACGTACGTACGTA\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n",
 }
+
+
+def free_port() -> int:
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def spawn_ranks(fn, make_args, nprocs: int, timeout_s: float = 240.0, attempts: int = 2) -> None:
+    """torch.multiprocessing.spawn with a deadline and one retry on a fresh port: a rendezvous that never completes (a
+    port grabbed between free_port() and the bind, a straggler from an earlier run) must fail or recover, not hang
+    the suite.  make_args(port) -> the argument tuple of fn after the rank."""
+    import time
+
+    import torch.multiprocessing as mp
+    last = None
+    for _ in range(attempts):
+        ctx = mp.spawn(fn, args=make_args(free_port()), nprocs=nprocs, join=False)
+        deadline = time.time() + timeout_s
+        try:
+            while not ctx.join(timeout=5.0):
+                if time.time() > deadline:
+                    raise TimeoutError(f"ranks still running after {timeout_s:.0f} s")
+            return
+        except Exception as ex:  # a rank failed, or the deadline passed: stop exactly the processes started here
+            last = ex
+            for pr in ctx.processes:
+                if pr.is_alive():
+                    pr.terminate()
+            for pr in ctx.processes:
+                pr.join(10)
+            if not isinstance(ex, TimeoutError):
+                raise
+    raise last

@@ -51,7 +51,8 @@ def worker(rank: int, world: int, port: int, scenario: str, path: str, env: dict
     import torch.distributed as dist
     from varigraph_b200 import capi
     from varigraph_b200 import dist as vdist
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import datetime
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     try:
         z = np.load(path + ".in.npz")
         keys, lines, k = z["keys"], z["lines"], int(z["k"])
@@ -85,8 +86,13 @@ def worker(rank: int, world: int, port: int, scenario: str, path: str, env: dict
             counts = comm.allreduce_counts(ix)  # the key-order call on a replica: slot-order reduce + one gather
             ix.end(want_counts=False)
             out = dict(counts=counts, slot_counts=slots[perm], perm=perm, pos=pos, hits=hits, parts=ix.partitions, n=ix.n)
-        elif scenario == "sharded":
-            ix = capi.Index(ctx, keys, k, comm=comm, round_bytes=int(z["round_bytes"]))
+        elif scenario in ("sharded", "sharded_device"):
+            if scenario == "sharded_device":  # the keys already sit on this rank's GPU
+                dk = torch.from_numpy(keys.view(np.int64)).cuda(dev)
+                torch.cuda.synchronize(dev)
+                ix = capi.Index(ctx, (dk.data_ptr(), keys.size), k, comm=comm, round_bytes=int(z["round_bytes"]))
+            else:
+                ix = capi.Index(ctx, keys, k, comm=comm, round_bytes=int(z["round_bytes"]))
             for rep in range(2):
                 ix.begin()
                 rounds = submit_in_rounds(ix, mine, dist)

@@ -2,6 +2,7 @@
 world_size 2.  The per-rank count here comes from the oracle -- in the test only, standing in for
 the CUDA kernel -- so what is checked is the sharding and the reduce: min(255, sum of per-rank
 saturated counts) must equal the single-process result, including for saturating k-mers."""
+import datetime
 import os
 import socket
 
@@ -27,7 +28,7 @@ def _worker(rank, world, port, keys, lines, k, out_path):
     from tests import oracle_binding as ob
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     b, e = vdist.shard_bounds(lines, world)[rank]
     mine, pos, hits = ob.Oracle().count_lines(keys, lines[b:e], k)
     total = vdist.reduce_counts(torch.from_numpy(mine.astype(np.int32)))
@@ -59,7 +60,7 @@ def test_two_rank_reduce_matches_single_process(tmp_path, oracle, saturate):
         lines = np.concatenate([hot[: 150 * 151], lines, hot[150 * 151:]])
     want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
     out = str(tmp_path / "r0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), t["keys"], lines, t["k"], out), nprocs=2, join=True)
+    helpers.spawn_ranks(_worker, lambda port: (2, port, t["keys"], lines, t["k"], out), nprocs=2)
     z = np.load(out)
     assert np.array_equal(z["counts"], want)
     assert (int(z["pos"]), int(z["hits"])) == (wpos, whits)
@@ -89,7 +90,7 @@ def _rounds_worker(rank, world, port, sizes, out_path):
     from tests import multi_worker
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     rng = np.random.default_rng(rank)
     reads = [bytes(rng.choice(list(b"ACGT"), size=rng.integers(1, 90)).tolist()) + b"\n" for _ in range(sizes[rank])]
     lines = np.frombuffer(b"".join(reads), dtype=np.uint8)
@@ -104,7 +105,7 @@ def test_sharded_rounds_are_collective(tmp_path):
     """Ranks with very different amounts of reads still make the same number of collective flushes, and
     every rank submits all of its reads, cut at read boundaries, never beyond the room of a round."""
     out = str(tmp_path / "rounds")
-    mp.spawn(_rounds_worker, args=(2, _free_port(), (400, 7), out), nprocs=2, join=True)
+    helpers.spawn_ranks(_rounds_worker, lambda port: (2, port, (400, 7), out), nprocs=2)
     z = [np.load(f"{out}.{r}.npz") for r in range(2)]
     assert bool(z[0]["ok"]) and bool(z[1]["ok"])
     assert int(z[0]["rounds"]) == int(z[1]["rounds"]) >= int(z[0]["nbytes"]) // 1000

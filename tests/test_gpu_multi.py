@@ -62,7 +62,7 @@ def _run_two_ranks(tmp_path, scenario, keys, lines, k, env=None, round_bytes=0, 
     import torch.multiprocessing as mp
     path = str(tmp_path / scenario)
     np.savez(path + ".in.npz", keys=keys, lines=lines, k=k, arena=arena, round_bytes=round_bytes)
-    mp.spawn(multi_worker.worker, args=(2, _free_port(), scenario, path, env or {}), nprocs=2, join=True)
+    helpers.spawn_ranks(multi_worker.worker, lambda port: (2, port, scenario, path, env or {}), nprocs=2)
     res = [np.load(f"{path}.out{r}.npz") for r in range(2)]
     import torch
     if torch.cuda.device_count() >= 2:  # a real pair of GPUs: the peer memory the ranks read is across NVLink
@@ -102,15 +102,16 @@ def test_two_ranks_replica_group_slot_order_reduce(tmp_path, oracle, two_level):
     assert want.max() == 255
 
 
-@pytest.mark.parametrize("skewed", [False, True])
-def test_two_ranks_sharded_index_matches_oracle(tmp_path, oracle, skewed):
-    """The index cut over two ranks; every rank scatters its reads' k-mers into the owner's key lists."""
+@pytest.mark.parametrize("skewed,scenario", [(False, "sharded"), (True, "sharded"), (False, "sharded_device")])
+def test_two_ranks_sharded_index_matches_oracle(tmp_path, oracle, skewed, scenario):
+    """The index cut over two ranks; every rank scatters its reads' k-mers into the owner's key lists.  Built from host
+    keys or from keys that already sit on each rank's GPU (vg_index_create_sharded_device)."""
     keys, lines, g = _workload(oracle, seed=11)
     env = {"VG_SLICE_BYTES": "16384", "VG_PART_SLACK": "64"}
     if skewed:  # identical reads overflow the owner's key list: those keys are probed in the peer's table
         env["VG_PART_SLACK"] = "0"
         lines = np.concatenate([np.tile(_read_of(g, 2000), 700), lines[: 151 * 800], np.tile(_read_of(g, 7000), 254)])
-    r0, r1 = _run_two_ranks(tmp_path, "sharded", keys, lines, 27, env=env, round_bytes=96 * 1024)
+    r0, r1 = _run_two_ranks(tmp_path, scenario, keys, lines, 27, env=env, round_bytes=96 * 1024)
     want, wpos, whits = oracle.count_lines(keys, lines, 27)
     assert np.array_equal(r0["counts"], want) and np.array_equal(r1["counts"], want)
     assert int(r0["pos"]) + int(r1["pos"]) == wpos and int(r0["hits"]) + int(r1["hits"]) == whits

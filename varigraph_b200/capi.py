@@ -92,6 +92,7 @@ def _load() -> ctypes.CDLL:
         "vg_index_replicate": (c_int, [c_void_p, c_int, c_void_p, P(c_void_p)]),
         "vg_count_allreduce_slots": (c_int, [c_void_p, c_void_p, c_void_p, P(c_void_p)]),
         "vg_index_create_sharded": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, c_uint64, P(c_void_p)]),
+        "vg_index_create_sharded_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_double, c_uint64, P(c_void_p)]),
         "vg_index_own_keys": (c_uint64, [c_void_p]),
         "vg_count_room": (c_uint64, [c_void_p]),
         "vg_host_alloc": (c_int, [P(c_void_p), c_uint64]),
@@ -243,8 +244,11 @@ class Index:
         h = c_void_p()
         if isinstance(keys, tuple):  # (device pointer, n): keys resident in the memory of ctx's GPU
             dev_ptr, n = keys
-            _chk(lib.vg_index_create_device(ctx._h, c_void_p(dev_ptr), n, k, load_factor, byref(h)))
-            self._h, self.ctx, self.comm, self.n, self.k = h, ctx, None, int(n), k
+            if comm is None:
+                _chk(lib.vg_index_create_device(ctx._h, c_void_p(dev_ptr), n, k, load_factor, byref(h)))
+            else:
+                _chk(lib.vg_index_create_sharded_device(comm._h, c_void_p(dev_ptr), n, k, load_factor, round_bytes, byref(h)))
+            self._h, self.ctx, self.comm, self.n, self.k = h, ctx, comm, int(n), k
             return
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         if comm is None:

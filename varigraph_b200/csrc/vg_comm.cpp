@@ -525,8 +525,19 @@ int vg_comm_check(vg_comm* cm) {
 // ---------------------------------------------------------------------------
 // sharded index
 // ---------------------------------------------------------------------------
+static int index_create_sharded(vg_comm* cm, const uint64_t* keys, bool keys_on_device, uint64_t n, uint32_t k, double load_factor,
+                                uint64_t round_bytes, vg_index** out);
 int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint32_t k, double load_factor,
                             uint64_t round_bytes, vg_index** out) {
+    return index_create_sharded(cm, keys, false, n, k, load_factor, round_bytes, out);
+}
+int vg_index_create_sharded_device(vg_comm* cm, const uint64_t* dev_keys, uint64_t n, uint32_t k, double load_factor,
+                                   uint64_t round_bytes, vg_index** out) {
+    return index_create_sharded(cm, dev_keys, true, n, k, load_factor, round_bytes, out);
+}
+// keys: host memory, staged through a bounded buffer twice -- or (keys_on_device) memory of this rank's GPU, read in place
+static int index_create_sharded(vg_comm* cm, const uint64_t* keys, bool keys_on_device, uint64_t n, uint32_t k, double load_factor,
+                                uint64_t round_bytes, vg_index** out) {
     if (!cm || !out || (!keys && n)) return fail(VG_E_INVALID, "vg_index_create_sharded: NULL argument");
     *out = nullptr;
     if (!cm->connected) return fail(VG_E_STATE, "vg_index_create_sharded: vg_comm_connect first");
@@ -641,13 +652,15 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
 
     // ---- keys: pass 0 counts this rank's own keys, pass 1 keeps them (with their caller positions) ----
     const uint64_t piece = 1ull << 22;
-    std::vector<uint64_t> tmp((size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
+    std::vector<uint64_t> tmp(keys_on_device ? 0 : (size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
     uint64_t* d_piece = nullptr;
     unsigned long long* d_n_own = nullptr;
-    CUB(cudaMalloc((void**)&d_piece, tmp.size() * sizeof(uint64_t)));
+    unsigned long long* d_bad = nullptr;
+    CUB(cudaMalloc((void**)&d_piece, (size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)) * sizeof(uint64_t)));
     auto bail2 = [&](int code) {
         cudaFree(d_piece);
         cudaFree(d_n_own);
+        cudaFree(d_bad);
         return bail(code);
     };
 #define CUB2(expr)                                                                                           \
@@ -658,10 +671,22 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
                               cudaGetErrorString(e__)));                                                     \
     } while (0)
     CUB2(cudaMalloc((void**)&d_n_own, sizeof(unsigned long long)));
+    if (keys_on_device) {
+        unsigned long long none = ~0ull;
+        CUB2(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
+        CUB2(cudaMemcpyAsync(d_bad, &none, sizeof none, cudaMemcpyHostToDevice, s));
+    }
     for (int pass = 0; pass < 2; ++pass) {
         CUB2(cudaMemsetAsync(d_n_own, 0, sizeof(unsigned long long), s));
         for (uint64_t off = 0; off < n; off += piece) {
             const uint64_t m = std::min<uint64_t>(piece, n - off);
+            if (keys_on_device) {  // validated and un-hashed on the device, piece by piece
+                CUB2(vg::launch_keys_to_key56(keys + off, m, k, ix->view.mask, d_piece, d_bad, s));
+                CUB2(vg::launch_select_owned(ix->view, d_piece, m, off, pass ? ix->d_key56 : nullptr, pass ? ix->d_idx : nullptr,
+                                             d_n_own, s));
+                if (pass == 1 && nwords) CUB2(vg::launch_prefilter_build(ps.d_filter, nwords, d_piece, m, k, fspan, s));
+                continue;
+            }
             for (uint64_t i = 0; i < m; ++i) {
                 const uint64_t key = keys[off + i];
                 if (pass == 0) {
@@ -682,16 +707,26 @@ int vg_index_create_sharded(vg_comm* cm, const uint64_t* keys, uint64_t n, uint3
         }
         if (pass == 0) {
             unsigned long long no = 0;
+            CUB2(cudaStreamSynchronize(s));
+            if (keys_on_device) {
+                unsigned long long bad = ~0ull;
+                CUB2(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+                if (bad != ~0ull)
+                    return bail2(fail(VG_E_INVALID, "keys[%llu]: low byte is not k=%u or the hash exceeds 2k bits (src/kmer.cpp:138)", bad, k));
+            }
             CUB2(cudaMemcpy(&no, d_n_own, sizeof no, cudaMemcpyDeviceToHost));
             ix->n_own = no;
             CUB2(cudaMalloc((void**)&ix->d_key56, std::max<uint64_t>(no, 1) * sizeof(uint64_t)));
             CUB2(cudaMalloc((void**)&ix->d_idx, std::max<uint64_t>(no, 1) * sizeof(uint64_t)));
         }
     }
+    CUB2(cudaStreamSynchronize(s));
     cudaFree(d_piece);
     cudaFree(d_n_own);
+    cudaFree(d_bad);
     d_piece = nullptr;
     d_n_own = nullptr;
+    d_bad = nullptr;
     if (ix->n_own > 3.6 * nb_local)
         return bail(fail(VG_E_NOMEM, "rank %d owns %llu keys for %llu slots", cm->rank, (unsigned long long)ix->n_own,
                          (unsigned long long)(4 * nb_local)));
