@@ -42,6 +42,68 @@ def test_encoder_even_k_matches_oracle(ctx, oracle, k):
     assert np.array_equal(ctx.encode_positions(adversarial, k), oracle.positions(adversarial, k))
 
 
+def _palindrome_dense_lines(rng, k, nreads=400):
+    """Reads that exercise every branch of the even-k rule: own-reverse-complement windows (random AT / GC text, tandem
+    repeats, explicit w + revcomp(w) inserts), ambiguous bases next to them (stale registers), short and long reads."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads = []
+    for _ in range(nreads):
+        n = rng.choice((0, 1, k - 1, k, k + 1, 2 * k, 40, 150, 151, 600))
+        mode = rng.random()
+        if mode < 0.25:
+            r = [rng.choice("AT") for _ in range(n)]
+        elif mode < 0.35:
+            unit = rng.choice(("AT", "TA", "CG", "ACGT", "AATT", "GAATTC"))
+            r = list((unit * (n // len(unit) + 1))[:n])
+        else:
+            r = [rng.choice("ACGT") for _ in range(n)]
+            for _ in range(rng.randint(0, 3)):  # a palindrome of exactly k bases somewhere
+                if n >= k:
+                    at = rng.randint(0, n - k)
+                    w = [rng.choice("ACGT") for _ in range(k // 2)]
+                    r[at:at + k] = w + [comp[b] for b in reversed(w)]
+        for j in range(len(r)):
+            x = rng.random()
+            if x < 0.004:
+                r[j] = rng.choice("NnRY")
+            elif x < 0.05:
+                r[j] = r[j].lower()
+        reads.append("".join(r))
+    return ("\n".join(reads) + "\n").encode()
+
+
+@pytest.mark.parametrize("window", ["1", "0"])
+@pytest.mark.parametrize("k", [4, 8, 12, 16, 20, 28])
+def test_even_k_count_paths_follow_the_palindrome_rule(vglib, oracle, monkeypatch, k, window):
+    """The count kernels' own encoders for even k (window encoder with the closed-form palindrome rule, and the byte-wise
+    state machine behind VG_EVEN_WINDOW=0) against the oracle's state machine (src/kmer.cpp:126-146): direct probing
+    and, where the key set is large enough to slice, scatter + slice sweep."""
+    monkeypatch.setenv("VG_EVEN_WINDOW", window)
+    rng = random.Random(1000 + k)
+    lines = _palindrome_dense_lines(rng, k)
+    pos = oracle.positions(lines, k)
+    keys = np.unique(pos[pos != NOKMER])
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    assert wpos == int((pos != NOKMER).sum()) and whits == wpos
+    for partitioned in (False, True):
+        if partitioned:
+            if len(keys) < 20000:
+                continue
+            monkeypatch.setenv("VG_PARTITION", "1")
+            monkeypatch.setenv("VG_SLICE_BYTES", "16384")
+            monkeypatch.setenv("VG_ROUND_KEYS", "65536")
+        c = vglib.Context(0, buffer_mb=1)
+        ix = vglib.Index(c, keys, k)
+        assert (ix.partitions > 0) == partitioned
+        ix.begin()
+        ix.submit(lines)
+        counts, positions, hits = ix.end()
+        assert (positions, hits) == (wpos, whits), (k, partitioned)
+        assert np.array_equal(counts, want), (k, partitioned)
+        ix.close()
+        c.close()
+
+
 def test_encoder_golden_edge_cases(ctx):
     """Every (seq, k) edge case recorded from the reference itself in tests/golden/primitives.json
     (lower case, U, N runs, CR, bytes 0x00-0x03 which seq_nt4_table maps to 0-3, short reads)."""

@@ -37,15 +37,18 @@ __device__ __forceinline__ uint8_t nt4_entry(uint32_t b) {
 // Shared-memory tables of a CTA: lut[0..255] the byte table above, then four 16-bit tables, one per byte
 // position j of a 32-bit word of text (j = 0 is the first base): code << 2(3-j) | valid << (8 + 3-j).  OR-ing
 // the four lookups of a word yields its four 2-bit codes (first base highest) in bits 0-7 and its four
-// validity bits in bits 8-11, already in place -- no per-base shifting.
+// validity bits in bits 8-11, already in place -- no per-base shifting.  hard_flags (the even-k window encoder):
+// bits 12-15 likewise say which of the four bytes are newlines.
 constexpr int kLutBytes = 256 + 4 * 256 * 2;
-__device__ __forceinline__ void lut_init(uint8_t* lut) {
+__device__ __forceinline__ void lut_init(uint8_t* lut, bool hard_flags = false) {
     uint16_t* w4 = reinterpret_cast<uint16_t*>(lut + 256);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint32_t e = nt4_entry((uint32_t)i);
         lut[i] = (uint8_t)e;
+        const uint32_t nl = hard_flags ? (e >> 3) & 1u : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w4[j * 256 + i] = (uint16_t)(((e & 3u) << (2 * (3 - j))) | (((e >> 2) & 1u) << (8 + 3 - j)));
+        for (int j = 0; j < 4; ++j)
+            w4[j * 256 + i] = (uint16_t)(((e & 3u) << (2 * (3 - j))) | (((e >> 2) & 1u) << (8 + 3 - j)) | (nl << (12 + 3 - j)));
     }
     __syncthreads();
 }
@@ -314,6 +317,51 @@ __device__ __forceinline__ void encode_seg(const Chunk& c, const Src& src, int64
         for (int j = 0; j < 16; ++j)
             if (off + j >= c.lo && off + j < c.hi) keep |= 1u << (15 - j);
         vmask &= keep;
+    }
+}
+
+// The same two with the newline flags of a table built with hard_flags: encode_word_h returns them in bits 12-15,
+// encode_seg_h as a third mask.  Bytes outside the chunk are hard boundaries.
+template <class Src>
+__device__ __forceinline__ uint32_t encode_word_h(const Chunk& c, const Src& src, int64_t off, const uint8_t* lut) {
+    if (off + 4 <= c.lo || off >= c.hi || off < 0) return 0xf000u;
+    const uint32_t t = src.ld4(off);
+    const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
+    uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] | w4[768 + (t >> 24)];
+    if (off < c.lo || off + 4 > c.hi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (off + j < c.lo || off + j >= c.hi) v = (v & ~(0x1100u << (3 - j))) | (0x1000u << (3 - j));
+    }
+    return v;
+}
+template <class Src>
+__device__ __forceinline__ void encode_seg_h(const Chunk& c, const Src& src, int64_t off, const uint8_t* lut,
+                                             uint32_t& packed, uint32_t& vmask, uint32_t& hmask) {
+    packed = 0;
+    vmask = 0;
+    hmask = 0xffffu;
+    if (off + kSegBytes <= c.lo || off >= c.hi || off < 0) return;
+    uint4 w = src.ld16(off);
+    uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    hmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t t = ws[i];
+        const uint16_t* w4 = reinterpret_cast<const uint16_t*>(lut + 256);
+        const uint32_t v = (uint32_t)w4[t & 0xffu] | w4[256 + ((t >> 8) & 0xffu)] | w4[512 + ((t >> 16) & 0xffu)] |
+                           w4[768 + (t >> 24)];
+        packed = (packed << 8) | (v & 0xffu);
+        vmask = (vmask << 4) | ((v >> 8) & 0xfu);
+        hmask = (hmask << 4) | (v >> 12);
+    }
+    if (off < c.lo || off + kSegBytes > c.hi) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (off + j >= c.lo && off + j < c.hi) keep |= 1u << (15 - j);
+        vmask &= keep;
+        hmask = (hmask & keep) | (~keep & 0xffffu);
     }
 }
 
@@ -625,5 +673,277 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
     }
     return emit;
 }
+
+
+// ---- even k: the window encoder with the reference's palindrome rule ------------------------
+// For even k a window can equal its own reverse complement; the reference then skips the position WITHOUT advancing its
+// run length (src/kmer.cpp:131-146), and an ambiguous base clears the run length but not the registers.  What that
+// state machine emits, position by position:
+//   * After a hard boundary (newline, chunk edge: registers zeroed) the registers cannot be equal while they fill up
+//     (fwd pads with A, rev pads with the complement of T), and a palindrome at a later position t skips t alone: by
+//     position i there have been i - b bases since the boundary b and at most i - b - k skipped ones, so the run length
+//     is >= k whenever the k bytes ending at i are valid.  Hence emit(i) = all_k(i) && !palindrome(i): no look-back at all.
+//   * After an ambiguous base the stale registers CAN be equal during the next k - 1 bases, each time delaying the first
+//     emission by one; only then do palindromes further on matter as well.
+// So a lane takes the closed form unless an ambiguous (non-newline) byte lies within 64 bytes in front of its segment
+// or inside it, or a palindrome lies within 32 -- then it runs the exact state machine (exact_emit_mask) for its own 16
+// positions.  With neither in sight the 2k - 1 bytes ending at an emitting position are valid or cut by a newline,
+// and k clean non-palindromic windows in a row saturate the run length whatever came before.
+// Checked against the state machine in tests/test_gpu_parity.py (random text dense in palindromes, N and newlines).
+
+// exact emit mask of the 16 positions of a segment (bit 15 - j = position j): encode_keys_any without the keys
+__device__ __noinline__ uint32_t exact_emit_mask(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+    uint64_t keys[16];
+    const uint32_t e = encode_keys_any<false, 16>(c, off, kp, lut, keys, nullptr);
+    return __brev(e) >> 16;
+}
+
+#ifndef VG_ROLLING_ENCODER
+// palindromes among the windows ending at the 16 own positions: bit 2(15 - j) of the result (a 2-bit slot per position)
+// is set iff the k bases ending at own position j read the same on both strands.  Slot-parallel: pair d of a window is
+// (base[t - d], base[t - k + 1 + d]); the pairs of all 16 windows are two shifted views of the 96 bits in sight, and a
+// pair is complementary iff its XOR is 3.  The warp stops as soon as no lane has a candidate left (4^-d of them survive
+// d pairs).
+__device__ __forceinline__ uint32_t palindrome_slots(uint32_t p2, uint32_t p1, uint32_t p0, uint32_t k) {
+    uint32_t acc = 0x55555555u;
+    const uint32_t half = k >> 1;
+    for (uint32_t d = 0; d < half; ++d) {
+        const uint32_t a = __funnelshift_r(p0, p1, 2u * d);  // slot j: base[t_j - d]; 2d < 32
+        const uint32_t sh = 2u * (k - 1u - d);               // 2 .. 54
+        const uint32_t b = sh < 32u ? __funnelshift_r(p0, p1, sh) : __funnelshift_r(p1, p2, sh - 32u);
+        const uint32_t x = a ^ b;
+        acc &= x & (x >> 1);
+        if ((d & 1u) && !__any_sync(kFullMask, acc != 0u)) break;
+    }
+    return acc;
+}
+
+// bit i of the result: the k bytes ending at the byte of bit i are all valid (V: one bit per byte, earlier bytes higher)
+__device__ __forceinline__ uint64_t all_valid_k(uint64_t V, uint32_t k) {
+    uint64_t pw = V, acc = ~0ULL;
+    uint32_t have = 0;
+#pragma unroll
+    for (int bit = 0; bit < 5; ++bit) {
+        if (k & (1u << bit)) {
+            acc &= pw >> have;
+            have += 1u << bit;
+        }
+        pw &= pw >> (1u << bit);
+    }
+    return acc;
+}
+
+// palindrome_slots for one lane on its own (no votes), only for the positions in `want` (bit 15 - j = own position j)
+__device__ __forceinline__ bool palindrome_among(uint32_t p2, uint32_t p1, uint32_t p0, uint32_t k, uint32_t want) {
+    uint32_t acc = want;  // spread to one 2-bit slot per position
+    acc = (acc | (acc << 8)) & 0x00ff00ffu;
+    acc = (acc | (acc << 4)) & 0x0f0f0f0fu;
+    acc = (acc | (acc << 2)) & 0x33333333u;
+    acc = (acc | (acc << 1)) & 0x55555555u;
+    const uint32_t half = k >> 1;
+    for (uint32_t d = 0; d < half && acc; ++d) {
+        const uint32_t a = __funnelshift_r(p0, p1, 2u * d);
+        const uint32_t sh = 2u * (k - 1u - d);
+        const uint32_t b = sh < 32u ? __funnelshift_r(p0, p1, sh) : __funnelshift_r(p1, p2, sh - 32u);
+        const uint32_t x = a ^ b;
+        acc &= x & (x >> 1);
+    }
+    return acc != 0u;
+}
+
+// The registers after an ambiguous byte: it is skipped, so until k bases have followed it they hold the bases on both
+// sides of it spliced together -- and may read the same on both strands.  True iff that happens (or cannot be ruled
+// out from the 48 bases in view) at one of the 16 positions of the view's last segment.  V / S: validity and
+// ambiguity of the 48 bytes, first byte in bit 47.  Only called where S != 0.
+// Per ambiguous byte: cut it out of the view (bases, V and S alike) and look for palindromes among the windows of the
+// spliced text that end at own positions fewer than k bases after it.
+__device__ __noinline__ bool stale_palindrome(uint32_t p2, uint32_t p1, uint32_t p0, uint64_t V, uint64_t S, uint32_t k) {
+    const uint32_t warm = (uint32_t)V & ~(uint32_t)all_valid_k(V, k) & 0xffffu;  // own, valid, fewer than k bases into the run
+    if (!warm) return false;
+    uint64_t soft = S & 0xffffffffffffULL;
+    while (soft) {
+        const uint32_t bb = 63u - (uint32_t)__clzll((long long)soft);
+        soft &= ~(1ULL << bb);
+        if (bb == 0u) continue;
+        const uint64_t below = (1ULL << bb) - 1ULL;
+        const uint64_t inv_below = ~V & below;
+        const uint32_t stop = inv_below ? 64u - (uint32_t)__clzll((long long)inv_below) : 0u;  // the run after it ends above this bit
+        const uint32_t lo = max(stop, bb >= k - 1u ? bb - (k - 1u) : 0u);
+        const uint32_t mine = (uint32_t)(below & ~((1ULL << lo) - 1ULL)) & warm;  // own positions 1 .. k-1 bases after the byte
+        if (!mine) continue;
+        // the view without the byte: everything above it moves down one place
+        const uint64_t Vs = ((V >> (bb + 1u)) << bb) | (V & below);
+        const uint64_t Ss = ((S >> (bb + 1u)) << bb) | (S & below) | (1ULL << 47);  // what moves in at the top is unknown
+        const uint32_t y0 = __funnelshift_r(p0, p1, 2u), y1 = __funnelshift_r(p1, p2, 2u), y2 = p2 >> 2;
+        uint32_t m0, m1, m2;  // 96-bit mask of the bases below the byte
+        const uint32_t b2 = 2u * bb;
+        if (b2 >= 64u) { m0 = m1 = ~0u; m2 = (1u << (b2 - 64u)) - 1u; }
+        else if (b2 >= 32u) { m0 = ~0u; m1 = (1u << (b2 - 32u)) - 1u; m2 = 0u; }
+        else { m0 = (1u << b2) - 1u; m1 = m2 = 0u; }
+        const uint32_t q0 = (p0 & m0) | (y0 & ~m0), q1 = (p1 & m1) | (y1 & ~m1), q2 = (p2 & m2) | (y2 & ~m2);
+        const uint32_t clean = (uint32_t)all_valid_k(Vs, k) & mine;
+        if (clean && palindrome_among(q2, q1, q0, k, clean)) return true;
+        if (mine & ~clean) {
+            // another invalid byte fewer than k bases in front of the cut: a newline means registers still filling up
+            // (never equal); a second ambiguous byte is not worked out here
+            const uint64_t inv_above = ~Vs >> bb;  // bit 0: the byte that moved next to the run
+            const uint32_t a = bb + (uint32_t)__ffsll((long long)inv_above) - 1u;  // inv_above != 0: bit 47 of Vs is clear
+            if ((Ss >> a) & 1ULL) return true;
+        }
+    }
+    return false;
+}
+
+struct EvenEncoder : OddEncoder {
+    __device__ __forceinline__ void init(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        init(c, GlobalText{c.al}, off, kp, lut);
+    }
+    // lut: built with hard_flags
+    template <class Src>
+    __device__ __forceinline__ void init(const Chunk& c, const Src& src, int64_t off, const KmerParams& kp, const uint8_t* lut) {
+        const int lane = threadIdx.x & 31;
+        uint32_t v0, h0;
+        encode_seg_h(c, src, off, lut, p0, v0, h0);
+        // The 64 bases in front of the warp's text: lanes 0-15 encode a word each, lanes 0 4 8 12 assemble a segment
+        // each, everybody collects the four segments (ex[3] is the one right in front of the warp's text).
+        uint32_t wv = 0xf000u;
+        if (lane < 16) wv = encode_word_h(c, src, off - 16 * lane - 64 + 4 * lane, lut);
+        const uint32_t w1 = __shfl_down_sync(kFullMask, wv, 1), w2 = __shfl_down_sync(kFullMask, wv, 2),
+                       w3 = __shfl_down_sync(kFullMask, wv, 3);
+        const uint32_t segp = ((wv & 0xffu) << 24) | ((w1 & 0xffu) << 16) | ((w2 & 0xffu) << 8) | (w3 & 0xffu);
+        const uint32_t segv = (((wv >> 8) & 0xfu) << 12) | (((w1 >> 8) & 0xfu) << 8) | (((w2 >> 8) & 0xfu) << 4) | ((w3 >> 8) & 0xfu);
+        const uint32_t segh = ((wv >> 12) << 12) | ((w1 >> 12) << 8) | ((w2 >> 12) << 4) | (w3 >> 12);
+        uint32_t ex[4], exv[4], exs[4];  // bases, validity, ambiguous (neither valid nor newline)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            ex[m] = __shfl_sync(kFullMask, segp, 4 * m);
+            const uint32_t vh = __shfl_sync(kFullMask, segv | (segh << 16), 4 * m);
+            exv[m] = vh & 0xffffu;
+            exs[m] = ~(vh | (vh >> 16)) & 0xffffu;
+        }
+        uint32_t v1 = __shfl_up_sync(kFullMask, v0, 1), v2 = __shfl_up_sync(kFullMask, v0, 2);
+        p1 = __shfl_up_sync(kFullMask, p0, 1);
+        p2 = __shfl_up_sync(kFullMask, p0, 2);
+        if (lane == 0) { p1 = ex[3]; v1 = exv[3]; p2 = ex[2]; v2 = exv[2]; }
+        if (lane == 1) { p2 = ex[3]; v2 = exv[3]; }
+        const uint64_t V = ((uint64_t)v2 << 32) | ((uint64_t)v1 << 16) | v0;
+        uint64_t pw = V, acc = ~0ULL;
+        uint32_t have = 0;
+#pragma unroll
+        for (int bit = 0; bit < 5; ++bit) {
+            if (kp.k & (1u << bit)) {
+                acc &= pw >> have;
+                have += 1u << bit;
+            }
+            pw &= pw >> (1u << bit);
+        }
+        all_k = (uint32_t)acc & 0xffffu;
+        // palindromes at own positions (only where the window is clean), spread to one bit per position
+        uint32_t pal = palindrome_slots(p2, p1, p0, kp.k);
+        if (pal) {
+            pal = (pal | (pal >> 1)) & 0x33333333u;
+            pal = (pal | (pal >> 2)) & 0x0f0f0f0fu;
+            pal = (pal | (pal >> 4)) & 0x00ff00ffu;
+            pal = (pal | (pal >> 8)) & 0x0000ffffu;
+            pal &= all_k;
+        }
+        // palindromes among the k - 1 windows that end in front of the warp's text: lane q tests the one ending q + 1 bases
+        // before it (its window is clean iff the k bytes are valid)
+        bool lead_pal = false;
+        {
+            const uint64_t hi = ((uint64_t)ex[0] << 32) | ex[1], lo = ((uint64_t)ex[2] << 32) | ex[3];
+            const uint64_t lv = ((uint64_t)exv[0] << 48) | ((uint64_t)exv[1] << 32) | ((uint64_t)exv[2] << 16) | exv[3];
+            const uint32_t q = (uint32_t)lane;
+            const uint64_t win = (q ? (lo >> (2u * q)) | (hi << (64u - 2u * q)) : lo) & kp.mask;
+            const uint64_t ones = (1ULL << kp.k) - 1ULL;
+            lead_pal = q + 1u < kp.k && ((lv >> q) & ones) == ones && win == revcomp2k(win, kp.k);
+        }
+        // Who must run the state machine instead: lanes within reach of a position where the registers, spliced over an
+        // ambiguous byte, read the same on both strands (reach: the 2k - 2 positions after it, i.e. the lane's own segment
+        // and the four in front of it; the lead-in segments count as lanes -4 .. -1), and lanes with a palindrome in
+        // their own segment or the two in front of it.
+        const uint32_t sf0 = ~(v0 | h0) & 0xffffu;
+        const uint32_t soft_lanes = __ballot_sync(kFullMask, sf0 != 0u);
+        const uint32_t pal_lanes = __ballot_sync(kFullMask, pal != 0u);
+        const uint32_t lead_pal_any = __ballot_sync(kFullMask, lead_pal);
+        const uint32_t lead_soft = (exs[0] ? 1u : 0u) | (exs[1] ? 2u : 0u) | (exs[2] ? 4u : 0u) | (exs[3] ? 8u : 0u);
+        all_k &= ~pal;
+        if (soft_lanes | pal_lanes | lead_pal_any | lead_soft) {  // rare: nothing of the kind in most warps' sight
+            uint32_t stale_lanes = 0, lead_stale = 0;
+            if (soft_lanes | lead_soft) {
+                uint32_t sf1 = __shfl_up_sync(kFullMask, sf0, 1), sf2 = __shfl_up_sync(kFullMask, sf0, 2);
+                if (lane == 0) { sf1 = exs[3]; sf2 = exs[2]; }
+                if (lane == 1) sf2 = exs[3];
+                const uint64_t S = ((uint64_t)sf2 << 32) | ((uint64_t)sf1 << 16) | sf0;
+                bool stale = false;
+                if (S) stale = stale_palindrome(p2, p1, p0, V, S, kp.k);
+                stale_lanes = __ballot_sync(kFullMask, stale);
+                if (lead_soft) {
+                    // The same for the four lead-in segments, by lanes 0-3.  Their views reach 32 bases further back:
+                    // lanes 0-7 fetch those now (two more segments, assembled at lanes 0 and 4).
+                    uint32_t xw = 0xf000u;
+                    if (lane < 8) xw = encode_word_h(c, src, off - 16 * lane - 96 + 4 * lane, lut);
+                    const uint32_t x1 = __shfl_down_sync(kFullMask, xw, 1), x2 = __shfl_down_sync(kFullMask, xw, 2),
+                                   x3 = __shfl_down_sync(kFullMask, xw, 3);
+                    const uint32_t xp = ((xw & 0xffu) << 24) | ((x1 & 0xffu) << 16) | ((x2 & 0xffu) << 8) | (x3 & 0xffu);
+                    const uint32_t xv = (((xw >> 8) & 0xfu) << 12) | (((x1 >> 8) & 0xfu) << 8) | (((x2 >> 8) & 0xfu) << 4) | ((x3 >> 8) & 0xfu);
+                    const uint32_t xh = ((xw >> 12) << 12) | ((x1 >> 12) << 8) | ((x2 >> 12) << 4) | (x3 >> 12);
+                    uint32_t fx[6], fv[6], fs[6];  // segments -2 .. 3 in front of the warp's text
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        fx[m] = __shfl_sync(kFullMask, xp, 4 * m);
+                        const uint32_t vh = __shfl_sync(kFullMask, xv | (xh << 16), 4 * m);
+                        fv[m] = vh & 0xffffu;
+                        fs[m] = ~(vh | (vh >> 16)) & 0xffffu;
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { fx[m + 2] = ex[m]; fv[m + 2] = exv[m]; fs[m + 2] = exs[m]; }
+                    // lane m < 4 takes lead-in segment m: view = segments m, m + 1, m + 2 of the six (selects, not
+                    // indexing: the arrays live in registers)
+                    auto at = [&](const uint32_t (&a)[6], int i) {
+                        return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : i == 3 ? a[3] : i == 4 ? a[4] : a[5];
+                    };
+                    bool ls = false;
+                    if (lane < 4) {
+                        const uint64_t LV = ((uint64_t)at(fv, lane) << 32) | ((uint64_t)at(fv, lane + 1) << 16) | at(fv, lane + 2);
+                        const uint64_t LS = ((uint64_t)at(fs, lane) << 32) | ((uint64_t)at(fs, lane + 1) << 16) | at(fs, lane + 2);
+                        if (LS) ls = stale_palindrome(at(fx, lane), at(fx, lane + 1), at(fx, lane + 2), LV, LS, kp.k);
+                    }
+                    lead_stale = __ballot_sync(kFullMask, ls) & 0xfu;
+                }
+            }
+            const uint64_t SL = ((uint64_t)stale_lanes << 4) | lead_stale;             // bit (l + 4): lane l
+            const uint64_t PL = ((uint64_t)pal_lanes << 2) | (lead_pal_any ? 3u : 0u);  // bit (l + 2): lane l
+            bool slow = (((SL >> lane) & 0x1fu) | ((PL >> lane) & 0x7u)) != 0;
+#ifdef VG_EVEN_SKIP_SLOW  // timing experiment only: wrong counts near such positions
+            slow = false;
+#endif
+            if (slow) all_k = exact_emit_mask(c, off, kp, lut);
+        }
+        const uint32_t rt = revcomp16(p0), rm = revcomp16(p1), rb = revcomp16(p2);
+        const uint32_t base = 66u - 2u * kp.k;
+        if (base < 32u) {
+            l0 = __funnelshift_r(rb, rm, base);
+            l1 = __funnelshift_r(rm, rt, base);
+            l2 = rt >> base;
+        } else if (base < 64u) {
+            l0 = __funnelshift_r(rm, rt, base - 32u);
+            l1 = rt >> (base - 32u);
+            l2 = 0;
+        } else {
+            l0 = rt;
+            l1 = l2 = 0;
+        }
+        pos = 0;
+    }
+};
+#endif
+
+// which encoder a kernel instantiation runs
+constexpr int kEncAny = 0, kEncOdd = 1, kEncEven = 2;
+template <int kEnc> struct EncoderOf { using type = OddEncoder; };
+#ifndef VG_ROLLING_ENCODER
+template <> struct EncoderOf<kEncEven> { using type = EvenEncoder; };
+#endif
 
 }  // namespace vg

@@ -376,13 +376,16 @@ __device__ __forceinline__ void probe_and_count(const IndexView& ix, const uint6
     }
 }
 
-template <bool kOdd, int kBatch>
+// kEnc: which encoder -- kEncAny the byte-wise state machine (any k), kEncOdd / kEncEven the position-parallel window
+// encoders (vg_device.cuh)
+template <int kEnc, int kBatch>
 __global__ void __launch_bounds__(kCtaThreads, kBatch >= 8 ? 2 : 3)
 count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
+    constexpr bool kOdd = kEnc != kEncAny;  // a window encoder
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ unsigned long long blk[2];
     if (c.skip && *c.skip) return;
-    lut_init(lut);
+    lut_init(lut, kEnc == kEncEven);
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
     __syncthreads();
     KmerParams kp{ix.k, ix.mask};
@@ -390,13 +393,13 @@ count_kernel(IndexView ix, Chunk c, int64_t ntiles, CountStats* stats) {
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = t * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         if (kOdd) {
-            OddEncoder enc;
+            typename EncoderOf<kEnc>::type enc;
             enc.init(c, off, kp, lut);
             // rolled on purpose: one probe batch of registers, and a loop body that stays in the I-cache
 #pragma unroll 1
             for (int part = 0; part < 16 / kBatch; ++part) {
                 uint64_t keys[kBatch];
-                uint32_t emit = enc.next<kBatch, false>(kp, keys);
+                uint32_t emit = enc.template next<kBatch, false>(kp, keys);
                 n_pos += __popc(emit);
                 probe_and_count<kBatch>(ix, keys, emit, n_hit);
             }
@@ -572,10 +575,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // encoder and the LSU only sees shared-memory loads.
 // kK: the k-mer length as a compile-time constant (27, the reference's default) or 0 = whatever the index says; with a
 // constant k the validity windows, the window offsets and the masks of the encoder fold into immediates.
-template <bool kOdd, bool kTma, int kSpan, int kK>
+template <int kEnc, bool kTma, int kSpan, int kK>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chunk c, int64_t first_tile, int64_t ntiles,
                CountStats* stats) {
+    constexpr bool kOdd = kEnc != kEncAny;  // a window encoder (odd k, or even k with the palindrome rule)
     extern __shared__ __align__(16) uint64_t smem_bins[];  // indexed directly: STS / LDS with the base folded in
     const uint32_t P = pv.P, cap = cfg.cap;
     unsigned long long* base_s = reinterpret_cast<unsigned long long*>(smem_bins + (size_t)P * cfg.stride);
@@ -586,7 +590,7 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
     __shared__ unsigned long long blk_pos;
     __shared__ uint32_t max_cnt;
     if (c.skip && *c.skip) return;
-    lut_init(lut);
+    lut_init(lut, kEnc == kEncEven);
     if (threadIdx.x == 0) blk_pos = 0, max_cnt = 0;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -682,14 +686,14 @@ scatter_kernel(IndexView ix, PartView pv, PrefilterView pf, ScatterCfg cfg, Chun
             }
         };
         if (kOdd) {
-            OddEncoder enc;
+            typename EncoderOf<kEnc>::type enc;
             if (kTma) enc.init(c, SharedText{tile_a + (it & 1) * kStage, (first_tile + t) * kTileBytes - 32}, off, kp, lut);
             else enc.init(c, off, kp, lut);
             uint64_t keys[8], pairs[kGroups];
-            uint32_t emit = enc.next<8, false, true, kSpan>(kp, keys, pairs);
+            uint32_t emit = enc.template next<8, false, true, kSpan>(kp, keys, pairs);
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
-            emit = enc.next<8, false, true, kSpan>(kp, keys, pairs);
+            emit = enc.template next<8, false, true, kSpan>(kp, keys, pairs);
             n_pos += __popc(emit);
             bin8(keys, pairs, emit);
         } else {
@@ -1475,6 +1479,20 @@ int count_variant() {
     return v;
 }
 
+// A/B knob: VG_EVEN_WINDOW=0 runs even k through the byte-wise state machine (round 1's only even-k path) instead of
+// the window encoder with the palindrome rule.  Same results either way.
+static bool even_window() {
+#ifdef VG_ROLLING_ENCODER
+    return false;
+#else
+    static bool v = [] {
+        const char* e = getenv("VG_EVEN_WINDOW");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+#endif
+}
+
 int sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
@@ -1587,8 +1605,9 @@ cudaError_t launch_count(const IndexView& ix, const uint8_t* d_bases, uint64_t n
     int64_t ntiles = tiles_for(c);
     // persistent grid: exactly the CTAs that are resident at once, each striding over the tiles
     using KernelT = void (*)(IndexView, Chunk, int64_t, CountStats*);
-    KernelT kern = (ix.k & 1) ? (count_variant() == 4 ? (KernelT)count_kernel<true, 4> : (KernelT)count_kernel<true, 8>)
-                              : (KernelT)count_kernel<false, 4>;
+    KernelT kern = (ix.k & 1) ? (count_variant() == 4 ? (KernelT)count_kernel<kEncOdd, 4> : (KernelT)count_kernel<kEncOdd, 8>)
+                   : even_window() ? (KernelT)count_kernel<kEncEven, 4>
+                                   : (KernelT)count_kernel<kEncAny, 4>;
     int occ = 0;
     if (ctas_per_sm <= 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, 0) != cudaSuccess || occ < 1) occ = 2;
@@ -1622,10 +1641,11 @@ cudaError_t launch_scatter(const IndexView& ix, const PartView& pv, const Prefil
     const bool tma = tma_env && atoi(tma_env) != 0 && (ix.k & 1);
     const bool s8 = pf.words && pf.span == 8;
     KernelT kern;
-    if (!(ix.k & 1)) kern = s8 ? (KernelT)scatter_kernel<false, false, 8, 0> : (KernelT)scatter_kernel<false, false, 4, 0>;
-    else if (tma) kern = s8 ? (KernelT)scatter_kernel<true, true, 8, 0> : (KernelT)scatter_kernel<true, true, 4, 0>;
-    else if (ix.k == 27) kern = s8 ? (KernelT)scatter_kernel<true, false, 8, 27> : (KernelT)scatter_kernel<true, false, 4, 27>;
-    else kern = s8 ? (KernelT)scatter_kernel<true, false, 8, 0> : (KernelT)scatter_kernel<true, false, 4, 0>;
+    if (!(ix.k & 1) && even_window()) kern = s8 ? (KernelT)scatter_kernel<kEncEven, false, 8, 0> : (KernelT)scatter_kernel<kEncEven, false, 4, 0>;
+    else if (!(ix.k & 1)) kern = s8 ? (KernelT)scatter_kernel<kEncAny, false, 8, 0> : (KernelT)scatter_kernel<kEncAny, false, 4, 0>;
+    else if (tma) kern = s8 ? (KernelT)scatter_kernel<kEncOdd, true, 8, 0> : (KernelT)scatter_kernel<kEncOdd, true, 4, 0>;
+    else if (ix.k == 27) kern = s8 ? (KernelT)scatter_kernel<kEncOdd, false, 8, 27> : (KernelT)scatter_kernel<kEncOdd, false, 4, 27>;
+    else kern = s8 ? (KernelT)scatter_kernel<kEncOdd, false, 8, 0> : (KernelT)scatter_kernel<kEncOdd, false, 4, 0>;
     // Bin capacity: ~1.8x the expected k-mers per slice and tile (the pre-filter passes roughly half),
     // shrunk to a shared-memory budget that lets four CTAs share an SM -- or two, when there are so many
     // slices that four would leave bins of a handful of keys.  Overflowing keys take the key-by-key
