@@ -16,6 +16,8 @@ every read k-mer of the sample against the index, produce the count vector.
             reference arm reads) -> counts in host memory; file reads, H2D and D2H inside the timed region
   e2e_staged  vg_count_begin / vg_count_submit from pinned host memory holding parsed "read\\n" records /
             vg_count_end_slots into host memory (round 1's e2e)
+  e2e_gz    vg_count_files over gzip-compressed FASTQ (a bounded sample, N=1): the parallel inflater against zlib on one
+            thread per file
   roofline  the count pass against the measured HBM copy bandwidth (MEASURED_PEAKS.json) with
             B_alg = 1 + 32 + 32 h bytes per position; per-kernel times from the library's own CUDA
             events, the L1TEX gather rate that actually binds the kernels, and the measured random-sector rate
@@ -395,7 +397,7 @@ def emitted_positions(sub) -> int:
 # ------------------------------------------------------------------------------------------------
 # one workload on our arm -> the JSON line's fields
 # ------------------------------------------------------------------------------------------------
-def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_files_e2e=True, want_cpu=True,
+def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_files_e2e=True, want_cpu=True, want_gz_e2e=True,
             staged_cap_bytes=None):
     dev = torch.device("cuda", local)
     L = w["genome_mb"] * 1_000_000
@@ -645,6 +647,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
 
     # ---- e2e: the reference-facing call, from the FASTQ files the reference arm reads ----------------------
     e2e = None
+    e2e_gz = None
     if want_files_e2e and not sharded:
         tmpdir = tmpfs_dir()
         try:
@@ -696,6 +699,56 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                    "counts_equal_device_path": files_ok, "file_bytes_per_step": int(file_bytes), "host_threads": threads,
                    "input": "two plain four-line FASTQ files per rank on tmpfs through vg_count_files "
                             "(the same kind of file the reference arm reads)"}
+            # ---- e2e_gz: the same call on gzip-compressed FASTQ (what sequencers deliver) ----------------------------------
+            # one ordinary single-member .gz per mate (zlib level 6), a bounded sample; the parallel inflater
+            # (vg_gzip.cpp) against zlib on one thread per file (VG_GZ_PARALLEL=0: round 1's road, and the reference's)
+            if world == 1 and want_gz_e2e:
+                import threading
+                import zlib
+                gz_reads = min(nreads, 2_000_000)
+                ghalf = gz_reads // 2
+                plain = [os.path.join(tmpdir, "g_1.fq"), os.path.join(tmpdir, "g_2.fq")]
+                write_fastq_sample(plain[0], lines_np, ghalf, 0)
+                write_fastq_sample(plain[1], lines_np, gz_reads - ghalf, ghalf)
+                gzs = [f + ".gz" for f in plain]
+
+                def deflate(src, dst):
+                    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+                    with open(src, "rb") as fi, open(dst, "wb") as fo:
+                        for blk in iter(lambda: fi.read(8 << 20), b""):
+                            fo.write(co.compress(blk))
+                        fo.write(co.flush())
+
+                th = [threading.Thread(target=deflate, args=(a_, b_)) for a_, b_ in zip(plain, gzs)]
+                [t.start() for t in th]
+                [t.join() for t in th]
+                gz_bytes = sum(os.path.getsize(f) for f in gzs)
+                text_bytes = sum(os.path.getsize(f) for f in plain)
+                [os.unlink(f) for f in plain]
+                gz_positions = gz_reads * (READ_LEN - a.kmer + 1)  # upper bound; the exact figure comes from the pass below
+
+                def gz_step():
+                    ix.begin()
+                    rb_ = ix.count_files(gzs, threads=threads)
+                    c_, pos_, _ = ix.end_slots()
+                    return rb_, c_, pos_
+
+                os.environ["VG_GZ_PARALLEL"] = "0"
+                t0 = time.perf_counter()
+                rb_z, c_z, pos_z = gz_step()
+                zlib_s = time.perf_counter() - t0
+                os.environ["VG_GZ_PARALLEL"] = "1"
+                gz_step()
+                t0 = time.perf_counter()
+                gsteps = 3
+                for _ in range(gsteps):
+                    rb_p, c_p, pos_p = gz_step()
+                gz_s = (time.perf_counter() - t0) / gsteps
+                e2e_gz = {"value": pos_p / gz_s, "unit": UNIT, "zlib_road_value": pos_z / zlib_s,
+                          "inflated_text_gb_per_s": text_bytes / gz_s / 1e9, "gz_bytes_per_step": int(gz_bytes),
+                          "text_bytes_per_step": int(text_bytes), "host_threads": threads,
+                          "counts_equal_zlib_road": bool(rb_p == rb_z and pos_p == pos_z and np.array_equal(c_p, c_z)),
+                          "input": f"first {gz_reads} reads as two single-member .gz files (zlib level 6) on tmpfs through vg_count_files"}
         finally:
             rm_tree(tmpdir)
     ctx.set_stream(stream.cuda_stream)
@@ -806,7 +859,7 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
                                            if world > 1 else "1 GPU"),
                            "l2": "inputs (reads + index table) far larger than the 126 MB L2; no explicit flush",
                            "generate_s": t_gen, "index_build_s": t_build, "index_replicate_s": t_repl if replica else None},
-                "e2e": e2e if e2e is not None else e2e_staged, "e2e_staged": e2e_staged,
+                "e2e": e2e if e2e is not None else e2e_staged, "e2e_staged": e2e_staged, "e2e_gz": e2e_gz,
                 "gpu_launches": int(launches_timed), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "parity": parity}
     if world > 1:
@@ -839,6 +892,7 @@ def main() -> None:
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files-e2e", action="store_true")
+    ap.add_argument("--no-gz-e2e", action="store_true")
     ap.add_argument("--human", default="auto", choices=["auto", "on", "off"],
                     help="add the human-scale section to the line (auto: at N == 8)")
     ap.add_argument("--human-coverage", type=float, default=30.0)
@@ -901,7 +955,7 @@ def main() -> None:
 
     big = L > 512_000_000
     line = measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist,
-                   want_files_e2e=not a.no_files_e2e and not big, want_cpu=(world == 1 or big),
+                   want_files_e2e=not a.no_files_e2e and not big, want_gz_e2e=not a.no_gz_e2e, want_cpu=(world == 1 or big),
                    staged_cap_bytes=(2 << 30) if big else None)
     if line is not None:
         line["config"]["host_binding"] = numa

@@ -121,6 +121,13 @@ int64_t vg_fastq_record_boundary(const char* path, uint64_t at, uint64_t window)
  * last != 0: the block ends at the end of the file, where the final newline may be missing. */
 int64_t vg_fastq_strip_block(const char* text, uint64_t nbytes, int last, uint8_t* out, uint64_t* bases, int64_t* bad_at);
 
+/* Host-only diagnostic (no GPU needed): the parallel inflater behind vg_count_files' gzip road (replaces gzread of
+ * /root/reference/include/kseq.h:242 + src/fastq_kmer.cpp:74 for .gz input).  Inflates the gzip file at path -- one or
+ * many members -- with `threads` workers, `chunk_bytes` compressed bytes per worker and round; *out (release it with
+ * vg_gunzip_free) holds the *out_len bytes zlib would return.  0 ok, -1 cannot read the file, -2 not gzip / corrupt. */
+int vg_gunzip_parallel(const char* path, int threads, uint64_t chunk_bytes, uint8_t** out, uint64_t* out_len);
+void vg_gunzip_free(uint8_t* p);
+
 /* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
  * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */
 int vg_count_flush(vg_index* ix);

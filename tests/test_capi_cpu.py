@@ -169,3 +169,80 @@ def test_fastq_strip_block_vs_kseq_restatement(vglib, oracle):
         assert bad == 0 or data[bad - 1: bad] == b"\n", trial
         rest_lines, _, rest_bases, _ = oracle.fastq_to_lines(data[bad:])
         assert w + _no_empty(rest_lines) == want_lines and b + rest_bases == want_bases, (trial, bad)
+
+
+# ---- the parallel inflater behind the gzip road (vg_gzip.cpp): bytes identical to zlib's ------------------------
+def _gunzip(vglib, path, threads, chunk):
+    import ctypes
+    p, n = ctypes.c_void_p(), ctypes.c_uint64()
+    rc = vglib.lib.vg_gunzip_parallel(str(path).encode(), threads, chunk, ctypes.byref(p), ctypes.byref(n))
+    if rc != 0:
+        return rc, None
+    data = ctypes.string_at(p, n.value)
+    vglib.lib.vg_gunzip_free(p)
+    return 0, data
+
+
+def _fastq_text(n, seed, L=150):
+    import random
+    r = random.Random(seed)
+    return "".join("@read%d/1 lane:%d\n%s\n+\n%s\n" % (i, i % 7, "".join(r.choice("ACGTN") for _ in range(L)),
+                                                          "".join(r.choice("FFFFFFFF:,#") for _ in range(L))) for i in range(n)).encode()
+
+
+def _bgzf(data: bytes) -> bytes:
+    """What bgzip writes: gzip members of <= 64 KiB of text each with a BC extra field, then the empty EOF member."""
+    import zlib
+    out = []
+    for i in range(0, len(data), 65280):
+        blk = data[i:i + 65280]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        cd = co.compress(blk) + co.flush()
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + (len(cd) + 25).to_bytes(2, "little") + cd +
+                   zlib.crc32(blk).to_bytes(4, "little") + len(blk).to_bytes(4, "little"))
+    out.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return b"".join(out)
+
+
+def test_parallel_gunzip_matches_zlib(vglib, tmp_path):
+    """Every shape of gzip the feeder can meet, cut into chunks small enough that block starts are searched and windows
+    are resolved many times over: single member at three levels, concatenated members, bgzip blocks, stored blocks
+    (level 0), members so small they use the fixed code, sync-flushed streams (empty stored blocks), binary content (no
+    block start is ever found: the first worker inflates everything), an empty member, trailing garbage, a flipped bit."""
+    import gzip
+    import random
+    import zlib
+    txt = _fastq_text(6000, 1)
+    cases = []
+    for lvl in (1, 6, 9):
+        cases.append(("level%d" % lvl, txt, gzip.compress(txt, lvl)))
+    parts = [_fastq_text(300, 10 + i) for i in range(25)]
+    cases.append(("members", b"".join(parts), b"".join(gzip.compress(p, 6) for p in parts)))
+    cases.append(("bgzf", txt, _bgzf(txt)))
+    cases.append(("stored", txt[:300000], gzip.compress(txt[:300000], 0)))
+    tiny = [b"@r\nACGT\n+\nFFFF\n"] * 200
+    cases.append(("fixed", b"".join(tiny), b"".join(gzip.compress(p, 6) for p in tiny)))
+    co, sf = zlib.compressobj(6, zlib.DEFLATED, 31), b""
+    for i in range(0, len(txt), 70000):
+        sf += co.compress(txt[i:i + 70000]) + co.flush(zlib.Z_SYNC_FLUSH)
+    cases.append(("syncflush", txt, sf + co.flush()))
+    r = random.Random(5)
+    binary = bytes(r.getrandbits(8) for _ in range(150000)) + txt[:100000] + bytes(r.getrandbits(3) for _ in range(100000))
+    cases.append(("binary", binary, gzip.compress(binary, 6)))
+    cases.append(("empty", b"", gzip.compress(b"", 6)))
+    cases.append(("trailing", txt[:100000], gzip.compress(txt[:100000], 6) + b"\0" * 100))
+    for name, raw, gz in cases:
+        if name != "trailing":
+            assert gzip.decompress(gz) == raw
+        path = tmp_path / (name + ".gz")
+        path.write_bytes(gz)
+        for threads, chunk in ((1, 1 << 20), (4, 4096), (8, 20000), (3, 1 << 16)):
+            rc, got = _gunzip(vglib, path, threads, chunk)
+            assert rc == 0 and got == raw, (name, threads, chunk, rc)
+    bad = bytearray(gzip.compress(txt, 6))
+    bad[len(bad) // 2] ^= 0x55
+    (tmp_path / "bad.gz").write_bytes(bad)
+    assert _gunzip(vglib, tmp_path / "bad.gz", 4, 1 << 16)[0] == -2
+    (tmp_path / "plain.txt").write_bytes(txt[:1000])
+    assert _gunzip(vglib, tmp_path / "plain.txt", 4, 1 << 16)[0] == -2
+    assert _gunzip(vglib, tmp_path / "missing.gz", 4, 1 << 16)[0] == -1

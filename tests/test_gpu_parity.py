@@ -519,6 +519,57 @@ def test_count_files_raw_fastq_parsed_on_device(ctx, vglib, oracle, tmp_path, mo
     ix.close()
 
 
+@pytest.mark.parametrize("shape", ["single", "members", "flawed", "fasta", "corrupt", "truncated"])
+def test_count_files_gzip_parallel_road(ctx, vglib, oracle, tmp_path, monkeypatch, shape):
+    """.gz input: inflated by all workers at once (vg_gzip.cpp: chunks of 4 KiB here, so block starts are searched and
+    windows resolved hundreds of times; windows of 1 MiB of text, so the carry-over between windows is exercised), then
+    the strip road.  Same counts and mReadBase as zlib + kseq (VG_GZ_PARALLEL=0, the reference's road) and as the
+    oracle -- also when the text stops being four-line FASTQ half way (flawed), is FASTA (never enters the fast road),
+    fails its CRC (corrupt: what the inflater already handed over is good, zlib takes the rest and stops where it
+    stops), or is cut short (truncated)."""
+    import zlib
+    t = helpers.tiny()
+    rng = random.Random(77)
+    recs = _fastq_text(rng, t["genome"], 30_000)
+    if shape == "flawed":
+        recs[17_000] = b"@multi line\nACGTACGTAC\nGGTTAACC\n+\nIIIIIIIIIIIIIIIIII\n"
+    if shape == "fasta":
+        recs = [b">r%d\n" % i + r.split(b"\n")[1] + b"\n" for i, r in enumerate(recs)]
+    data = b"".join(recs)
+    if shape == "members":
+        gz = b"".join(gzip.compress(b"".join(recs[i:i + 2000]), 6) for i in range(0, len(recs), 2000))
+    else:
+        gz = gzip.compress(data, 6)
+    if shape == "corrupt":
+        gz = bytearray(gz)
+        gz[len(gz) * 2 // 3] ^= 0x10
+        gz = bytes(gz)
+    if shape == "truncated":
+        gz = gz[: len(gz) * 2 // 3]
+    p = tmp_path / "reads.fq.gz"
+    p.write_bytes(gz)
+    ix = vglib.Index(ctx, t["keys"], t["k"])
+    monkeypatch.setenv("VG_GZ_PARALLEL", "0")
+    ix.begin()
+    rb0 = ix.count_files([str(p)], threads=2)
+    counts0, pos0, hits0 = ix.end()
+    if shape in ("corrupt", "truncated"):
+        assert 0 < rb0 < sum(len(r.split(b"\n")[1]) for r in recs)  # zlib reads up to the damage; kseq takes that as the end
+    else:
+        lines, nreads, bases, status = oracle.fastq_to_lines(data)
+        want, wpos, whits = oracle.count_lines(t["keys"], lines, t["k"])
+        assert rb0 == bases and (pos0, hits0) == (wpos, whits) and np.array_equal(counts0, want)
+    monkeypatch.setenv("VG_GZ_PARALLEL", "1")
+    monkeypatch.setenv("VG_GZ_CHUNK", "4096")
+    monkeypatch.setenv("VG_GZ_WINDOW_MB", "1")
+    for threads in (6, 1):
+        ix.begin()
+        rb = ix.count_files([str(p)], threads=threads)
+        counts, pos, hits = ix.end()
+        assert rb == rb0 and (pos, hits) == (pos0, hits0) and np.array_equal(counts, counts0), (shape, threads)
+    ix.close()
+
+
 @pytest.mark.parametrize("flaw", ["multiline", "short_qual", "truncated_tail", "fasta_inside", "nul"])
 def test_count_files_raw_fastq_irregular_record_falls_back(ctx, vglib, oracle, tmp_path, road, flaw):
     """An irregular record deep inside a plain FASTQ file: the blocks before it are counted on the device,

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvgb200.so")
-SOURCES = ["vg_kernels.cu", "vg_capi.cpp", "vg_comm.cpp", "vg_feeder.cpp"]
-HEADERS = ["vg_device.cuh", "vg_internal.h", "vg_host.h", os.path.join("..", "..", "include", "vgb200.h")]
+SOURCES = ["vg_kernels.cu", "vg_capi.cpp", "vg_comm.cpp", "vg_feeder.cpp", "vg_gzip.cpp"]
+HEADERS = ["vg_device.cuh", "vg_internal.h", "vg_host.h", "vg_gzip.h", os.path.join("..", "..", "include", "vgb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3", "-shared"]
 

@@ -48,6 +48,7 @@
 #include <vector>
 
 #include "../../include/vgb200.h"
+#include "vg_gzip.h"
 #include "vg_host.h"
 
 namespace {
@@ -169,6 +170,8 @@ struct RawFile {  // a plain four-line FASTQ file shipped as raw text
     uint64_t tail_from = ~0ull;          // no boundary found beyond this one: the rest goes to the kseq reader
     const char* map = nullptr;           // strip road: the file, memory-mapped
     uint64_t bad_from = ~0ull;           // strip road: first irregular record found so far (submission order)
+    bool borrowed = false;               // map is somebody else's memory (inflated gzip text): never unmapped here
+    bool ends_at_eof = true;             // the text ends where the input ends (false: a window of inflated text, more follows)
 };
 
 struct RawItem {
@@ -421,7 +424,7 @@ void block_worker(Feeder* fd, const Sinks* sinks, const std::vector<RawFile>* fi
         {   // give the block's pages back right away, here, in parallel: tearing down the whole mapping at the end costs
             // the calling thread ~20 ms per GB (the kseq fallback re-opens the file, it does not need the mapping)
             const uint64_t page = 4096, a = (it.start + page - 1) & ~(page - 1), b = it.end & ~(page - 1);
-            if (b > a) munmap((void*)(f.map + a), (size_t)(b - a));
+            if (b > a && !f.borrowed) munmap((void*)(f.map + a), (size_t)(b - a));
         }
         fd->busy_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
         {
@@ -489,17 +492,54 @@ double strip_share(bool multi) {
 }
 bool raw_enabled() { return fastq_road() != kKseq; }
 
+// Cut a mapped text into record-aligned blocks of at most a staging chunk each, `share` of them for the strip road.
+void cut_blocks(RawFile& f, vg_ctx* ctx, double share, int file_index, std::vector<RawItem>& items) {
+    const uint64_t window = std::min<uint64_t>(1u << 20, ctx->chunk_bytes / 4);
+    const uint64_t step = ctx->chunk_bytes - window - 64;
+    std::vector<char> buf;
+    f.cut.push_back(0);
+    while (f.cut.back() < f.size) {
+        const uint64_t target = f.cut.back() + step;
+        if (target >= f.size) {
+            f.cut.push_back(f.size);
+            break;
+        }
+        const int64_t b = record_boundary(f.fd, f.map, target, f.size, window, buf);
+        if (b < 0) {  // records longer than the window, or not four-line FASTQ: the host parser takes over here
+            f.tail_from = f.cut.back();
+            break;
+        }
+        f.cut.push_back((uint64_t)b);
+    }
+    for (size_t b = 0; b + 1 < f.cut.size(); ++b) {
+        const bool strip = (uint64_t)((double)(b + 1) * share) > (uint64_t)((double)b * share);  // evenly spread over the file
+        items.push_back({file_index, (uint32_t)b, f.cut[b], f.cut[b + 1], f.cut[b + 1] == f.size && f.ends_at_eof, strip});
+    }
+}
+
+// gzip input takes the parallel inflater (vg_gzip.cpp) unless VG_GZ_PARALLEL=0 (then, as in round 1: zlib on one thread per file)
+bool gz_parallel_enabled() {
+    const char* e = getenv("VG_GZ_PARALLEL");
+    return !(e && atoi(e) == 0) && raw_enabled();
+}
+
 // Route one path: plain text starting with '@' -> raw blocks (as far as record boundaries can be found),
 // anything else (gzip, FASTA, leading junk) -> the kseq reader.  false: cannot open.
 bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& raws, std::vector<RawItem>& items,
-               std::vector<KseqItem>& kseqs) {
+               std::vector<KseqItem>& kseqs, std::vector<std::string>& gzs) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) return false;
     unsigned char magic[2] = {0, 0};
     struct stat st;
-    const bool plain = raw_enabled() && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 &&
-                       pread(fd, magic, 2, 0) >= 1 && magic[0] == '@' && (uint64_t)st.st_size < (1ull << 62) &&
-                       ctx->chunk_bytes >= (64u << 10) && ctx->chunk_bytes < (1ull << 32);
+    const bool regular = raw_enabled() && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 &&
+                         pread(fd, magic, 2, 0) == 2 && (uint64_t)st.st_size < (1ull << 62) &&
+                         ctx->chunk_bytes >= (64u << 10) && ctx->chunk_bytes < (1ull << 32);
+    if (regular && magic[0] == 0x1f && magic[1] == 0x8b && gz_parallel_enabled()) {
+        close(fd);
+        gzs.push_back(path);
+        return true;
+    }
+    const bool plain = regular && magic[0] == '@';
     if (!plain) {
         close(fd);
         kseqs.push_back({path, 0});
@@ -519,29 +559,7 @@ bool plan_file(const char* path, vg_ctx* ctx, bool multi, std::vector<RawFile>& 
         madvise(m, (size_t)f.size, MADV_SEQUENTIAL);
         f.map = (const char*)m;
     }
-    const uint64_t window = std::min<uint64_t>(1u << 20, ctx->chunk_bytes / 4);
-    const uint64_t step = ctx->chunk_bytes - window - 64;
-    std::vector<char> buf;
-    f.cut.push_back(0);
-    while (f.cut.back() < f.size) {
-        const uint64_t target = f.cut.back() + step;
-        if (target >= f.size) {
-            f.cut.push_back(f.size);
-            break;
-        }
-        const int64_t b = record_boundary(fd, f.map, target, f.size, window, buf);
-        if (b < 0) {  // records longer than the window, or not four-line FASTQ: the host parser takes over here
-            f.tail_from = f.cut.back();
-            break;
-        }
-        f.cut.push_back((uint64_t)b);
-    }
-    const int fi = (int)raws.size();
-    const double share = strip_share(multi);
-    for (size_t b = 0; b + 1 < f.cut.size(); ++b) {
-        const bool strip = (uint64_t)((double)(b + 1) * share) > (uint64_t)((double)b * share);  // evenly spread over the file
-        items.push_back({fi, (uint32_t)b, f.cut[b], f.cut[b + 1], f.cut[b + 1] == f.size, strip});
-    }
+    cut_blocks(f, ctx, strip_share(multi), (int)raws.size(), items);
     raws.push_back(std::move(f));
     return true;
 }
@@ -695,6 +713,90 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
 
 }  // namespace
 
+// One gzip file: windows of inflated text (vg_gzip.cpp, all workers), each cut at its last record boundary and run
+// through the strip road like a mapped plain file; the cut-off tail is carried into the next window.  The moment
+// anything is off -- the text is not four-line FASTQ, a record fails the strip road's check, the inflater reports an
+// error -- the rest of the file, from the uncompressed offset reached, goes to the kseq reader over zlib (`kseqs`), which is
+// the reference's own road (src/fastq_kmer.cpp:74-141): same reads counted for any input.
+static int count_gz_file(const Sinks& sinks, const std::string& path, int threads, uint64_t* read_bases, std::vector<KseqItem>& kseqs) {
+    int fd = open(path.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {
+        if (fd >= 0) close(fd);
+        return vg::fail(VG_E_IO, "'%s': No such file or directory.", path.c_str());
+    }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+        kseqs.push_back({path, 0});
+        return VG_OK;
+    }
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    vg_ctx* ctx = sinks.ix[0]->ctx;
+    const char* e = getenv("VG_GZ_CHUNK");
+    const uint64_t chunk = e ? strtoull(e, nullptr, 10) : (1ull << 20);
+    const char* w = getenv("VG_GZ_WINDOW_MB");
+    const uint64_t window_bytes = (w ? strtoull(w, nullptr, 10) : 512ull) << 20;
+    const bool debug = getenv("VG_FEEDER_DEBUG") != nullptr;
+    double t_inflate = 0, t_count = 0;
+    int rc = VG_OK;
+    {
+        vg::gz::Stream stream((const uint8_t*)m, (uint64_t)st.st_size, threads, chunk);
+        vg::gz::Buffer text;
+        uint64_t done = 0;  // uncompressed offset of text.data[0]: everything in front of it has been counted
+        bool first = true;
+        for (;;) {
+            const auto t0 = std::chrono::steady_clock::now();
+            bool good = true;
+            while (good && !stream.eof() && text.size < window_bytes) good = stream.next(text, 2);
+            const auto t1 = std::chrono::steady_clock::now();
+            t_inflate += std::chrono::duration<double>(t1 - t0).count();
+            const bool eof = good && stream.eof();
+            if (first && text.size && text.data[0] != '@') good = false;  // FASTA, or not sequence data at all
+            first = false;
+            uint64_t use = text.size;
+            if (good && !eof) {  // cut at the first record boundary inside the last stretch of the window
+                const uint64_t back = std::min<uint64_t>(text.size > 1 ? text.size - 1 : 0, std::max<uint64_t>(1u << 20, ctx->chunk_bytes / 4));
+                const uint64_t from = text.size - back;
+                const int64_t b = back ? record_boundary_in((const char*)text.data + from - 1, back + 1, from - 1) : -1;
+                if (b <= 0) good = false;
+                else use = (uint64_t)b;
+            }
+            if (!good) {  // text.data[0] on (uncompressed offset `done`) has not been counted
+                if (debug && !stream.error().empty()) fprintf(stderr, "[vg_feeder] %s: %s; the rest goes through zlib\n", path.c_str(), stream.error().c_str());
+                kseqs.push_back({path, done});
+                break;
+            }
+            if (use) {
+                std::vector<RawFile> raws(1);
+                std::vector<RawItem> items;
+                RawFile& f = raws[0];
+                f.path = path;
+                f.size = use;
+                f.map = (const char*)text.data;
+                f.borrowed = true;
+                f.ends_at_eof = eof;
+                cut_blocks(f, ctx, 1.0, 0, items);
+                rc = run_feeder(sinks, {}, raws, items, nullptr, threads, read_bases);
+                t_count += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+                if (rc != VG_OK) break;
+                const uint64_t from = std::min(f.tail_from, f.bad_from);
+                if (from != ~0ull && from < use) {  // an irregular record: exact semantics from there on
+                    kseqs.push_back({path, done + from});
+                    break;
+                }
+            }
+            if (eof) break;
+            memmove(text.data, text.data + use, (size_t)(text.size - use));
+            text.size -= use;
+            done += use;
+        }
+    }
+    munmap(m, (size_t)st.st_size);
+    if (debug) fprintf(stderr, "[vg_feeder] %s: inflate %.1f ms, count %.1f ms\n", path.c_str(), t_inflate * 1e3, t_count * 1e3);
+    return rc;
+}
+
 // ixs: one index per GPU, all of them counting; the chunks of the files are dealt to them as they come.
 static int count_files_multi(const std::vector<vg_index*>& ixs, const char* const* paths, int npaths, int threads, uint64_t* read_bases) {
     Sinks sinks{ixs};
@@ -708,16 +810,26 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
     std::vector<RawItem> items;
     auto close_all = [&] {
         for (auto& f : raws) {
-            if (f.map) munmap((void*)f.map, (size_t)f.size);
+            if (f.map && !f.borrowed) munmap((void*)f.map, (size_t)f.size);
             if (f.fd >= 0) close(f.fd);
             f.map = nullptr;
             f.fd = -1;
         }
     };
+    std::vector<std::string> gzs;
     for (int i = 0; i < npaths; ++i) {
-        if (!plan_file(paths[i], ctx, multi, raws, items, kseqs)) {
+        if (!plan_file(paths[i], ctx, multi, raws, items, kseqs, gzs)) {
             close_all();
             return vg::fail(VG_E_IO, "'%s': No such file or directory.", paths[i]);
+        }
+    }
+    // gzip files first, one after the other, each inflated by all the workers; whatever the fast road cannot take of
+    // them joins the kseq list below
+    for (const std::string& g : gzs) {
+        int rc = count_gz_file(sinks, g, threads, read_bases, kseqs);
+        if (rc != VG_OK) {
+            close_all();
+            return rc;
         }
     }
     bool any_raw = false;
