@@ -127,6 +127,9 @@ int64_t vg_fastq_strip_block(const char* text, uint64_t nbytes, int last, uint8_
  * vg_gunzip_free) holds the *out_len bytes zlib would return.  0 ok, -1 cannot read the file, -2 not gzip / corrupt. */
 int vg_gunzip_parallel(const char* path, int threads, uint64_t chunk_bytes, uint8_t** out, uint64_t* out_len);
 void vg_gunzip_free(uint8_t* p);
+/* Host-only diagnostic: the CRC-32 the inflater checks gzip members with (carry-less multiply where the CPU has it);
+ * equals zlib's crc32(crc, buf, len). */
+uint32_t vg_crc32(uint32_t crc, const uint8_t* buf, uint64_t len);
 
 /* Enqueues whatever counting work is still deferred (the partitioned path accumulates k-mers of a
  * round before probing); asynchronous.  vg_count_end / _stats / _extract_device imply it. */

@@ -243,6 +243,19 @@ def test_parallel_gunzip_matches_zlib(vglib, tmp_path):
     bad[len(bad) // 2] ^= 0x55
     (tmp_path / "bad.gz").write_bytes(bad)
     assert _gunzip(vglib, tmp_path / "bad.gz", 4, 1 << 16)[0] == -2
+    for cut in (len(bad) // 3, len(bad) - 9, 30):  # truncated: must stop, not inflate the zeros behind the end for ever
+        (tmp_path / "cut.gz").write_bytes(gzip.compress(txt, 6)[:cut])
+        assert _gunzip(vglib, tmp_path / "cut.gz", 4, 1 << 16)[0] == -2
     (tmp_path / "plain.txt").write_bytes(txt[:1000])
     assert _gunzip(vglib, tmp_path / "plain.txt", 4, 1 << 16)[0] == -2
     assert _gunzip(vglib, tmp_path / "missing.gz", 4, 1 << 16)[0] == -1
+
+
+def test_crc32_matches_zlib(vglib):
+    import random
+    import zlib
+    r = random.Random(9)
+    for n in list(range(0, 200)) + [1000, 4096, 65537, 1_000_003]:
+        b = r.randbytes(n)
+        for init in (0, 0x12345678):
+            assert vglib.lib.vg_crc32(init, b, n) == zlib.crc32(b, init), (n, init)

@@ -63,6 +63,7 @@ def _load() -> ctypes.CDLL:
         "vg_fastq_strip_block": (ctypes.c_int64, [c_char_p, c_uint64, c_int, c_void_p, P(c_uint64), P(ctypes.c_int64)]),
         "vg_gunzip_parallel": (c_int, [c_char_p, c_int, c_uint64, P(c_void_p), P(c_uint64)]),
         "vg_gunzip_free": (None, [c_void_p]),
+        "vg_crc32": (c_uint32, [c_uint32, c_char_p, c_uint64]),
         "vg_index_set_flags": (c_int, [c_void_p, c_void_p]),
         "vg_count_histogram": (c_int, [c_void_p, c_void_p]),
         "vg_count_end": (c_int, [c_void_p, c_void_p, P(c_uint64), P(c_uint64)]),

@@ -741,8 +741,12 @@ static int count_gz_file(const Sinks& sinks, const std::string& path, int thread
     double t_inflate = 0, t_count = 0;
     int rc = VG_OK;
     {
-        vg::gz::Stream stream((const uint8_t*)m, (uint64_t)st.st_size, threads, chunk);
-        vg::gz::Buffer text;
+        // working memory kept from file to file and call to call (per calling thread): the inflated window and the workers'
+        // symbol buffers -- mapping and faulting in ~1 GB afresh per file costs as much as inflating it
+        static thread_local vg::gz::Scratch scratch;
+        static thread_local vg::gz::Buffer text;
+        text.size = 0;
+        vg::gz::Stream stream((const uint8_t*)m, (uint64_t)st.st_size, threads, chunk, &scratch);
         uint64_t done = 0;  // uncompressed offset of text.data[0]: everything in front of it has been counted
         bool first = true;
         for (;;) {

@@ -8,6 +8,8 @@
 namespace vg {
 namespace gz {
 
+uint32_t crc32_fast(uint32_t crc, const uint8_t* buf, uint64_t len);  // == zlib's crc32
+
 // a growable byte buffer that does not zero what it grows by (std::vector::resize does)
 struct Buffer {
     uint8_t* data = nullptr;
@@ -27,10 +29,25 @@ struct Buffer {
     }
 };
 
+// Working memory of the inflater that is worth keeping from one file to the next.
+class Scratch {
+   public:
+    Scratch();
+    ~Scratch();
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+
+   private:
+    friend class Stream;
+    struct Pool;
+    Pool* pool_;
+};
+
 class Stream {
    public:
-    // data / size: the whole .gz file (it must stay mapped); chunk_bytes: compressed bytes per worker and round
-    Stream(const uint8_t* data, uint64_t size, int threads, uint64_t chunk_bytes);
+    // data / size: the whole .gz file (it must stay mapped); chunk_bytes: compressed bytes per worker and round;
+    // scratch (optional): working memory to reuse, not shared with another live Stream
+    Stream(const uint8_t* data, uint64_t size, int threads, uint64_t chunk_bytes, Scratch* scratch = nullptr);
     ~Stream();
     Stream(const Stream&) = delete;
     Stream& operator=(const Stream&) = delete;
