@@ -713,91 +713,213 @@ int run_feeder(const Sinks& sinks, const std::vector<KseqItem>& kseqs, std::vect
 
 }  // namespace
 
-// One gzip file: windows of inflated text (vg_gzip.cpp, all workers), each cut at its last record boundary and run
-// through the strip road like a mapped plain file; the cut-off tail is carried into the next window.  The moment
-// anything is off -- the text is not four-line FASTQ, a record fails the strip road's check, the inflater reports an
-// error -- the rest of the file, from the uncompressed offset reached, goes to the kseq reader over zlib (`kseqs`), which is
-// the reference's own road (src/fastq_kmer.cpp:74-141): same reads counted for any input.
-static int count_gz_file(const Sinks& sinks, const std::string& path, int threads, uint64_t* read_bases, std::vector<KseqItem>& kseqs) {
-    int fd = open(path.c_str(), O_RDONLY);
-    struct stat st;
-    if (fd < 0 || fstat(fd, &st) != 0) {
+// gzip files: windows of inflated text (vg_gzip.cpp, all workers), each cut at its last record boundary and run through
+// the strip road like a mapped plain file; the cut-off tail is carried into the next window.  A helper thread inflates
+// the next window (of this file or the next) while the calling thread counts the current one.  The moment anything is
+// off -- the text is not four-line FASTQ, a record fails the strip road's check, the inflater reports an error -- the
+// rest of that file, from the uncompressed offset reached, goes to the kseq reader over zlib (`kseqs`), which is the
+// reference's own road (src/fastq_kmer.cpp:74-141): same reads counted for any input.
+namespace {
+struct GzWindow {
+    vg::gz::Buffer* text = nullptr;  // [0, use) is this window; null: the producer is done
+    uint64_t use = 0;
+    uint64_t done = 0;               // uncompressed offset of text->data[0]
+    bool eof = false;                // the file ends with this window
+    bool good = true;                // false: nothing of this window is to be counted; zlib takes over at `done`
+    int file = -1;
+};
+struct GzPipe {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<GzWindow> ready;
+    std::deque<vg::gz::Buffer*> free_bufs;
+    std::vector<char> stopped;       // per file: the consumer gave up on the fast road
+    bool abort = false;
+    double inflate_s = 0;
+    vg::gz::Buffer* take() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return abort || !free_bufs.empty(); });
+        if (abort) return nullptr;
+        vg::gz::Buffer* b = free_bufs.front();
+        free_bufs.pop_front();
+        return b;
+    }
+    void give(vg::gz::Buffer* b) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            free_bufs.push_back(b);
+        }
+        cv.notify_all();
+    }
+    void push(const GzWindow& w) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ready.push_back(w);
+        }
+        cv.notify_all();
+    }
+    bool is_stopped(int f) {
+        std::lock_guard<std::mutex> lk(mu);
+        return abort || stopped[(size_t)f] != 0;
+    }
+};
+// working memory kept from call to call (per calling thread): the inflated windows and the workers' symbol buffers --
+// mapping and faulting in ~1 GB afresh per file costs as much as inflating it
+struct GzArena {
+    vg::gz::Scratch scratch;
+    vg::gz::Buffer bufs[2];
+};
+
+void gz_produce(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* paths, int threads, uint64_t chunk, uint64_t window_bytes,
+                uint64_t boundary_back, bool debug);
+void gz_producer(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* paths, int threads, uint64_t chunk, uint64_t window_bytes,
+                 uint64_t boundary_back, bool debug) {
+    gz_produce(pipe, arena, paths, threads, chunk, window_bytes, boundary_back, debug);
+    pipe->push(GzWindow{});  // whatever happened: the consumer waits for this
+}
+void gz_produce(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* paths, int threads, uint64_t chunk, uint64_t window_bytes,
+                uint64_t boundary_back, bool debug) {
+    for (int fi = 0; fi < (int)paths->size(); ++fi) {
+        const std::string& path = (*paths)[(size_t)fi];
+        int fd = open(path.c_str(), O_RDONLY);
+        struct stat st;
+        void* m = MAP_FAILED;
+        if (fd >= 0 && fstat(fd, &st) == 0) m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
         if (fd >= 0) close(fd);
-        return vg::fail(VG_E_IO, "'%s': No such file or directory.", path.c_str());
+        GzWindow w;
+        w.file = fi;
+        if (m == MAP_FAILED) {  // the kseq road reports what is wrong with it
+            w.good = false;
+            w.text = nullptr;
+            vg::gz::Buffer* b = pipe->take();
+            if (!b) return;
+            b->size = 0;
+            w.text = b;
+            pipe->push(w);
+            continue;
+        }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        {
+            vg::gz::Stream stream((const uint8_t*)m, (uint64_t)st.st_size, threads, chunk, &arena->scratch);
+            vg::gz::Buffer* cur = pipe->take();
+            if (!cur) {
+                munmap(m, (size_t)st.st_size);
+                return;
+            }
+            cur->size = 0;
+            uint64_t done = 0;
+            bool first = true;
+            for (;;) {
+                if (pipe->is_stopped(fi)) {
+                    pipe->give(cur);
+                    break;
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                bool good = true;
+                while (good && !stream.eof() && cur->size < window_bytes) good = stream.next(*cur, 2);
+                pipe->inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                const bool eof = good && stream.eof();
+                if (first && cur->size && cur->data[0] != '@') good = false;  // FASTA, or not sequence data at all
+                first = false;
+                uint64_t use = cur->size;
+                if (good && !eof) {  // cut at the first record boundary inside the last stretch of the window
+                    const uint64_t back = std::min<uint64_t>(cur->size > 1 ? cur->size - 1 : 0, boundary_back);
+                    const uint64_t from = cur->size - back;
+                    const int64_t b = back ? record_boundary_in((const char*)cur->data + from - 1, back + 1, from - 1) : -1;
+                    if (b <= 0) good = false;
+                    else use = (uint64_t)b;
+                }
+                if (!good && debug && !stream.error().empty())
+                    fprintf(stderr, "[vg_feeder] %s: %s; the rest goes through zlib\n", path.c_str(), stream.error().c_str());
+                vg::gz::Buffer* nxt = nullptr;
+                if (good && !eof) {  // the tail moves to the front of the next window
+                    nxt = pipe->take();
+                    if (!nxt || !nxt->reserve(cur->size - use + 1)) {
+                        if (nxt) pipe->give(nxt);
+                        nxt = nullptr;
+                        good = false;
+                    } else {
+                        memcpy(nxt->data, cur->data + use, (size_t)(cur->size - use));
+                        nxt->size = cur->size - use;
+                    }
+                }
+                w.text = cur;
+                w.use = use;
+                w.done = done;
+                w.eof = eof;
+                w.good = good;
+                pipe->push(w);
+                if (!good || eof) break;
+                done += use;
+                cur = nxt;
+            }
+        }
+        munmap(m, (size_t)st.st_size);
     }
-    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
-    close(fd);
-    if (m == MAP_FAILED) {
-        kseqs.push_back({path, 0});
-        return VG_OK;
-    }
-    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+}
+}  // namespace
+
+static int count_gz_files(const Sinks& sinks, const std::vector<std::string>& paths, int threads, uint64_t* read_bases,
+                          std::vector<KseqItem>& kseqs) {
     vg_ctx* ctx = sinks.ix[0]->ctx;
     const char* e = getenv("VG_GZ_CHUNK");
     const uint64_t chunk = e ? strtoull(e, nullptr, 10) : (1ull << 20);
-    const char* w = getenv("VG_GZ_WINDOW_MB");
-    const uint64_t window_bytes = (w ? strtoull(w, nullptr, 10) : 512ull) << 20;
+    const char* wmb = getenv("VG_GZ_WINDOW_MB");
+    const uint64_t window_bytes = (wmb ? strtoull(wmb, nullptr, 10) : 512ull) << 20;
     const bool debug = getenv("VG_FEEDER_DEBUG") != nullptr;
-    double t_inflate = 0, t_count = 0;
+    static thread_local GzArena arena;
+    GzPipe pipe;
+    pipe.stopped.assign(paths.size(), 0);
+    for (auto& b : arena.bufs) pipe.free_bufs.push_back(&b);
+    std::thread producer(gz_producer, &pipe, &arena, &paths, threads, chunk, window_bytes,
+                         std::max<uint64_t>(1u << 20, ctx->chunk_bytes / 4), debug);
+    double t_count = 0;
     int rc = VG_OK;
-    {
-        // working memory kept from file to file and call to call (per calling thread): the inflated window and the workers'
-        // symbol buffers -- mapping and faulting in ~1 GB afresh per file costs as much as inflating it
-        static thread_local vg::gz::Scratch scratch;
-        static thread_local vg::gz::Buffer text;
-        text.size = 0;
-        vg::gz::Stream stream((const uint8_t*)m, (uint64_t)st.st_size, threads, chunk, &scratch);
-        uint64_t done = 0;  // uncompressed offset of text.data[0]: everything in front of it has been counted
-        bool first = true;
-        for (;;) {
-            const auto t0 = std::chrono::steady_clock::now();
-            bool good = true;
-            while (good && !stream.eof() && text.size < window_bytes) good = stream.next(text, 2);
-            const auto t1 = std::chrono::steady_clock::now();
-            t_inflate += std::chrono::duration<double>(t1 - t0).count();
-            const bool eof = good && stream.eof();
-            if (first && text.size && text.data[0] != '@') good = false;  // FASTA, or not sequence data at all
-            first = false;
-            uint64_t use = text.size;
-            if (good && !eof) {  // cut at the first record boundary inside the last stretch of the window
-                const uint64_t back = std::min<uint64_t>(text.size > 1 ? text.size - 1 : 0, std::max<uint64_t>(1u << 20, ctx->chunk_bytes / 4));
-                const uint64_t from = text.size - back;
-                const int64_t b = back ? record_boundary_in((const char*)text.data + from - 1, back + 1, from - 1) : -1;
-                if (b <= 0) good = false;
-                else use = (uint64_t)b;
-            }
-            if (!good) {  // text.data[0] on (uncompressed offset `done`) has not been counted
-                if (debug && !stream.error().empty()) fprintf(stderr, "[vg_feeder] %s: %s; the rest goes through zlib\n", path.c_str(), stream.error().c_str());
-                kseqs.push_back({path, done});
-                break;
-            }
-            if (use) {
+    for (;;) {
+        GzWindow w;
+        {
+            std::unique_lock<std::mutex> lk(pipe.mu);
+            pipe.cv.wait(lk, [&] { return !pipe.ready.empty(); });
+            w = pipe.ready.front();
+            pipe.ready.pop_front();
+        }
+        if (!w.text) break;
+        const std::string& path = paths[(size_t)w.file];
+        char& stopped = pipe.stopped[(size_t)w.file];
+        if (rc == VG_OK && !stopped) {
+            if (!w.good) {  // text->data[0] on (uncompressed offset `done`) has not been counted
+                kseqs.push_back({path, w.done});
+                std::lock_guard<std::mutex> lk(pipe.mu);
+                stopped = 1;
+            } else if (w.use) {
+                const auto t1 = std::chrono::steady_clock::now();
                 std::vector<RawFile> raws(1);
                 std::vector<RawItem> items;
                 RawFile& f = raws[0];
                 f.path = path;
-                f.size = use;
-                f.map = (const char*)text.data;
+                f.size = w.use;
+                f.map = (const char*)w.text->data;
                 f.borrowed = true;
-                f.ends_at_eof = eof;
+                f.ends_at_eof = w.eof;
                 cut_blocks(f, ctx, 1.0, 0, items);
                 rc = run_feeder(sinks, {}, raws, items, nullptr, threads, read_bases);
                 t_count += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-                if (rc != VG_OK) break;
                 const uint64_t from = std::min(f.tail_from, f.bad_from);
-                if (from != ~0ull && from < use) {  // an irregular record: exact semantics from there on
-                    kseqs.push_back({path, done + from});
-                    break;
+                if (rc == VG_OK && from != ~0ull && from < w.use) {  // an irregular record: exact semantics from there on
+                    kseqs.push_back({path, w.done + from});
+                    std::lock_guard<std::mutex> lk(pipe.mu);
+                    stopped = 1;
+                }
+                if (rc != VG_OK) {
+                    std::lock_guard<std::mutex> lk(pipe.mu);
+                    pipe.abort = true;
                 }
             }
-            if (eof) break;
-            memmove(text.data, text.data + use, (size_t)(text.size - use));
-            text.size -= use;
-            done += use;
         }
+        pipe.give(w.text);
     }
-    munmap(m, (size_t)st.st_size);
-    if (debug) fprintf(stderr, "[vg_feeder] %s: inflate %.1f ms, count %.1f ms\n", path.c_str(), t_inflate * 1e3, t_count * 1e3);
+    producer.join();
+    if (debug) fprintf(stderr, "[vg_feeder] %zu gzip file(s): inflate %.1f ms (helper thread), count %.1f ms\n", paths.size(), pipe.inflate_s * 1e3, t_count * 1e3);
     return rc;
 }
 
@@ -829,8 +951,8 @@ static int count_files_multi(const std::vector<vg_index*>& ixs, const char* cons
     }
     // gzip files first, one after the other, each inflated by all the workers; whatever the fast road cannot take of
     // them joins the kseq list below
-    for (const std::string& g : gzs) {
-        int rc = count_gz_file(sinks, g, threads, read_bases, kseqs);
+    if (!gzs.empty()) {
+        int rc = count_gz_files(sinks, gzs, threads, read_bases, kseqs);
         if (rc != VG_OK) {
             close_all();
             return rc;
