@@ -422,8 +422,6 @@ struct Chunk {
     uint64_t first_byte = 0;          // the chunk's share of the file starts here ...
     uint64_t start_bit = ~0ull;       // ... and this is where a block starts (searched, or known for the first one)
     bool fresh_member = false;        // start_bit is the first block of a member: nothing can be referenced in front of it
-    uint64_t search_end = 0;          // the search covers bits [first_byte * 8, search_end)
-    std::atomic<int> searched{2};     // 0 not yet, 1 somebody is at it, 2 start_bit is final
     // filled by the worker
     uint16_t* sym = nullptr;
     uint64_t nsym = 0, cap = 0;
@@ -443,7 +441,6 @@ struct Chunk {
     void reset() {  // for the next round; the symbol buffer (and the pages behind it) are kept
         start_bit = ~0ull;
         fresh_member = false;
-        searched.store(2);
         nsym = 0;
         end_bit = 0;
         next = -1;
@@ -470,29 +467,10 @@ inline bool grow(Chunk& c, uint64_t need) {
 
 enum { kErrNone = 0, kErrCorrupt = 1, kErrMemory = 2 };
 
-// The first plausible block start of a chunk, by whoever needs it first: the worker that is about to inflate the chunk, or a
-// predecessor that has inflated its way into the chunk's bytes and must know whether it has arrived.
-void ensure_searched(const uint8_t* data, uint64_t size, Chunk& c, Tables& scratch) {
-    int state = c.searched.load(std::memory_order_acquire);
-    if (state == 2) return;
-    int expected = 0;
-    if (state == 0 && c.searched.compare_exchange_strong(expected, 1, std::memory_order_acq_rel)) {
-        for (uint64_t bit = c.first_byte * 8; bit < c.search_end; ++bit)
-            if (plausible_block_start(data, size, bit, scratch)) {
-                c.start_bit = bit;
-                break;
-            }
-        c.searched.store(2, std::memory_order_release);
-        return;
-    }
-    while (c.searched.load(std::memory_order_acquire) != 2) std::this_thread::yield();  // its searcher is running right now
-}
-
 // Inflate from c.start_bit until a block boundary that is the start of a later chunk (targets: ascending start bits of the
 // chunks after this one, ~0 where none was found), or -- past the last target -- the first boundary at or after
 // `stop_byte`, or the end of the data.
-void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vector<Chunk*>& later, uint64_t stop_byte, Tables& t,
-                   Tables& search_tables) {
+void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vector<Chunk*>& later, uint64_t stop_byte, Tables& t) {
     Bits b{data, size, 0, 0, 0};
     b.seek(c.start_bit);
     size_t ti = 0;
@@ -504,17 +482,8 @@ void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vect
     for (;;) {
         // ---- at a block boundary ----
         const uint64_t here = b.bitpos();
-        bool arrived = false;
-        while (ti < later.size() && later[ti]->first_byte * 8 <= here) {  // (a start lies at or behind its chunk's first byte)
-            ensure_searched(data, size, *later[ti], search_tables);
-            if (later[ti]->start_bit == here) {
-                arrived = true;
-                break;
-            }
-            if (later[ti]->start_bit != ~0ull && later[ti]->start_bit > here) break;
-            ++ti;  // no start found there, or one that nobody arrives at
-        }
-        if (arrived && c.nsym > 0) {
+        while (ti < later.size() && (later[ti]->start_bit == ~0ull || later[ti]->start_bit < here)) ++ti;  // starts nobody arrives at
+        if (ti < later.size() && later[ti]->start_bit == here && c.nsym > 0) {
             c.end_bit = here;
             c.next = (int)ti;  // index into `later`
             break;
@@ -714,39 +683,44 @@ bool Stream::next(Buffer& out, int per_thread) {
     chunks[0]->fresh_member = s.fresh;
     const int n = (int)chunks.size();
     const int nthreads = std::min(s.threads, n);
+    auto parallel = [&](auto fn) {
+        std::atomic<int> next{0};
+        std::vector<std::thread> pool;
+        auto body = [&] {
+            Tables* t = new Tables;
+            for (int i; (i = next.fetch_add(1)) < n;) fn(i, *t);
+            delete t;
+        };
+        for (int w = 1; w < nthreads; ++w) pool.emplace_back(body);
+        body();
+        for (auto& th : pool) th.join();
+    };
     const bool dbg = getenv("VG_GZ_DEBUG") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
     const auto t0 = now();
-    // 1 + 2. where can the chunks after the first start, and inflate from there
-    for (int i = 1; i < n; ++i) {
-        chunks[(size_t)i]->search_end = std::min(s.size, chunks[(size_t)i]->first_byte + s.chunk_bytes) * 8;
-        chunks[(size_t)i]->searched.store(0);
-    }
-    const auto t1 = now();
-    {
-        std::atomic<int> next{0};
-        std::vector<std::thread> pool;
-        auto body = [&] {
-            Tables* t = new Tables;
-            Tables* ts = new Tables;
-            for (int i; (i = next.fetch_add(1)) < n;) {
-                Chunk& c = *chunks[(size_t)i];
-                ensure_searched(s.data, s.size, c, *ts);
-                if (c.start_bit == ~0ull) continue;
-                std::vector<Chunk*> later(chunks.begin() + i + 1, chunks.end());
-                inflate_chunk(s.data, s.size, c, later, stop_byte, *t, *ts);
-                if (c.next >= 0) c.next += i + 1;
+    // 1. where can the chunks after the first start?
+    parallel([&](int i, Tables& t) {
+        if (i == 0) return;
+        Chunk& c = *chunks[(size_t)i];
+        const uint64_t lo = c.first_byte * 8, hi = std::min(s.size, c.first_byte + s.chunk_bytes) * 8;
+        for (uint64_t bit = lo; bit < hi; ++bit)
+            if (plausible_block_start(s.data, s.size, bit, t)) {
+                c.start_bit = bit;
+                break;
             }
-            delete t;
-            delete ts;
-        };
-        for (int w = 1; w < nthreads; ++w) pool.emplace_back(body);
-        body();
-        for (auto& th : pool) th.join();
-    }
+    });
+    const auto t1 = now();
+    // 2. inflate
+    parallel([&](int i, Tables& t) {
+        Chunk& c = *chunks[(size_t)i];
+        if (c.start_bit == ~0ull) return;
+        std::vector<Chunk*> later(chunks.begin() + i + 1, chunks.end());
+        inflate_chunk(s.data, s.size, c, later, stop_byte, t);
+        if (c.next >= 0) c.next += i + 1;
+    });
     const auto t2 = now();
     // 3. follow the chain from the first chunk: windows, output offsets
     bool ok = true;
@@ -857,7 +831,7 @@ bool Stream::next(Buffer& out, int per_thread) {
         if (!ok) out.size = base;
     }
     if (dbg)
-        fprintf(stderr, "[vg_gzip] round of %d chunks (%zu in chain): set-up %.1f ms, search + inflate %.1f ms, chain %.1f ms, resolve + crc %.1f ms, %.1f MB out\n",
+        fprintf(stderr, "[vg_gzip] round of %d chunks (%zu in chain): search %.1f ms, inflate %.1f ms, chain %.1f ms, resolve + crc %.1f ms, %.1f MB out\n",
                 n, chain.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()), total / 1e6);
     return ok;
 }
