@@ -709,6 +709,16 @@ def test_cbf_vs_oracle_multi_chromosome(ctx, vglib, oracle, k):
     chroms = [synth.make_genome(n, seed=k * 10 + i) for i, n in enumerate((70_000, 4097, 30, 150_001))]
     chroms[0][1000:1100] = ord("N")
     chroms[3][5000:9000] = chroms[0][2000:6000]
+    # what a real chromosome has and a read does not: a long run of N with no newline anywhere (the even-k state machine
+    # used to walk every such run from every lane inside it), single N next to tandem repeats, soft-masked lower case
+    special = synth.make_genome(400_000, seed=k + 77)
+    special[50_000:300_000] = ord("N")
+    special[300_100:300_400] = np.frombuffer(b"AT" * 150, dtype=np.uint8)
+    special[300_250] = ord("N")
+    special[310_000:310_060] = np.frombuffer(b"ACGT" * 15, dtype=np.uint8)
+    special[320_000:330_000] |= 0x20
+    special[325_000] = ord("n")
+    chroms.append(special)
     n = sum(len(c) for c in chroms) - k + 1
     m = int(oracle.lib.vgo_cbf_size(n, 0.01))
     seeds = rng.integers(1, 2**63, size=7, dtype=np.uint64)

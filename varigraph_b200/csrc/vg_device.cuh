@@ -630,6 +630,14 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
             cnt = (e & 4u) ? cnt + 1 : 0;
             --p;
             if (cnt == need) { start = p; break; }
+            if (!(e & 4u) && (p & 7) == 0) {
+                // inside a run of N (a chromosome's centromere is megabases of them): eight at a time
+                while (p - 8 >= c.lo) {
+                    const uint64_t w = *reinterpret_cast<const uint64_t*>(c.al + p - 8);
+                    if (w != 0x4E4E4E4E4E4E4E4EULL && w != 0x6E6E6E6E6E6E6E6EULL) break;
+                    p -= 8;
+                }
+            }
         }
         st.fwd = st.rev = 0;
         st.run = 0;
@@ -937,6 +945,21 @@ struct EvenEncoder : OddEncoder {
         pos = 0;
     }
 };
+#endif
+
+#ifndef VG_ROLLING_ENCODER
+// Whole segment at once, even k (lut built with hard_flags).
+__device__ __forceinline__ uint32_t encode_keys_even(const Chunk& c, int64_t off, const KmerParams& kp,
+                                                     const uint8_t* lut, uint64_t (&keys)[16]) {
+    EvenEncoder enc;
+    enc.init(c, off, kp, lut);
+    return enc.next<16>(kp, keys);
+}
+#else
+__device__ __forceinline__ uint32_t encode_keys_even(const Chunk& c, int64_t off, const KmerParams& kp,
+                                                     const uint8_t* lut, uint64_t (&keys)[16]) {
+    return encode_keys_any(c, off, kp, lut, keys);
+}
 #endif
 
 // which encoder a kernel instantiation runs

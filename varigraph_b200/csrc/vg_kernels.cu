@@ -1203,14 +1203,16 @@ __global__ void histogram_kernel(const uint8_t* __restrict__ counts, const uint8
 // per-position keys (test hook + synthetic index construction for bench.py)
 // out[p] = (hash << 8 | k) for the k-mer ENDING at byte p, or ~0.
 // ---------------------------------------------------------------------------
-template <bool kOdd>
+template <int kEnc>
 __global__ void __launch_bounds__(kCtaThreads) positions_kernel(KmerParams kp, Chunk c, int64_t ntiles, uint64_t* out) {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
-    lut_init(lut);
+    lut_init(lut, kEnc == kEncEven);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = t * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         uint64_t keys[16];
-        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, lut, keys) : encode_keys_any(c, off, kp, lut, keys);
+        uint32_t emit = kEnc == kEncOdd ? encode_keys_odd(c, off, kp, lut, keys)
+                        : kEnc == kEncEven ? encode_keys_even(c, off, kp, lut, keys)
+                                           : encode_keys_any(c, off, kp, lut, keys);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             int64_t p = off + j;
@@ -1235,17 +1237,22 @@ __device__ __forceinline__ void cell_sat_inc(uint8_t* cells, uint64_t pos) {
     }
 }
 
-template <bool kOdd>
+// Even k through the window encoder as well: the byte-wise state machine walks back to the last newline, and a chromosome
+// has none -- every lane inside a multi-Mb run of N walked the whole run (quadratic); now only the few lanes at the
+// end of such a run do, once.
+template <int kEnc>
 __global__ void __launch_bounds__(kCtaThreads) cbf_add_kernel(CbfView cbf, KmerParams kp, Chunk c, int64_t first_tile,
                                                             int64_t ntiles, unsigned long long* added) {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
-    lut_init(lut);
+    lut_init(lut, kEnc == kEncEven);
     FastMod64 fm{cbf.magic_hi, cbf.magic_lo, cbf.m};
     uint32_t n = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int64_t off = (first_tile + t) * kTileBytes + (int64_t)threadIdx.x * kSegBytes;
         uint64_t keys[16];
-        uint32_t emit = kOdd ? encode_keys_odd(c, off, kp, lut, keys) : encode_keys_any(c, off, kp, lut, keys);
+        uint32_t emit = kEnc == kEncOdd ? encode_keys_odd(c, off, kp, lut, keys)
+                        : kEnc == kEncEven ? encode_keys_even(c, off, kp, lut, keys)
+                                           : encode_keys_any(c, off, kp, lut, keys);
         n += __popc(emit);
         // (Loading a k-mer's seven cells together before one CAS each was tried: 2.03 vs 2.76 G k-mers/s -- the rolled
         // loop it needs keeps fewer k-mers in flight per lane than this unrolled one.)
@@ -1854,8 +1861,9 @@ cudaError_t launch_positions(uint32_t k, const uint8_t* d_bases, uint64_t nbytes
     int64_t ntiles = tiles_for(c);
     KmerParams kp{k, (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1)};
     int64_t grid = ntiles < 148 * 8 ? ntiles : 148 * 8;
-    if (k & 1) positions_kernel<true><<<(unsigned)grid, kCtaThreads, 0, s>>>(kp, c, ntiles, d_out);
-    else positions_kernel<false><<<(unsigned)grid, kCtaThreads, 0, s>>>(kp, c, ntiles, d_out);
+    if (k & 1) positions_kernel<kEncOdd><<<(unsigned)grid, kCtaThreads, 0, s>>>(kp, c, ntiles, d_out);
+    else if (even_window()) positions_kernel<kEncEven><<<(unsigned)grid, kCtaThreads, 0, s>>>(kp, c, ntiles, d_out);
+    else positions_kernel<kEncAny><<<(unsigned)grid, kCtaThreads, 0, s>>>(kp, c, ntiles, d_out);
     return cudaGetLastError();
 }
 
@@ -1868,8 +1876,9 @@ cudaError_t launch_cbf_add(const CbfView& cbf, uint32_t k, const uint8_t* d_base
     KmerParams kp{k, (1ULL << (2 * k)) - 1};
     int64_t grid = (int64_t)nsm * 8;
     if (grid > ntiles) grid = ntiles;
-    if (k & 1) cbf_add_kernel<true><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
-    else cbf_add_kernel<false><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
+    if (k & 1) cbf_add_kernel<kEncOdd><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
+    else if (even_window()) cbf_add_kernel<kEncEven><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
+    else cbf_add_kernel<kEncAny><<<(unsigned)grid, kCtaThreads, 0, s>>>(cbf, kp, c, first_tile, ntiles, d_added);
     return cudaGetLastError();
 }
 
