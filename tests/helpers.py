@@ -76,9 +76,9 @@ def free_port() -> int:
 
 
 def spawn_ranks(fn, make_args, nprocs: int, timeout_s: float = 240.0, attempts: int = 2) -> None:
-    """torch.multiprocessing.spawn with a deadline and one retry on a fresh port: a rendezvous that never completes (a
-    port grabbed between free_port() and the bind, a straggler from an earlier run) must fail or recover, not hang
-    the suite.  make_args(port) -> the argument tuple of fn after the rank."""
+    """torch.multiprocessing.spawn with a deadline and one retry on a fresh port: a rendezvous that never completes or
+    times out (a port grabbed between free_port() and the bind, a straggler from an earlier run) must fail or recover,
+    not hang the suite; a real failure fails twice.  make_args(port) -> the argument tuple of fn after the rank."""
     import time
 
     import torch.multiprocessing as mp
@@ -98,6 +98,4 @@ def spawn_ranks(fn, make_args, nprocs: int, timeout_s: float = 240.0, attempts: 
                     pr.terminate()
             for pr in ctx.processes:
                 pr.join(10)
-            if not isinstance(ex, TimeoutError):
-                raise
     raise last
