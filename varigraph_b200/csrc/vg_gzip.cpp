@@ -527,12 +527,35 @@ void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vect
             }
             const uint32_t* lt = tt->lit;
             const uint32_t* dt = tt->dist;
+            // the hot loop works on locals (the chunk's fields are written back behind it)
+            uint16_t* sym = c.sym;
+            uint64_t n = c.nsym, cap = c.cap;
+            uint32_t min_marker = c.min_marker;
+            const uint64_t pos_limit = size + 16;
             bool done = false;
             while (!done) {
-                if (c.nsym + 258 + 8 > c.cap && !grow(c, 258 + 8)) { fail(kErrMemory); break; }
+                if (n + 258 + 16 > cap) {
+                    c.nsym = n;
+                    if (!grow(c, 258 + 16)) { fail(kErrMemory); break; }
+                    sym = c.sym;
+                    cap = c.cap;
+                }
                 b.refill();
-                if (b.pos > size + 16) { fail(kErrCorrupt); break; }  // reading zeros past the end of a truncated file
+                if (b.pos > pos_limit) { fail(kErrCorrupt); break; }  // reading zeros past the end of a truncated file
                 uint32_t e = lt[b.peek(kLitBits)];
+                if (e_kind(e) == kLiteral) {  // up to three literals from one refill (>= 56 bits: 3 x 10 fit)
+                    b.drop((int)e_bits(e));
+                    sym[n++] = (uint16_t)e_val(e);
+                    e = lt[b.peek(kLitBits)];
+                    if (e_kind(e) != kLiteral) continue;
+                    b.drop((int)e_bits(e));
+                    sym[n++] = (uint16_t)e_val(e);
+                    e = lt[b.peek(kLitBits)];
+                    if (e_kind(e) != kLiteral) continue;
+                    b.drop((int)e_bits(e));
+                    sym[n++] = (uint16_t)e_val(e);
+                    continue;
+                }
                 if (e_kind(e) == kSub) {
                     b.drop(kLitBits);
                     e = lt[e_val(e) + b.peek((int)e_extra(e))];
@@ -540,13 +563,7 @@ void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vect
                 b.drop((int)e_bits(e));
                 const uint32_t kind = e_kind(e);
                 if (kind == kLiteral) {
-                    c.sym[c.nsym++] = (uint16_t)e_val(e);
-                    // a second literal from the same refill (>= 41 bits are left: two more codes fit)
-                    uint32_t e2 = lt[b.peek(kLitBits)];
-                    if (e_kind(e2) == kLiteral) {
-                        b.drop((int)e_bits(e2));
-                        c.sym[c.nsym++] = (uint16_t)e_val(e2);
-                    }
+                    sym[n++] = (uint16_t)e_val(e);
                     continue;
                 }
                 if (kind == kLength) {
@@ -560,27 +577,32 @@ void inflate_chunk(const uint8_t* data, uint64_t size, Chunk& c, const std::vect
                     b.drop((int)e_bits(d));
                     if (b.cnt < 13) b.refill();
                     const uint32_t dist = e_val(d) + b.take((int)e_extra(d));
-                    const int64_t src = (int64_t)c.nsym - (int64_t)dist;
+                    const int64_t src = (int64_t)n - (int64_t)dist;
                     if (src < floor) { fail(kErrCorrupt); break; }
-                    uint16_t* out = c.sym + c.nsym;
+                    uint16_t* out = sym + n;
                     if (src >= 0) {
-                        const uint16_t* in = c.sym + src;
-                        if (dist >= len) memcpy(out, in, len * sizeof(uint16_t));
-                        else for (uint32_t i = 0; i < len; ++i) out[i] = in[i];
+                        const uint16_t* in = sym + src;
+                        if (dist >= 8) {  // eight symbols at a time; may write up to 7 past the match (the buffer has the room)
+                            for (uint32_t i = 0; i < len; i += 8) memcpy(out + i, in + i, 16);
+                        } else {
+                            for (uint32_t i = 0; i < len; ++i) out[i] = in[i];
+                        }
                     } else {
-                        if ((uint32_t)(32768 + src) < c.min_marker) c.min_marker = (uint32_t)(32768 + src);
+                        if ((uint32_t)(32768 + src) < min_marker) min_marker = (uint32_t)(32768 + src);
                         for (uint32_t i = 0; i < len; ++i) {
-                            const int64_t s = src + (int64_t)i;
-                            out[i] = s >= 0 ? c.sym[s] : (uint16_t)(0x8000u | (uint32_t)(32768 + s));
+                            const int64_t sp = src + (int64_t)i;
+                            out[i] = sp >= 0 ? sym[sp] : (uint16_t)(0x8000u | (uint32_t)(32768 + sp));
                         }
                     }
-                    c.nsym += len;
+                    n += len;
                     continue;
                 }
                 if (kind == kEob) { done = true; continue; }
                 fail(kErrCorrupt);
                 break;
             }
+            c.nsym = n;
+            c.min_marker = min_marker;
             if (c.err) break;
         }
         if (b.overrun()) { fail(kErrCorrupt); break; }
