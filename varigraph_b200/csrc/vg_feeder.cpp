@@ -779,6 +779,10 @@ void gz_producer(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* p
 }
 void gz_produce(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* paths, int threads, uint64_t chunk, uint64_t window_bytes,
                 uint64_t boundary_back, bool debug) {
+    // chunks per worker and round: several, so that the workers' loads even out (a chunk of text-like input takes 2-3x as
+    // long as one of low-entropy qualities) and a file's last round is not a short one
+    const char* pe = getenv("VG_GZ_PER_THREAD");
+    const int per_thread = pe && atoi(pe) > 0 ? atoi(pe) : 4;
     for (int fi = 0; fi < (int)paths->size(); ++fi) {
         const std::string& path = (*paths)[(size_t)fi];
         int fd = open(path.c_str(), O_RDONLY);
@@ -816,7 +820,7 @@ void gz_produce(GzPipe* pipe, GzArena* arena, const std::vector<std::string>* pa
                 }
                 const auto t0 = std::chrono::steady_clock::now();
                 bool good = true;
-                while (good && !stream.eof() && cur->size < window_bytes) good = stream.next(*cur, 2);
+                while (good && !stream.eof() && cur->size < window_bytes) good = stream.next(*cur, per_thread);
                 pipe->inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
                 const bool eof = good && stream.eof();
                 if (first && cur->size && cur->data[0] != '@') good = false;  // FASTA, or not sequence data at all
