@@ -9,7 +9,7 @@
 //
 // Plain (not gzip) four-line FASTQ takes a shorter road, cut into record-aligned blocks that many
 // workers handle at once.  Two ways to take a block, and by default (VG_FASTQ_ROAD=hybrid) both at once, because one
-// is bound by the host cores and the other by PCIe: VG_STRIP_SHARE (default 0.5) of the blocks are stripped, the rest
+// is bound by the host cores and the other by PCIe: VG_STRIP_SHARE (default 0.65) of the blocks are stripped, the rest
 // go to the device as raw text, in one submission order, so the pipeline runs at the sum of the two rates.
 //   strip            the workers scan the memory-mapped file with vector compares (64 bytes per step), check every
 //                    record against what kseq reads as a four-line record, and copy only the sequences into the
@@ -487,7 +487,7 @@ double strip_share(bool multi) {
     if (multi || r == kStrip) return 1.0;  // several GPUs: host only (the device road's per-file state lives on ONE device)
     if (r == kDevice) return 0.0;
     const char* e = getenv("VG_STRIP_SHARE");
-    const double v = e ? atof(e) : 0.5;
+    const double v = e ? atof(e) : 0.65;
     return v < 0 ? 0 : (v > 1 ? 1 : v);
 }
 bool raw_enabled() { return fastq_road() != kKseq; }
