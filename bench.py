@@ -817,14 +817,19 @@ def measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist, want_fil
         lines_np = lines_host.numpy()
         r = reference_run(a.cpu_sample_reads, sample_keys_np, lines_np, steps=1, warmup=0, want_counts=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-    if want_cpu and not a.no_cpu_baseline and not sharded:
+    if want_cpu and not a.no_cpu_baseline:
         # the same reads through the CUDA path must give the reference's counts exactly (rank 0 checks; with N > 1
-        # the other ranks submit nothing and the reduce is part of what is checked)
+        # the other ranks submit nothing and the reduce -- or, for a sharded index, the k-mer exchange -- is part of what
+        # is checked)
         nr = min(a.cpu_sample_reads, host_bytes // rec)
+        barrier()  # rank 0 comes from the CPU run: the library's own barriers give a peer 20 s
         ix.begin()
         if rank == 0:
             ix.submit_ptr(lines_host.data_ptr(), nr * rec)
-        if replica:
+        if sharded:
+            ix.flush()  # collective: one round
+            mine, mp, _ = ix.end()  # collective: the counts of all keys, in key order
+        elif replica:
             mine = comm.allreduce_counts(ix, want_host=True)
             mp = ix.end(want_counts=False)[1]
         elif world > 1:
@@ -955,7 +960,7 @@ def main() -> None:
 
     big = L > 512_000_000
     line = measure(a, w, steps, warmup, rank, world, local, dist, capi, vdist,
-                   want_files_e2e=not a.no_files_e2e and not big, want_gz_e2e=not a.no_gz_e2e, want_cpu=(world == 1 or big),
+                   want_files_e2e=not a.no_files_e2e and not big, want_gz_e2e=not a.no_gz_e2e, want_cpu=(world == 1 or big or a.index == "sharded"),
                    staged_cap_bytes=(2 << 30) if big else None)
     if line is not None:
         line["config"]["host_binding"] = numa
