@@ -300,6 +300,30 @@ def test_partitioned_matches_oracle(ctx, vglib, oracle, force_partition, k):
     ix.close()
 
 
+@pytest.mark.parametrize("k", [27, 21, 28, 22, 12])
+def test_span8_prefilter_matches_oracle(ctx, vglib, oracle, force_partition, monkeypatch, k):
+    """The pre-filter of a huge index: (k - 7)-mers, one lookup per eight read positions (VG_PREFILTER_SPAN=8), for the
+    odd-k and the even-k encoder; with and without the two-level partitions that go with it at that size."""
+    monkeypatch.setenv("VG_PREFILTER_SPAN", "8")
+    g = synth.make_genome(120_000, seed=k + 300)
+    lines = synth.random_reads_lines(5000, 150, g, seed=k + 301)
+    pos = oracle.positions(g[:50_000], k)
+    keys = np.unique(pos[pos != NOKMER])
+    want, wpos, whits = oracle.count_lines(keys, lines, k)
+    for two_level in (False, True):
+        force_partition(slice_bytes=2048 if two_level else 16384)
+        if two_level:
+            monkeypatch.setenv("VG_TWO_LEVEL_FROM", "8")
+        ix = vglib.Index(ctx, keys, k)
+        assert ix.partitions >= 8 and (ix.slices > ix.partitions) == two_level
+        ix.begin()
+        ix.submit(lines)
+        counts, positions, hits = ix.end()
+        assert (positions, hits) == (wpos, whits) and np.array_equal(counts, want), (k, two_level)
+        assert 0 < ix.keys_scattered < positions  # the filter is there and lets the hits through
+        ix.close()
+
+
 @pytest.mark.parametrize("k,ahead", [(27, "0"), (21, "1"), (28, "1")])
 def test_two_level_scatter_matches_oracle(ctx, vglib, oracle, force_partition, monkeypatch, k, ahead):
     """Many slices: the scatter bins by coarse partition, the sweep re-scatters each coarse list into its slices

@@ -760,7 +760,8 @@ static int index_create_sharded(vg_comm* cm, const uint64_t* keys, bool keys_on_
     if (nwords) {
         ps.filter.words = ps.d_filter;
         ps.filter.nwords = nwords;
-        vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
+        ps.filter.span = fspan;  // the scatter must ask with the word length the filter was built with
+        if ((size_t)nwords * 4 <= (64ull << 20)) vg::pin_in_l2(c, ps.d_filter, (size_t)nwords * 4);
     }
     ps.enabled = true;
 #undef CUB
