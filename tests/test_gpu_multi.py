@@ -118,7 +118,7 @@ def test_two_ranks_sharded_index_matches_oracle(tmp_path, oracle, skewed, scenar
     env = {"VG_SLICE_BYTES": "16384", "VG_PART_SLACK": "64"}
     if scenario.endswith("+huge"):
         scenario = scenario[:-5]
-        env.update({"VG_PREFILTER_SPAN": "8", "VG_SLICE_BYTES": "2048", "VG_TWO_LEVEL_FROM": "8"})
+        env.update({"VG_PREFILTER_SPAN": "8", "VG_SLICE_BYTES": "2048", "VG_TWO_LEVEL_FROM": "8", "VG_SHARD_PIECE": "5000"})
     if skewed:  # identical reads overflow the owner's key list: those keys are probed in the peer's table
         env["VG_PART_SLACK"] = "0"
         lines = np.concatenate([np.tile(_read_of(g, 2000), 700), lines[: 151 * 800], np.tile(_read_of(g, 7000), 254)])

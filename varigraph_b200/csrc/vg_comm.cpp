@@ -651,7 +651,8 @@ static int index_create_sharded(vg_comm* cm, const uint64_t* keys, bool keys_on_
     }
 
     // ---- keys: pass 0 counts this rank's own keys, pass 1 keeps them (with their caller positions) ----
-    const uint64_t piece = 1ull << 22;
+    uint64_t piece = 1ull << 22;
+    if (const char* e = getenv("VG_SHARD_PIECE")) piece = std::max<uint64_t>(64, strtoull(e, nullptr, 10));  // (tests: many pieces)
     std::vector<uint64_t> tmp(keys_on_device ? 0 : (size_t)std::min<uint64_t>(piece, std::max<uint64_t>(n, 1)));
     uint64_t* d_piece = nullptr;
     unsigned long long* d_n_own = nullptr;
