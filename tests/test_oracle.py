@@ -213,3 +213,77 @@ def test_fastq_parser_vs_reference_random_damage(oracle, reference, tmp_path):
         assert checked >= 30
     finally:
         reference.graph_destroy(h)
+
+
+def test_even_k_closed_form_rule(oracle):
+    """The rule the even-k window encoder rests on (varigraph_b200/csrc/vg_device.cuh, EvenEncoder), checked against the
+    state machine (src/kmer.cpp:126-146) without a GPU: outside the reach of a palindrome of the registers spliced over
+    an ambiguous byte (its 16-byte segment and the four behind it) and of a clean palindrome (its segment and the two
+    behind it), position i emits iff the k bytes ending at i are valid and do not read the same on both strands."""
+    import random
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rng = random.Random(7)
+    for k in (4, 8, 12, 16, 20, 28):
+        checked = 0
+        for trial in range(60):
+            parts = []
+            for _ in range(rng.randint(1, 6)):
+                n = rng.randint(0, 150)
+                mode = rng.random()
+                if mode < 0.3:
+                    s = [rng.choice("AT") for _ in range(n)]
+                elif mode < 0.4:
+                    s = list(("AT" * n)[:n])
+                else:
+                    s = [rng.choice("ACGT") for _ in range(n)]
+                for j in range(len(s)):
+                    if rng.random() < 0.01:
+                        s[j] = rng.choice("NnX")
+                parts.append("".join(s))
+            text = "\n".join(parts) + "\n"
+            n = len(text)
+            pos = oracle.positions(text.encode(), k)
+            truth = {i for i in range(n) if pos[i] != helpers.NOKMER}
+            valid = [c in comp for c in text]
+            hard = [c == "\n" for c in text]
+
+            def V(i):
+                return 0 <= i < n and valid[i]
+
+            def allk(i):
+                return all(V(j) for j in range(i - k + 1, i + 1))
+
+            def ispal(w):
+                return all(w[d] == comp[w[k - 1 - d]] for d in range(k // 2))
+
+            nseg = (n + 15) // 16
+            stale, clean = [False] * nseg, [False] * nseg
+            for sg in range(nseg):
+                for t in range(sg * 16, min(sg * 16 + 16, n)):
+                    if not V(t):
+                        continue
+                    if allk(t):
+                        clean[sg] |= ispal(text[t - k + 1: t + 1])
+                        continue
+                    b = t - 1
+                    while V(b):
+                        b -= 1
+                    if b < 0 or hard[b]:
+                        continue  # registers zeroed there: still filling up, never equal
+                    need = k - (t - b)
+                    a = b - 1
+                    while a >= b - need and V(a):
+                        a -= 1
+                    if a >= b - need:  # another invalid byte inside the spliced window
+                        if a >= 0 and not hard[a]:
+                            stale[sg] = True  # a second ambiguous byte: not worked out, the lane takes the state machine
+                        continue
+                    stale[sg] |= ispal(text[b - need: b] + text[b + 1: t + 1])
+            for sg in range(nseg):
+                if any(stale[max(0, sg - 4): sg + 1]) or any(clean[max(0, sg - 2): sg + 1]):
+                    continue  # these lanes run the state machine itself
+                for i in range(sg * 16, min(sg * 16 + 16, n)):
+                    want = allk(i) and not ispal(text[i - k + 1: i + 1])
+                    assert want == (i in truth), (k, trial, i)
+                    checked += 1
+        assert checked > (2000 if k >= 12 else 100), (k, checked)  # (small k: nearly every lane has a palindrome in reach)
