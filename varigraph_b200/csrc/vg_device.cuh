@@ -693,11 +693,15 @@ __device__ inline uint32_t encode_keys_any(const Chunk& c, int64_t off, const Km
 //     is >= k whenever the k bytes ending at i are valid.  Hence emit(i) = all_k(i) && !palindrome(i): no look-back at all.
 //   * After an ambiguous base the stale registers CAN be equal during the next k - 1 bases, each time delaying the first
 //     emission by one; only then do palindromes further on matter as well.
-// So a lane takes the closed form unless an ambiguous (non-newline) byte lies within 64 bytes in front of its segment
-// or inside it, or a palindrome lies within 32 -- then it runs the exact state machine (exact_emit_mask) for its own 16
-// positions.  With neither in sight the 2k - 1 bytes ending at an emitting position are valid or cut by a newline,
-// and k clean non-palindromic windows in a row saturate the run length whatever came before.
-// Checked against the state machine in tests/test_gpu_parity.py (random text dense in palindromes, N and newlines).
+// So a lane takes the closed form unless (a) a position fewer than k bases behind an ambiguous byte has registers --
+// the bases on both sides of that byte, spliced -- that read the same on both strands, and that position lies in the
+// lane's own segment or the four in front of it (stale_palindrome: the byte is cut out of the lane's 96-bit view and the
+// windows are tested slot-parallel; only run in warps that have such a byte in sight), or (b) a clean palindrome lies
+// in its own segment or the two in front of it.  Then it runs the exact state machine (exact_emit_mask) for its own 16
+// positions.  With neither, the 2k - 1 bytes ending at an emitting position are valid or cut by a newline, and k clean
+// non-palindromic windows in a row saturate the run length whatever came before.
+// The rule itself is pinned without a GPU (tests/test_oracle.py::test_even_k_closed_form_rule), the kernels against the
+// state machine in tests/test_gpu_parity.py (text dense in palindromes, tandem repeats, N and newlines).
 
 // exact emit mask of the 16 positions of a segment (bit 15 - j = position j): encode_keys_any without the keys
 __device__ __noinline__ uint32_t exact_emit_mask(const Chunk& c, int64_t off, const KmerParams& kp, const uint8_t* lut) {
