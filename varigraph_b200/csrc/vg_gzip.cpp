@@ -270,6 +270,22 @@ bool plausible_block_start(const uint8_t* data, uint64_t size, uint64_t bit, Tab
         w >>= (bit & 7u);
         if (((w >> 1) & 3u) != 2u) return false;
         if (((w >> 3) & 31u) > 29u || ((w >> 8) & 31u) > 29u) return false;
+        // the code-length code must be complete (Kraft sum exactly 1): 3 bits per length straight from the bytes; of
+        // the candidates that get this far, some 99 % stop here, before any table is built
+        if (byte + 12 > size) return false;
+        uint64_t lo, hi = 0;
+        memcpy(&lo, data + byte, 8);
+        memcpy(&hi, data + byte + 8, 4);
+        const unsigned sh = (unsigned)(bit & 7u) + 13u;  // 3 block bits + HLIT 5 + HDIST 5
+        const uint64_t bits = (lo >> sh) | (hi << (64u - sh));  // >= 61 valid bits: HCLEN (4) + up to 19 x 3
+        const uint32_t hclen = (uint32_t)(bits & 15u) + 4u;
+        uint32_t kraft = 0;  // in units of 2^-7
+        uint64_t rest = bits >> 4;
+        for (uint32_t i = 0; i < hclen; ++i, rest >>= 3) {
+            const uint32_t l = (uint32_t)(rest & 7u);
+            if (l) kraft += 128u >> l;
+        }
+        if (kraft != 128u) return false;
     }
     Bits b{data, size, 0, 0, 0};
     b.seek(bit);
