@@ -259,3 +259,45 @@ def test_crc32_matches_zlib(vglib):
         b = r.randbytes(n)
         for init in (0, 0x12345678):
             assert vglib.lib.vg_crc32(init, b, n) == zlib.crc32(b, init), (n, init)
+
+
+def test_parallel_gunzip_fuzz(vglib, tmp_path):
+    """Random payloads (text-like, low-entropy, binary, mixtures), every zlib strategy (default, filtered, Huffman only,
+    RLE, fixed codes -- the last three leave no or few dynamic blocks to search for), levels 0-9, small windows, one or
+    several members, sync flushes at random places; chunk sizes down to 1 KiB.  The bytes must be zlib's."""
+    import random
+    import zlib
+    rng = random.Random(20261017)
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+
+    def payload(n):
+        kind = rng.random()
+        if kind < 0.4:
+            return _fastq_text(max(1, n // 330), rng.randrange(1 << 30))[:n]
+        if kind < 0.55:
+            return bytes(rng.choice(b"ACGT\n") for _ in range(n))
+        if kind < 0.7:
+            return bytes([rng.choice(b"AN")]) * n
+        if kind < 0.85:
+            return rng.randbytes(n)
+        return b"".join(rng.choice([b"@read\n", b"ACGTACGT", b"+\n", b"FFFF:FFF\n", rng.randbytes(5)]) for _ in range(n // 6))
+
+    for trial in range(60):
+        raw_parts, gz = [], b""
+        for _ in range(rng.choice([1, 1, 2, 5])):
+            data = payload(rng.choice([0, 1, 200, 5000, 70_000, 300_000]))
+            co = zlib.compressobj(rng.randrange(0, 10), zlib.DEFLATED, 16 + rng.choice([9, 12, 15]), rng.randrange(1, 10),
+                                  rng.choice(strategies))
+            cut = sorted(rng.randrange(0, len(data) + 1) for _ in range(rng.choice([0, 0, 1, 3])))
+            prev = 0
+            for c in cut:
+                gz += co.compress(data[prev:c]) + co.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))
+                prev = c
+            gz += co.compress(data[prev:]) + co.flush()
+            raw_parts.append(data)
+        raw = b"".join(raw_parts)
+        path = tmp_path / ("fuzz%d.gz" % trial)
+        path.write_bytes(gz)
+        for threads, chunk in ((rng.choice([1, 2, 5, 8]), rng.choice([1024, 4096, 30_000, 1 << 20])) for _ in range(2)):
+            rc, got = _gunzip(vglib, path, threads, chunk)
+            assert rc == 0 and got == raw, (trial, threads, chunk, rc, len(raw))
