@@ -876,7 +876,7 @@ static int count_gz_files(const Sinks& sinks, const std::vector<std::string>& pa
     pipe.stopped.assign(paths.size(), 0);
     for (auto& b : arena.bufs) pipe.free_bufs.push_back(&b);
     std::thread producer(gz_producer, &pipe, &arena, &paths, threads, chunk, window_bytes,
-                         std::max<uint64_t>(1u << 20, ctx->chunk_bytes / 4), debug);
+                         std::min<uint64_t>(1u << 20, ctx->chunk_bytes / 4), debug);
     double t_count = 0;
     int rc = VG_OK;
     for (;;) {
